@@ -1,0 +1,191 @@
+"""Seeded synthetic scenes and cameras of the shapes BASELINE.json names.
+
+Camera conventions restate the reference exactly:
+  * `world_view_transform = getWorld2View2(R, T).T`            gs-simp/scene/cameras.py:60,
+                                                               utils/graphics_utils.py:38-49
+  * `projection_matrix = getProjectionMatrix(0.01, 100, ..).T`  cameras.py:54-55,61; graphics_utils.py:51-70
+  * `full_proj_transform = world_view_transform @ projection_matrix`          cameras.py:62
+  * `camera_center = world_view_transform.inverse()[3, :3]`                    cameras.py:63
+Gaussian parameters are produced post-activation, i.e. what GaussianModel's getters hand to the
+rasterizer (gs-simp/scene/gaussian_model.py:95-118): scales = exp(.), opacity = sigmoid(.),
+rotations normalised, SH `(P, M, 3)` coefficient-major.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+ZNEAR, ZFAR = 0.01, 100.0  # cameras.py:54-55
+
+
+@dataclass
+class Camera:
+    """The attributes render() reads from a viewpoint camera (gaussian_renderer/__init__.py:33-46)."""
+    image_width: int
+    image_height: int
+    FoVx: float
+    FoVy: float
+    world_view_transform: torch.Tensor  # (4,4) column-major W2C  (== W2C^T)
+    full_proj_transform: torch.Tensor   # (4,4) column-major P*W2C
+    camera_center: torch.Tensor         # (3,)
+
+    @property
+    def tanfovx(self):
+        return math.tan(self.FoVx * 0.5)
+
+    @property
+    def tanfovy(self):
+        return math.tan(self.FoVy * 0.5)
+
+    def to(self, device):
+        return Camera(self.image_width, self.image_height, self.FoVx, self.FoVy,
+                      self.world_view_transform.to(device), self.full_proj_transform.to(device),
+                      self.camera_center.to(device))
+
+
+def projection_matrix(znear, zfar, fovX, fovY) -> torch.Tensor:
+    """graphics_utils.py:51-70 (z_sign = +1)."""
+    tanHalfFovY = math.tan(fovY / 2)
+    tanHalfFovX = math.tan(fovX / 2)
+    top, right = tanHalfFovY * znear, tanHalfFovX * znear
+    bottom, left = -top, -right
+    Pm = torch.zeros(4, 4)
+    Pm[0, 0] = 2.0 * znear / (right - left)
+    Pm[1, 1] = 2.0 * znear / (top - bottom)
+    Pm[0, 2] = (right + left) / (right - left)
+    Pm[1, 2] = (top + bottom) / (top - bottom)
+    Pm[3, 2] = 1.0
+    Pm[2, 2] = zfar / (zfar - znear)
+    Pm[2, 3] = -(zfar * znear) / (zfar - znear)
+    return Pm
+
+
+def world2view(R: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """graphics_utils.py:38-49 with translate=0, scale=1 (R is camera-to-world rotation)."""
+    Rt = np.zeros((4, 4))
+    Rt[:3, :3] = R.transpose()
+    Rt[:3, 3] = t
+    Rt[3, 3] = 1.0
+    C2W = np.linalg.inv(Rt)
+    Rt = np.linalg.inv(C2W)
+    return np.float32(Rt)
+
+
+def make_camera(W: int, H: int, focal: float | None = None, R: np.ndarray | None = None,
+                T: np.ndarray | None = None) -> Camera:
+    focal = 1.1 * W if focal is None else focal
+    fovx = 2 * math.atan(W / (2 * focal))  # graphics_utils.py:75-76
+    fovy = 2 * math.atan(H / (2 * focal))
+    R = np.eye(3) if R is None else R
+    T = np.zeros(3) if T is None else T
+    wvt = torch.tensor(world2view(R, T)).transpose(0, 1).contiguous()
+    proj = projection_matrix(ZNEAR, ZFAR, fovx, fovy).transpose(0, 1)
+    full = wvt.unsqueeze(0).bmm(proj.unsqueeze(0)).squeeze(0).contiguous()
+    center = wvt.inverse()[3, :3]  # a row-slice view with storage offset, as in the reference
+    return Camera(W, H, fovx, fovy, wvt, full, center)
+
+
+def orbit_cameras(n: int, W: int, H: int, center=(0.0, 0.0, 6.5), max_deg: float = 30.0,
+                  focal: float | None = None) -> list[Camera]:
+    """n cameras on a +-max_deg yaw orbit about `center`, all looking at it from the distance of the
+    origin camera -- the shape of Scene.getSeqCameras (gs-simp/scene/__init__.py:160-176)."""
+    cams = []
+    c = np.asarray(center, dtype=np.float64)
+    dist = np.linalg.norm(c)
+    for k in range(n):
+        a = math.radians(-max_deg + 2 * max_deg * (k / max(n - 1, 1)))
+        # camera position: rotate the origin about `center` around the y axis
+        pos = c + np.array([-math.sin(a) * dist, 0.0, -math.cos(a) * dist])
+        fwd = (c - pos) / np.linalg.norm(c - pos)
+        up = np.array([0.0, 1.0, 0.0])
+        right = np.cross(up, fwd)
+        right /= np.linalg.norm(right)
+        up2 = np.cross(fwd, right)
+        R_c2w = np.stack([right, up2, fwd], axis=1)  # columns = camera axes in world
+        T = -R_c2w.T @ pos                            # W2C translation
+        cams.append(make_camera(W, H, focal, R_c2w, T))
+    return cams
+
+
+def default_mu_s(W: int, median_radius_px: float = 4.0, focal: float | None = None) -> float:
+    """log-scale mean such that the median screen radius ceil(3 sigma) is ~median_radius_px at the
+    median depth (6.5) of the slab; max over 3 lognormal(., 0.6) axes has median ~exp(mu + 0.5)."""
+    focal = 1.1 * W if focal is None else focal
+    sigma_px = max(((median_radius_px - 0.5) / 3.0) ** 2 - 0.3, 0.05) ** 0.5
+    return math.log(sigma_px * 6.5 / focal) - 0.5
+
+
+def make_scene(P: int, W: int, H: int, sh_degree: int, seed: int, *, max_sh_degree: int | None = None,
+               mu_s: float | None = None, sigma_s: float = 0.6, axis_ratio: float | None = None,
+               focal: float | None = None, device="cpu") -> dict:
+    """SURVEY 8d generator.  Returns post-activation tensors + the origin camera."""
+    g = torch.Generator().manual_seed(seed)
+    cam = make_camera(W, H, focal)
+    max_sh_degree = sh_degree if max_sh_degree is None else max_sh_degree
+    M = (max_sh_degree + 1) ** 2
+    n_cube = int(0.15 * P)
+    n_fr = P - n_cube
+    z = 1.0 + 11.0 * torch.rand(n_fr, generator=g)
+    x = (2 * torch.rand(n_fr, generator=g) - 1) * 1.2 * cam.tanfovx * z
+    y = (2 * torch.rand(n_fr, generator=g) - 1) * 1.2 * cam.tanfovy * z
+    fr = torch.stack([x, y, z], 1)
+    cube = (2 * torch.rand(n_cube, 3, generator=g) - 1) * 2.0
+    means3D = torch.cat([fr, cube], 0)[torch.randperm(P, generator=g)].contiguous()
+    mu = default_mu_s(W, focal=focal) if mu_s is None else mu_s
+    log_s = mu + sigma_s * torch.randn(P, 3, generator=g)
+    if axis_ratio is not None:  # stress config: stretch one axis by up to `axis_ratio`
+        stretch = torch.rand(P, generator=g) * math.log(axis_ratio)
+        log_s[:, 0] += stretch
+    scales = torch.exp(log_s)
+    rotations = torch.nn.functional.normalize(torch.randn(P, 4, generator=g))
+    opacities = torch.sigmoid(2.0 * torch.randn(P, 1, generator=g))
+    shs = torch.empty(P, M, 3)
+    shs[:, :1] = 0.5 * torch.randn(P, 1, 3, generator=g)
+    if M > 1:
+        shs[:, 1:] = 0.1 * torch.randn(P, M - 1, 3, generator=g)
+    scene = dict(means3D=means3D, scales=scales, rotations=rotations, opacities=opacities, shs=shs,
+                 sh_degree=sh_degree, bg=torch.zeros(3), camera=cam, W=W, H=H, P=P, M=M, seed=seed)
+    if device != "cpu":
+        scene = scene_to(scene, device)
+    return scene
+
+
+def scene_to(scene: dict, device) -> dict:
+    out = {}
+    for k, v in scene.items():
+        if isinstance(v, torch.Tensor):
+            out[k] = v.to(device)
+        elif isinstance(v, Camera):
+            out[k] = v.to(device)
+        else:
+            out[k] = v
+    return out
+
+
+def loss_weights(W: int, H: int, seed: int) -> torch.Tensor:
+    """Fixed U(0,1) weights; L = sum(color * Wt) makes dL/dcolor dense and deterministic (8d)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.rand(3, H, W, generator=g)
+
+
+# BASELINE.json configs -> concrete inputs
+CONFIGS = {
+    "plumbing":  dict(P=10_000,     W=256,  H=256,  sh_degree=0, seed=1),
+    "mip360":    dict(P=1_000_000,  W=1296, H=928,  sh_degree=3, seed=2),
+    "headline":  dict(P=3_000_000,  W=1600, H=1008, sh_degree=3, seed=6),
+    "svd_orbit": dict(P=3_000_000,  W=1024, H=576,  sh_degree=1, seed=3),
+    "inference": dict(P=6_000_000,  W=1920, H=1080, sh_degree=3, seed=4),
+    "stress":    dict(P=10_000_000, W=3840, H=2160, sh_degree=0, seed=5),
+}
+
+
+def make_config_scene(name: str, device="cpu", scale: float = 1.0) -> dict:
+    """`scale` < 1 shrinks P (same image) for bounded CPU samples."""
+    c = dict(CONFIGS[name])
+    c["P"] = max(1, int(c["P"] * scale))
+    if name == "stress":
+        return make_scene(**c, mu_s=default_mu_s(c["W"], 40.0), axis_ratio=20.0, device=device)
+    return make_scene(**c, device=device)
