@@ -1,0 +1,135 @@
+/*
+ * gsrast_b200.h -- C ABI of the B200-native differentiable Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path of JiuTongBro/MultiView_Inpaint that
+ * BASELINE.json names: the rasterizer behind
+ *     /root/reference/gs-simp/gaussian_renderer/__init__.py:14   (import)
+ *     /root/reference/gs-simp/gaussian_renderer/__init__.py:85-93 (the call)
+ * In the reference that is the third-party `diff_gaussian_rasterization` extension (w-depth fork,
+ * reference README.md:26; source not vendored).  Its pybind module `_C` exposes three functions --
+ * rasterize_gaussians / rasterize_gaussians_backward / mark_visible -- which sit on a plain C++
+ * core `CudaRasterizer::Rasterizer::{forward,backward,markVisible}` taking raw device pointers and
+ * three `std::function<char*(size_t)>` buffer growers.  The entry points
+ * below are that core, as `extern "C"`: plain pointers, sizes and C function pointers, no torch
+ * types.  INTEGRATION.md shows the ctypes / pybind stub a maintainer of the reference would add.
+ *
+ * All pointers are DEVICE pointers unless the name ends in `_host`.  `stream` is a cudaStream_t
+ * passed as void*.  Every function returns 0 on success, a positive cudaError_t value on a CUDA
+ * failure, or one of the negative GSR_E_* codes; gsr_last_error() gives the message.
+ * The library is stateless between calls except for a small per-device cache of pinned staging
+ * memory; calls for one device must not run concurrently from several host threads.
+ */
+#ifndef GSRAST_B200_H
+#define GSRAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_VERSION 1
+
+#define GSR_E_INVALID     (-1) /* bad argument (shape/alignment/null)                            */
+#define GSR_E_PREFILTERED (-2) /* `prefiltered` set but a point was culled (the reference traps) */
+#define GSR_E_ALLOC       (-3) /* a buffer-grower callback returned NULL                         */
+#define GSR_E_OVERFLOW    (-4) /* num_rendered does not fit the 30-bit sort prefix / uint32      */
+
+/* flags for gsr_forward */
+#define GSR_FLAG_BINNING_KEY64 1u /* bin exactly like the reference: one 64-bit (tile|depth) onesweep
+                                     sort (Appendix A.3/A.4).  Default (0) is the two-level scheme:
+                                     depth-sort P Gaussians, emit in depth order, 2-pass tile sort.
+                                     Both produce bit-identical point lists and tile ranges.          */
+#define GSR_FLAG_FAST_EXP      2u /* blend with ex2.approx instead of expf (off = parity build)   */
+
+/* Buffer grower, replaces `std::function<char*(size_t)>` of the reference core: must return a
+ * device allocation of at least `bytes` bytes, 256-byte aligned, that stays alive until the
+ * matching gsr_backward() has run. */
+typedef char* (*gsr_alloc_fn)(void* user, size_t bytes);
+
+/* Replaces CudaRasterizer::Rasterizer::forward (called by rasterize_gaussians, section 8b).
+ * Shapes: means3D (P,3)  shs (P,M,3) or NULL  colors_precomp (P,3) or NULL  opacities (P,)
+ *         scales (P,3) + rotations (P,4)  or  cov3D_precomp (P,6)
+ *         viewmatrix/projmatrix (4,4) as stored by scene/cameras.py:60-62 (column-major),
+ *         cam_pos (3,), background (3,)
+ * Out:    out_color (3,H,W)  out_depth (1,H,W) [median depth, 15.0f where none: gen_seq.py:50]
+ *         radii (P,) int32  *num_rendered_host = number of (tile, Gaussian) instances          */
+int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_alloc_fn binning_alloc,
+                void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
+                const float* background, int width, int height, const float* means3D,
+                const float* shs, const float* colors_precomp, const float* opacities,
+                const float* scales, float scale_modifier, const float* rotations,
+                const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                float* out_color, float* out_depth, int32_t* radii, int64_t* num_rendered_host,
+                uint32_t flags);
+
+/* Replaces CudaRasterizer::Rasterizer::backward (called by rasterize_gaussians_backward).
+ * dL_dpix (3,H,W).  Every output is fully WRITTEN (zeros for culled Gaussians), callers need not
+ * clear them:  dL_dmean2D (P,3) [.z = 0]  dL_dconic (P,4) [x,y,_,w]  dL_dopacity (P,)
+ * dL_dcolor (P,3)  dL_dmean3D (P,3)  dL_dcov3D (P,6)  dL_dsh (P,M,3) or NULL when M == 0
+ * dL_dscale (P,3)  dL_drot (P,4).  No gradient flows through depth.
+ * dL_dconic may be NULL (the reference keeps it internal).  `scratch` is a device buffer of at
+ * least gsr_backward_scratch_bytes(P) bytes (the packed per-Gaussian accumulator the blend
+ * backward reduces into); the reference core needs none because it adds straight into its outputs. */
+size_t gsr_backward_scratch_bytes(int P);
+int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const float* background,
+                 int width, int height, const float* means3D, const float* shs,
+                 const float* colors_precomp, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const int32_t* radii, const char* geom_buffer, const char* binning_buffer,
+                 const char* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                 float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, char* scratch,
+                 size_t scratch_bytes, uint32_t flags);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (mark_visible): present[i] = view z > 0.2 */
+int gsr_mark_visible(void* stream, int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present);
+
+/* ---- building blocks, exported so that parity tests can drive each stage through the C ABI ---- */
+
+/* Stable LSD onesweep radix sort of (key,value) pairs on key bits [0,end_bit), 8-bit digits.
+ * keys_in/vals_in are preserved.  `temp` must hold gsr_sort_temp_bytes(...) bytes. */
+size_t gsr_sort_temp_bytes(int64_t n, int key_bytes /*4 or 8*/, int end_bit);
+int gsr_sort_pairs_u64(void* stream, int64_t n, const uint64_t* keys_in, const uint32_t* vals_in,
+                       uint64_t* keys_out, uint32_t* vals_out, int end_bit, char* temp,
+                       size_t temp_bytes);
+int gsr_sort_pairs_u32(void* stream, int64_t n, const uint32_t* keys_in, const uint32_t* vals_in,
+                       uint32_t* keys_out, uint32_t* vals_out, int end_bit, char* temp,
+                       size_t temp_bytes);
+
+/* Single-pass (decoupled look-back) inclusive prefix sum of uint32; if `gather` is non-NULL the
+ * input element i is in[gather[i]].  `temp` must hold gsr_scan_temp_bytes(n) bytes. */
+size_t gsr_scan_temp_bytes(int64_t n);
+int gsr_inclusive_scan_u32(void* stream, int64_t n, const uint32_t* in, const uint32_t* gather,
+                           uint32_t* out, char* temp, size_t temp_bytes);
+
+/* Byte offsets of the arrays inside the three opaque scratch buffers (for stage-level parity
+ * tests and debuggers; the layout is otherwise private).  Unused entries are set to (size_t)-1. */
+typedef struct {
+  size_t rec;           /* geom: float4[3P]: {x,y,conic.x,conic.y} {conic.z,opacity,hx,hy} {r,g,b,power_cut} */
+  size_t depths;        /* geom: float[P]  view-space z                                     */
+  size_t clamped;       /* geom: uint8[P]  bit c set <=> colour channel c was clamped to 0  */
+  size_t tiles_touched; /* geom: uint32[P]                                                  */
+  size_t point_offsets; /* geom: uint32[P] inclusive scan (index order for KEY64, depth order otherwise) */
+  size_t order;         /* geom: uint32[P] Gaussian ids by ascending depth bits (two-level only)        */
+  size_t geom_bytes;
+  size_t final_T;       /* image: float[H*W]   */
+  size_t n_contrib;     /* image: uint32[H*W]  */
+  size_t ranges;        /* image: uint2[G]     */
+  size_t image_bytes;
+  size_t point_list;    /* binning: uint32[N] sorted Gaussian ids (front of the buffer)    */
+  size_t binning_bytes;
+} gsr_layout;
+int gsr_get_layout(int P, int width, int height, int64_t num_rendered, uint32_t flags, gsr_layout* out);
+
+const char* gsr_last_error(void);
+int gsr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,276 @@
+"""Torch-facing mirror of the reference extension's pybind module `diff_gaussian_rasterization._C`.
+
+Same three entry points, same positional arguments and return tuples as the w-depth fork the
+reference installs (README.md:26 of the reference; signatures in SURVEY.md section 8b):
+
+    rasterize_gaussians(...)           -> (num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer, depth)
+    rasterize_gaussians_backward(...)  -> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D,
+                                           dL_dsh, dL_dscales, dL_drotations)
+    mark_visible(means3D, viewmatrix, projmatrix) -> bool[P]
+
+but implemented over the C ABI of include/gsrast_b200.h (libgsrast_b200.so, hand-written sm_100a
+CUDA) through ctypes.  torch is only used for device memory and the current stream.  There is NO
+CPU or eager fallback: if the library is missing, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgsrast_b200.so")
+
+FLAG_BINNING_KEY64 = 1
+FLAG_FAST_EXP = 2
+#: default kernel flags (see include/gsrast_b200.h); override with GSR_FLAGS=<int>
+DEFAULT_FLAGS = int(os.environ.get("GSR_FLAGS", "0"))
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: the B200 rasterizer has no fallback path. Build it with "
+        "`python -m multiview_inpaint_b200.build` (needs nvcc, sm_100a).")
+
+_lib = C.CDLL(LIB_PATH)
+
+_ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class GsrLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "rec", "depths", "clamped", "tiles_touched", "point_offsets", "order", "geom_bytes",
+        "final_T", "n_contrib", "ranges", "image_bytes", "point_list", "binning_bytes")]
+
+
+_vp, _i, _f, _i64, _u32, _sz = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_uint32, C.c_size_t
+_lib.gsr_last_error.restype = C.c_char_p
+_lib.gsr_version.restype = _i
+_lib.gsr_forward.restype = _i
+_lib.gsr_forward.argtypes = [_vp, _ALLOC_FN, _vp, _ALLOC_FN, _vp, _ALLOC_FN, _vp, _i, _i, _i, _vp, _i, _i,
+                             _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
+                             _vp, _vp, _vp, C.POINTER(_i64), _u32]
+_lib.gsr_backward_scratch_bytes.restype = _sz
+_lib.gsr_backward_scratch_bytes.argtypes = [_i]
+_lib.gsr_backward.restype = _i
+_lib.gsr_backward.argtypes = [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp,
+                              _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _sz, _u32]
+_lib.gsr_mark_visible.restype = _i
+_lib.gsr_mark_visible.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+_lib.gsr_sort_temp_bytes.restype = _sz
+_lib.gsr_sort_temp_bytes.argtypes = [_i64, _i, _i]
+_lib.gsr_sort_pairs_u64.restype = _i
+_lib.gsr_sort_pairs_u64.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _sz]
+_lib.gsr_sort_pairs_u32.restype = _i
+_lib.gsr_sort_pairs_u32.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _sz]
+_lib.gsr_scan_temp_bytes.restype = _sz
+_lib.gsr_scan_temp_bytes.argtypes = [_i64]
+_lib.gsr_inclusive_scan_u32.restype = _i
+_lib.gsr_inclusive_scan_u32.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _sz]
+_lib.gsr_get_layout.restype = _i
+_lib.gsr_get_layout.argtypes = [_i, _i, _i, _i64, _u32, C.POINTER(GsrLayout)]
+
+EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
+                    "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
+                    "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
+                    "gsr_last_error", "gsr_version")
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = _lib.gsr_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def _ptr(t: torch.Tensor | None):
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    """float32, CUDA, contiguous (camera_center is a row-slice view in the reference,
+    scene/cameras.py:63, so contiguity must be enforced here)."""
+    if t.numel() == 0:
+        return t
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (this rasterizer has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _Grower:
+    """The reference's resizeFunctional(): a callback that (re)allocates a uint8 tensor."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cb = _ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        try:
+            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            return self.tensor.data_ptr()
+        except Exception:  # surfaces as GSR_E_ALLOC
+            return 0
+
+
+def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                        cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
+                        image_width, sh, degree, campos, prefiltered, debug=False, flags=None):
+    if means3D.ndim != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    flags = DEFAULT_FLAGS if flags is None else int(flags)
+    P, H, W = means3D.shape[0], int(image_height), int(image_width)
+    dev = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor (this rasterizer has no CPU path)")
+    M = 0
+    if sh.numel() != 0:
+        M = sh.shape[1]
+    with torch.cuda.device(dev):
+        if P == 0:
+            # the reference returns zero-filled outputs and rendered = 0 without launching
+            z = torch.zeros
+            e = torch.empty(0, dtype=torch.uint8, device=dev)
+            return (0, z(3, H, W, device=dev), z(0, dtype=torch.int32, device=dev), e, e.clone(), e.clone(),
+                    z(1, H, W, device=dev))
+        background = _f32c(background, "background")
+        means3D = _f32c(means3D, "means3D")
+        colors, opacity = _f32c(colors, "colors_precomp"), _f32c(opacity, "opacities")
+        scales, rotations = _f32c(scales, "scales"), _f32c(rotations, "rotations")
+        cov3D_precomp, sh = _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(sh, "shs")
+        viewmatrix, projmatrix, campos = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix"), _f32c(campos, "campos")
+        out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+        out_depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+        radii = torch.empty(P, dtype=torch.int32, device=dev)
+        geom, binning, img = _Grower(dev), _Grower(dev), _Grower(dev)
+        n = _i64(0)
+        rc = _lib.gsr_forward(
+            _stream(dev), geom.cb, None, binning.cb, None, img.cb, None, P, int(degree), M,
+            _ptr(background), W, H, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
+            float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
+            _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
+            _ptr(out_color), _ptr(out_depth), _ptr(radii), C.byref(n), flags)
+        _check(rc, "rasterize_gaussians")
+    return int(n.value), out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
+
+
+def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                 cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                 dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                 imageBuffer, debug=False, flags=None, return_conic=False):
+    flags = DEFAULT_FLAGS if flags is None else int(flags)
+    P = means3D.shape[0]
+    H, W = dL_dout_color.shape[1], dL_dout_color.shape[2]
+    dev = means3D.device
+    M = sh.shape[1] if sh.numel() != 0 else 0
+    with torch.cuda.device(dev):
+        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        dL_dmeans3D, dL_dmeans2D, dL_dcolors = e(P, 3), e(P, 3), e(P, 3)
+        dL_dconic, dL_dopacity, dL_dcov3D = e(P, 2, 2), e(P, 1), e(P, 6)
+        dL_dsh, dL_dscales, dL_drotations = e(P, M, 3), e(P, 3), e(P, 4)
+        if P != 0:
+            background = _f32c(background, "background")
+            means3D = _f32c(means3D, "means3D")
+            colors, scales, rotations = _f32c(colors, "colors_precomp"), _f32c(scales, "scales"), _f32c(rotations, "rotations")
+            cov3D_precomp, sh = _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(sh, "shs")
+            viewmatrix, projmatrix, campos = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix"), _f32c(campos, "campos")
+            dL_dout_color = _f32c(dL_dout_color, "dL_dout_color")
+            nscratch = int(_lib.gsr_backward_scratch_bytes(P))
+            scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+            rc = _lib.gsr_backward(
+                _stream(dev), P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh),
+                _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
+                _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL_dout_color),
+                _ptr(dL_dmeans2D), _ptr(dL_dconic), _ptr(dL_dopacity), _ptr(dL_dcolors), _ptr(dL_dmeans3D),
+                _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations), _ptr(scratch),
+                nscratch, flags)
+            _check(rc, "rasterize_gaussians_backward")
+    out = (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)
+    return out + (dL_dconic,) if return_conic else out
+
+
+def mark_visible(means3D, viewmatrix, projmatrix):
+    P = means3D.shape[0]
+    dev = means3D.device
+    present = torch.zeros(P, dtype=torch.bool, device=dev)
+    if P != 0:
+        with torch.cuda.device(dev):
+            means3D, viewmatrix, projmatrix = _f32c(means3D, "means3D"), _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+            _check(_lib.gsr_mark_visible(_stream(dev), P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix),
+                                         present.data_ptr()), "mark_visible")
+    return present
+
+
+# ---- stage-level access for parity tests (not part of the reference's _C surface) ----------------
+
+def get_layout(P, W, H, num_rendered, flags=None) -> GsrLayout:
+    flags = DEFAULT_FLAGS if flags is None else int(flags)
+    lay = GsrLayout()
+    _check(_lib.gsr_get_layout(int(P), int(W), int(H), int(num_rendered), flags, C.byref(lay)), "gsr_get_layout")
+    return lay
+
+
+def _view(buf: torch.Tensor, off: int, count: int, dtype) -> torch.Tensor:
+    nbytes = count * torch.empty(0, dtype=dtype).element_size()
+    return buf[off:off + nbytes].view(dtype)
+
+
+def unpack_state(P, W, H, num_rendered, geomBuffer, binningBuffer, imgBuffer, flags=None) -> dict:
+    """Typed views of the opaque buffers (Appendix A.8 names)."""
+    lay = get_layout(P, W, H, num_rendered, flags)
+    G = ((W + 15) // 16) * ((H + 15) // 16)
+    rec = _view(geomBuffer, lay.rec, 12 * P, torch.float32).view(P, 12)
+    out = dict(
+        means2D=rec[:, 0:2], conic_opacity=torch.stack([rec[:, 2], rec[:, 3], rec[:, 4], rec[:, 5]], 1),
+        rgb=rec[:, 8:11], cull=torch.stack([rec[:, 6], rec[:, 7], rec[:, 11]], 1),
+        depths=_view(geomBuffer, lay.depths, P, torch.float32),
+        clamped=_view(geomBuffer, lay.clamped, P, torch.uint8),
+        tiles_touched=_view(geomBuffer, lay.tiles_touched, P, torch.int32),
+        point_offsets=_view(geomBuffer, lay.point_offsets, P, torch.int32),
+        final_T=_view(imgBuffer, lay.final_T, H * W, torch.float32).view(H, W),
+        n_contrib=_view(imgBuffer, lay.n_contrib, H * W, torch.int32).view(H, W),
+        ranges=_view(imgBuffer, lay.ranges, 2 * G, torch.int32).view(G, 2),
+        point_list=_view(binningBuffer, lay.point_list, num_rendered, torch.int32),
+    )
+    if lay.order != C.c_size_t(-1).value:
+        out["order"] = _view(geomBuffer, lay.order, P, torch.int32)
+    return out
+
+
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, end_bit: int):
+    """gsr_sort_pairs_u64 / _u32.  keys: int64 (bit pattern of u64) or int32 (u32); vals int32."""
+    n = keys.numel()
+    dev = keys.device
+    kb = 8 if keys.dtype == torch.int64 else 4
+    keys_out, vals_out = torch.empty_like(keys), torch.empty_like(vals)
+    with torch.cuda.device(dev):
+        nt = int(_lib.gsr_sort_temp_bytes(n, kb, end_bit))
+        temp = torch.empty(nt, dtype=torch.uint8, device=dev)
+        fn = _lib.gsr_sort_pairs_u64 if kb == 8 else _lib.gsr_sort_pairs_u32
+        _check(fn(_stream(dev), n, _ptr(keys), _ptr(vals), _ptr(keys_out), _ptr(vals_out), int(end_bit),
+                  _ptr(temp), nt), "sort_pairs")
+    return keys_out, vals_out
+
+
+def inclusive_scan(x: torch.Tensor, gather: torch.Tensor | None = None) -> torch.Tensor:
+    n = x.numel() if gather is None else gather.numel()
+    dev = x.device
+    out = torch.empty(n, dtype=x.dtype, device=dev)
+    with torch.cuda.device(dev):
+        nt = int(_lib.gsr_scan_temp_bytes(n))
+        temp = torch.empty(max(nt, 1), dtype=torch.uint8, device=dev)
+        _check(_lib.gsr_inclusive_scan_u32(_stream(dev), n, _ptr(x), _ptr(gather), _ptr(out), _ptr(temp), nt),
+               "inclusive_scan")
+    return out

@@ -1,0 +1,392 @@
+// api.cu -- the extern "C" boundary declared in include/gsrast_b200.h.
+//
+// gsr_forward / gsr_backward / gsr_mark_visible stand where the reference's
+// CudaRasterizer::Rasterizer::{forward,backward,markVisible} stand, driven
+// by rasterize_gaussians / rasterize_gaussians_backward / mark_visible, which
+// /root/reference/gs-simp/gaussian_renderer/__init__.py:85-93 reaches through
+// GaussianRasterizer.forward.  Kernel order per view:
+//   forward : K1 preprocess -> [depth sort] -> K2 scan -> (N to host) -> K3 duplicate -> K4 sort
+//             -> K5 ranges -> K6 blend
+//   backward: K7 blend backward -> K8+K9 per-Gaussian backward
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+
+namespace gsr {
+
+static thread_local std::string g_last_error;
+void set_error(const char* msg) { g_last_error = msg; }
+
+static int fail_cuda(cudaError_t e, const char* where) {
+  g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+static int fail(int code, const char* msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define GSR_CUDA(expr, where)                         \
+  do {                                                \
+    cudaError_t _e = (expr);                          \
+    if (_e != cudaSuccess) return fail_cuda(_e, where); \
+  } while (0)
+
+static bool key64(uint32_t flags) { return (flags & GSR_FLAG_BINNING_KEY64) != 0; }
+
+GeomLayout geom_layout(int P, uint32_t flags) {
+  GeomLayout L{};
+  size_t off = 0;
+  const size_t n = (size_t)(P > 0 ? P : 1);
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  L.rec = take(n * 48);
+  L.depths = take(n * 4);
+  L.clamped = take(n);
+  L.tiles_touched = take(n * 4);
+  L.point_offsets = take(n * 4);
+  L.status = take(16);
+  L.temp_bytes = scan_temp_bytes(P);
+  if (!key64(flags)) {
+    L.depth_keys = take(n * 4);
+    L.order = take(n * 4);
+    L.depth_keys_alt = take(n * 4);
+    L.order_alt = take(n * 4);
+    const size_t st = sort_temp_bytes(P, 4, 32);
+    if (st > L.temp_bytes) L.temp_bytes = st;
+  } else {
+    L.depth_keys = L.order = L.depth_keys_alt = L.order_alt = (size_t)-1;
+  }
+  L.temp = take(L.temp_bytes);
+  L.bytes = off;
+  return L;
+}
+
+ImageLayout image_layout(int W, int H) {
+  ImageLayout L{};
+  size_t off = 0;
+  const size_t hw = (size_t)W * H;
+  const size_t G = (size_t)cdiv(W, TILE_X) * cdiv(H, TILE_Y);
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  L.final_T = take(hw * 4);
+  L.n_contrib = take(hw * 4);
+  L.ranges = take((G > 0 ? G : 1) * 8);
+  L.bytes = off;
+  return L;
+}
+
+static int tile_bits(int W, int H) {
+  const uint32_t G = (uint32_t)cdiv(W, TILE_X) * (uint32_t)cdiv(H, TILE_Y);
+  int b = ceil_log2(G);
+  return b < 1 ? 1 : b;
+}
+static int key64_end_bit(int W, int H) {
+  const uint32_t G = (uint32_t)cdiv(W, TILE_X) * (uint32_t)cdiv(H, TILE_Y);
+  return 32 + (int)higher_msb(G);  // exactly the reference's bit range (Appendix A.4)
+}
+
+BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags) {
+  BinningLayout L{};
+  size_t off = 0;
+  const size_t n = (size_t)(N > 0 ? N : 1);
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const bool k64 = key64(flags);
+  const int end_bit = k64 ? key64_end_bit(W, H) : tile_bits(W, H);
+  const int passes = (end_bit + 7) / 8;
+  const size_t kb = k64 ? 8 : 4;
+  // buffers a (emitted into) and b; the sorted result lands in b for odd pass counts, a for even
+  const size_t va = take(n * 4), vb = take(n * 4);
+  L.keys_a = take(n * kb);
+  L.keys_b = take(n * kb);
+  L.point_list = (passes & 1) ? vb : va;
+  L.vals_alt = (passes & 1) ? va : vb;
+  L.temp_bytes = sort_temp_bytes(N, (int)kb, end_bit);
+  L.temp = take(L.temp_bytes);
+  L.bytes = off;
+  return L;
+}
+
+static Camera make_camera(int W, int H, const float* view_d, const float* proj_d, const float* campos_d,
+                          float tan_fovx, float tan_fovy, float scale_modifier) {
+  Camera c;
+  c.view = view_d;
+  c.proj = proj_d;
+  c.campos = campos_d;
+  c.focal_y = H / (2.0f * tan_fovy);
+  c.focal_x = W / (2.0f * tan_fovx);
+  c.tan_fovx = tan_fovx;
+  c.tan_fovy = tan_fovy;
+  c.scale_modifier = scale_modifier;
+  c.W = W;
+  c.H = H;
+  c.grid_x = cdiv(W, TILE_X);
+  c.grid_y = cdiv(H, TILE_Y);
+  return c;
+}
+
+// pinned host staging for the one value that must reach the host per view: N (+ the trap flag)
+struct Pinned {
+  int64_t* result = nullptr;  // 2 x int64
+};
+static Pinned& pinned() {
+  static thread_local Pinned p;
+  if (!p.result) {
+    void* ptr = nullptr;
+    if (cudaMallocHost(&ptr, 64) == cudaSuccess) p.result = reinterpret_cast<int64_t*>(ptr);
+  }
+  return p;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+const char* gsr_last_error(void) { return g_last_error.c_str(); }
+int gsr_version(void) { return GSR_VERSION; }
+
+size_t gsr_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * 48); }
+size_t gsr_sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
+  // internal temp + alternate key/value buffers (inputs are preserved by the public entry points)
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  return sort_temp_bytes(n, key_bytes, end_bit) + align_up(nn * key_bytes) + align_up(nn * 4);
+}
+size_t gsr_scan_temp_bytes(int64_t n) { return scan_temp_bytes(n); }
+
+int gsr_get_layout(int P, int width, int height, int64_t num_rendered, uint32_t flags, gsr_layout* out) {
+  if (!out || P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail(GSR_E_INVALID, "gsr_get_layout: bad argument");
+  const GeomLayout g = geom_layout(P, flags);
+  const ImageLayout im = image_layout(width, height);
+  const BinningLayout b = binning_layout(num_rendered, width, height, flags);
+  out->rec = g.rec;
+  out->depths = g.depths;
+  out->clamped = g.clamped;
+  out->tiles_touched = g.tiles_touched;
+  out->point_offsets = g.point_offsets;
+  out->order = g.order;
+  out->geom_bytes = g.bytes;
+  out->final_T = im.final_T;
+  out->n_contrib = im.n_contrib;
+  out->ranges = im.ranges;
+  out->image_bytes = im.bytes;
+  out->point_list = b.point_list;
+  out->binning_bytes = b.bytes;
+  return 0;
+}
+
+int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_alloc_fn binning_alloc,
+                void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
+                const float* background, int width, int height, const float* means3D,
+                const float* shs, const float* colors_precomp, const float* opacities,
+                const float* scales, float scale_modifier, const float* rotations,
+                const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
+                float* out_color, float* out_depth, int32_t* radii, int64_t* num_rendered_host,
+                uint32_t flags) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (P < 0 || width <= 0 || height <= 0 || D < 0 || D > 3) return fail(GSR_E_INVALID, "gsr_forward: bad P/width/height/degree");
+  if (!geom_alloc || !binning_alloc || !image_alloc || !out_color || !out_depth || !background ||
+      !viewmatrix || !projmatrix || !cam_pos || !num_rendered_host)
+    return fail(GSR_E_INVALID, "gsr_forward: null argument");
+  if (P > 0) {
+    if (!means3D || !opacities || !radii) return fail(GSR_E_INVALID, "gsr_forward: null means3D/opacities/radii");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+      return fail(GSR_E_INVALID, "gsr_forward: provide exactly one of shs / colors_precomp");
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+      return fail(GSR_E_INVALID, "gsr_forward: provide exactly one of (scales, rotations) / cov3D_precomp");
+    if (shs && (D + 1) * (D + 1) > M) return fail(GSR_E_INVALID, "gsr_forward: sh degree needs more coefficients than M");
+    if (rotations && (reinterpret_cast<uintptr_t>(rotations) & 15)) return fail(GSR_E_INVALID, "gsr_forward: rotations must be 16-byte aligned");
+  }
+  *num_rendered_host = 0;
+  Pinned& pin = pinned();
+  if (!pin.result) return fail(GSR_E_ALLOC, "gsr_forward: cudaMallocHost failed");
+  const Camera cam = make_camera(width, height, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, scale_modifier);
+  const int G = cam.grid_x * cam.grid_y;
+
+  const GeomLayout gl = geom_layout(P, flags);
+  const ImageLayout il = image_layout(width, height);
+  char* geom = geom_alloc(geom_user, gl.bytes);
+  char* img = image_alloc(image_user, il.bytes);
+  if (!geom || !img) return fail(GSR_E_ALLOC, "gsr_forward: geometry/image buffer allocation failed");
+  float4* rec = reinterpret_cast<float4*>(geom + gl.rec);
+  float* depths = reinterpret_cast<float*>(geom + gl.depths);
+  uint8_t* clamped = reinterpret_cast<uint8_t*>(geom + gl.clamped);
+  uint32_t* tiles_touched = reinterpret_cast<uint32_t*>(geom + gl.tiles_touched);
+  uint32_t* offsets = reinterpret_cast<uint32_t*>(geom + gl.point_offsets);
+  int32_t* status = reinterpret_cast<int32_t*>(geom + gl.status);
+  float* final_T = reinterpret_cast<float*>(img + il.final_T);
+  uint32_t* n_contrib = reinterpret_cast<uint32_t*>(img + il.n_contrib);
+  uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
+  const bool k64 = key64(flags);
+
+  int64_t N = 0;
+  const uint32_t* order = nullptr;
+  if (P > 0) {
+    GSR_CUDA(cudaMemsetAsync(status, 0, 16, s), "memset status");
+    uint32_t* depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(geom + gl.depth_keys);
+    GSR_CUDA(launch_preprocess(s, P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
+                               colors_precomp, cam, prefiltered, radii, rec, depths, clamped,
+                               tiles_touched, depth_keys, status), "preprocess");
+    if (k64) {
+      GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, nullptr, offsets, geom + gl.temp), "scan");
+    } else {
+      // stable sort of (depth bits, index) over all P Gaussians; culled ones carry 0xFFFFFFFF and
+      // end up last.  32 bits = 4 passes (even): a -> b -> a -> b -> a, the sorted pairs land back
+      // in (depth_keys, order); pass 0 takes the element index as the value.
+      uint32_t* ka = depth_keys;
+      uint32_t* va = reinterpret_cast<uint32_t*>(geom + gl.order);
+      uint32_t* kb = reinterpret_cast<uint32_t*>(geom + gl.depth_keys_alt);
+      uint32_t* vb = reinterpret_cast<uint32_t*>(geom + gl.order_alt);
+      GSR_CUDA(launch_sort_pairs_u32(s, P, ka, nullptr, ka, va, kb, vb, 32, geom + gl.temp), "depth sort");
+      order = va;
+      GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, order, offsets, geom + gl.temp), "scan");
+    }
+    // ---- the one host round trip per view (the reference has the same one) ----
+    pin.result[0] = 0;
+    pin.result[1] = 0;
+    GSR_CUDA(cudaMemcpyAsync(pin.result, offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s), "memcpy num_rendered");
+    GSR_CUDA(cudaMemcpyAsync(pin.result + 1, status, 4, cudaMemcpyDeviceToHost, s), "memcpy status");
+    GSR_CUDA(cudaStreamSynchronize(s), "sync num_rendered");
+    N = (int64_t)(uint32_t)pin.result[0];
+    if ((int32_t)pin.result[1] != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
+    if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
+  }
+  *num_rendered_host = N;
+
+  const BinningLayout bl = binning_layout(N, width, height, flags);
+  char* bin = binning_alloc(binning_user, bl.bytes);
+  if (!bin) return fail(GSR_E_ALLOC, "gsr_forward: binning buffer allocation failed");
+  uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
+  uint32_t* vals_alt = reinterpret_cast<uint32_t*>(bin + bl.vals_alt);
+
+  if (N > 0) {
+    if (k64) {
+      const int end_bit = key64_end_bit(width, height);
+      const int passes = (end_bit + 7) / 8;
+      uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
+      uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
+      // emitted into "a" == the buffer that is NOT the final one for odd pass counts
+      uint32_t* va = (passes & 1) ? vals_alt : point_list;
+      uint32_t* vb = (passes & 1) ? point_list : vals_alt;
+      GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, va), "duplicateWithKeys");
+      uint64_t* kout = (passes & 1) ? kb : ka;
+      uint64_t* kalt = (passes & 1) ? ka : kb;
+      GSR_CUDA(launch_sort_pairs_u64(s, N, ka, va, kout, point_list, kalt, vals_alt, end_bit, bin + bl.temp), "sort");
+      (void)vb;
+      GSR_CUDA(launch_tile_ranges_u64(s, N, kout, G, ranges), "identifyTileRanges");
+    } else {
+      const int end_bit = tile_bits(width, height);
+      const int passes = (end_bit + 7) / 8;
+      uint32_t* ka = reinterpret_cast<uint32_t*>(bin + bl.keys_a);
+      uint32_t* kb = reinterpret_cast<uint32_t*>(bin + bl.keys_b);
+      uint32_t* va = (passes & 1) ? vals_alt : point_list;
+      GSR_CUDA(launch_duplicate_tiles(s, P, order, rec, offsets, radii, cam.grid_x, cam.grid_y, ka, va), "duplicate (depth order)");
+      uint32_t* kout = (passes & 1) ? kb : ka;
+      uint32_t* kalt = (passes & 1) ? ka : kb;
+      GSR_CUDA(launch_sort_pairs_u32(s, N, ka, va, kout, point_list, kalt, vals_alt, end_bit, bin + bl.temp), "tile sort");
+      GSR_CUDA(launch_tile_ranges_u32(s, N, kout, G, ranges), "identifyTileRanges");
+    }
+  } else {
+    GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
+  }
+
+  GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
+                                out_depth, final_T, n_contrib, (flags & GSR_FLAG_FAST_EXP) != 0), "blend forward");
+  return 0;
+}
+
+int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const float* background,
+                 int width, int height, const float* means3D, const float* shs,
+                 const float* colors_precomp, const float* scales, float scale_modifier,
+                 const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
+                 const float* projmatrix, const float* cam_pos, float tan_fovx, float tan_fovy,
+                 const int32_t* radii, const char* geom_buffer, const char* binning_buffer,
+                 const char* image_buffer, const float* dL_dpix, float* dL_dmean2D,
+                 float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, char* scratch,
+                 size_t scratch_bytes, uint32_t flags) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (P < 0 || width <= 0 || height <= 0 || num_rendered < 0) return fail(GSR_E_INVALID, "gsr_backward: bad P/width/height/num_rendered");
+  if (P == 0) return 0;
+  if (!means3D || !radii || !geom_buffer || !binning_buffer || !image_buffer || !dL_dpix || !dL_dmean2D ||
+      !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot || !scratch ||
+      !background || !viewmatrix || !projmatrix || !cam_pos)
+    return fail(GSR_E_INVALID, "gsr_backward: null argument");
+  if (scratch_bytes < gsr_backward_scratch_bytes(P)) return fail(GSR_E_INVALID, "gsr_backward: scratch too small");
+  if (shs && !dL_dsh) return fail(GSR_E_INVALID, "gsr_backward: dL_dsh missing");
+  if ((reinterpret_cast<uintptr_t>(dL_drot) & 15) || (dL_dconic && (reinterpret_cast<uintptr_t>(dL_dconic) & 15)) ||
+      (reinterpret_cast<uintptr_t>(scratch) & 15) || (rotations && (reinterpret_cast<uintptr_t>(rotations) & 15)))
+    return fail(GSR_E_INVALID, "gsr_backward: dL_drot / dL_dconic / scratch / rotations must be 16-byte aligned");
+  const Camera cam = make_camera(width, height, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, scale_modifier);
+
+  const GeomLayout gl = geom_layout(P, flags);
+  const ImageLayout il = image_layout(width, height);
+  const BinningLayout bl = binning_layout(num_rendered, width, height, flags);
+  const float4* rec = reinterpret_cast<const float4*>(geom_buffer + gl.rec);
+  const uint8_t* clamped = reinterpret_cast<const uint8_t*>(geom_buffer + gl.clamped);
+  const float* final_T = reinterpret_cast<const float*>(image_buffer + il.final_T);
+  const uint32_t* n_contrib = reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib);
+  const uint2* ranges = reinterpret_cast<const uint2*>(image_buffer + il.ranges);
+  const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list);
+  float* gacc = reinterpret_cast<float*>(scratch);
+
+  GSR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, s), "memset accumulator");
+  if (num_rendered > 0)
+    GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
+                                   dL_dpix, gacc, (flags & GSR_FLAG_FAST_EXP) != 0), "blend backward");
+  GSR_CUDA(launch_geom_backward(s, P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp,
+                                colors_precomp, cam, rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
+                                dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot), "per-Gaussian backward");
+  return 0;
+}
+
+int gsr_mark_visible(void* stream, int P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present) {
+  (void)projmatrix;  // the reference's frustum test only uses view-space z (x/y test disabled)
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return fail(GSR_E_INVALID, "gsr_mark_visible: bad argument");
+  GSR_CUDA(launch_mark_visible(reinterpret_cast<cudaStream_t>(stream), P, means3D, viewmatrix, present), "markVisible");
+  return 0;
+}
+
+int gsr_sort_pairs_u64(void* stream, int64_t n, const uint64_t* keys_in, const uint32_t* vals_in,
+                       uint64_t* keys_out, uint32_t* vals_out, int end_bit, char* temp, size_t temp_bytes) {
+  if (n < 0 || end_bit < 1 || end_bit > 64) return fail(GSR_E_INVALID, "gsr_sort_pairs_u64: bad argument");
+  if (n >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_sort_pairs_u64: n >= 2^30");
+  if (n == 0) return 0;
+  if (!keys_in || !keys_out || !vals_out || !temp || temp_bytes < gsr_sort_temp_bytes(n, 8, end_bit))
+    return fail(GSR_E_INVALID, "gsr_sort_pairs_u64: null argument or temp too small");
+  const size_t t0 = sort_temp_bytes(n, 8, end_bit);
+  uint64_t* kalt = reinterpret_cast<uint64_t*>(temp + t0);
+  uint32_t* valt = reinterpret_cast<uint32_t*>(temp + t0 + align_up((size_t)n * 8));
+  GSR_CUDA(launch_sort_pairs_u64(reinterpret_cast<cudaStream_t>(stream), n, keys_in, vals_in, keys_out, vals_out,
+                                 kalt, valt, end_bit, temp), "sort_pairs_u64");
+  return 0;
+}
+
+int gsr_sort_pairs_u32(void* stream, int64_t n, const uint32_t* keys_in, const uint32_t* vals_in,
+                       uint32_t* keys_out, uint32_t* vals_out, int end_bit, char* temp, size_t temp_bytes) {
+  if (n < 0 || end_bit < 1 || end_bit > 32) return fail(GSR_E_INVALID, "gsr_sort_pairs_u32: bad argument");
+  if (n >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_sort_pairs_u32: n >= 2^30");
+  if (n == 0) return 0;
+  if (!keys_in || !keys_out || !vals_out || !temp || temp_bytes < gsr_sort_temp_bytes(n, 4, end_bit))
+    return fail(GSR_E_INVALID, "gsr_sort_pairs_u32: null argument or temp too small");
+  const size_t t0 = sort_temp_bytes(n, 4, end_bit);
+  uint32_t* kalt = reinterpret_cast<uint32_t*>(temp + t0);
+  uint32_t* valt = reinterpret_cast<uint32_t*>(temp + t0 + align_up((size_t)n * 4));
+  GSR_CUDA(launch_sort_pairs_u32(reinterpret_cast<cudaStream_t>(stream), n, keys_in, vals_in, keys_out, vals_out,
+                                 kalt, valt, end_bit, temp), "sort_pairs_u32");
+  return 0;
+}
+
+int gsr_inclusive_scan_u32(void* stream, int64_t n, const uint32_t* in, const uint32_t* gather,
+                           uint32_t* out, char* temp, size_t temp_bytes) {
+  if (n < 0) return fail(GSR_E_INVALID, "gsr_inclusive_scan_u32: bad n");
+  if (n == 0) return 0;
+  if (!in || !out || !temp || temp_bytes < scan_temp_bytes(n)) return fail(GSR_E_INVALID, "gsr_inclusive_scan_u32: null argument or temp too small");
+  GSR_CUDA(launch_inclusive_scan(reinterpret_cast<cudaStream_t>(stream), n, in, gather, out, temp), "inclusive_scan");
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// common.cuh -- shared declarations of the sm_100a rasterizer kernels.
+//
+// Floating-point contract (DESIGN.md "FP contract"): everything that feeds an integer output
+// (radii, tile rects, depth keys) or the per-Gaussian geometry state is written with the explicit
+// round-to-nearest intrinsics below, which nvcc never contracts or reassociates, in exactly the
+// order the CPU oracle uses.  That is what makes radii / keys / sorted lists / ranges bit-exact.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsrast_b200.h"
+
+namespace gsr {
+
+constexpr int TILE_X = 16;
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIXELS = TILE_X * TILE_Y;
+
+__device__ __forceinline__ float MUL(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float ADD(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float SUB(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float DIV(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float FMA(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float SQRT(float a) { return __fsqrt_rn(a); }
+
+// SURVEY Appendix A.1 (== gs-simp/utils/sh_utils.py:26-43)
+#define GSR_SH_C0 0.28209479177387814f
+#define GSR_SH_C1 0.4886025119029199f
+#define GSR_SH_C2_0 1.0925484305920792f
+#define GSR_SH_C2_1 -1.0925484305920792f
+#define GSR_SH_C2_2 0.31539156525252005f
+#define GSR_SH_C2_3 -1.0925484305920792f
+#define GSR_SH_C2_4 0.5462742152960396f
+#define GSR_SH_C3_0 -0.5900435899266435f
+#define GSR_SH_C3_1 2.890611442640554f
+#define GSR_SH_C3_2 -0.4570457994644658f
+#define GSR_SH_C3_3 0.3731763325901154f
+#define GSR_SH_C3_4 -0.4570457994644658f
+#define GSR_SH_C3_5 1.445305721320277f
+#define GSR_SH_C3_6 -0.5900435899266435f
+
+// Slack added to the per-Gaussian power cut-off ln(255*opacity) used for culling: anything the
+// kernels skip has alpha < 1/255 with a margin ~1e3 x larger than the fp32 evaluation error of
+// `power`, so skipping is exactly equivalent to the reference's `if (alpha < 1/255) continue`.
+#define GSR_POWER_SLACK 0.05f
+
+// Uniform per launch.  The matrices stay on the device (the reference hands them over as CUDA
+// tensors, scene/cameras.py:60-63); each CTA copies the 35 floats into shared memory once, so no
+// host round trip is needed to launch.
+struct Camera {
+  const float* view;    // (4,4) column-major W2C
+  const float* proj;    // (4,4) column-major P*W2C
+  const float* campos;  // (3,)
+  float focal_x, focal_y, tan_fovx, tan_fovy, scale_modifier;
+  int W, H, grid_x, grid_y;
+};
+// s_cam[0..15] view, [16..31] proj, [32..34] campos
+__device__ __forceinline__ void load_camera(const Camera& cam, float* s_cam) {
+  const int t = threadIdx.x;
+  if (t < 16) s_cam[t] = __ldg(cam.view + t);
+  else if (t < 32) s_cam[t] = __ldg(cam.proj + (t - 16));
+  else if (t < 35) s_cam[t] = __ldg(cam.campos + (t - 32));
+  __syncthreads();
+}
+
+// A.2 step 9 (getRect), explicit fp32 sequence shared by K1 and K3
+__device__ __forceinline__ void get_rect(float px, float py, int max_radius, int gx, int gy,
+                                         int& x0, int& y0, int& x1, int& y1) {
+  const float r = (float)max_radius;
+  x0 = min(gx, max(0, __float2int_rz(DIV(SUB(px, r), 16.0f))));
+  y0 = min(gy, max(0, __float2int_rz(DIV(SUB(py, r), 16.0f))));
+  x1 = min(gx, max(0, __float2int_rz(DIV(SUB(ADD(ADD(px, r), 16.0f), 1.0f), 16.0f))));
+  y1 = min(gy, max(0, __float2int_rz(DIV(SUB(ADD(ADD(py, r), 16.0f), 1.0f), 16.0f))));
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// A.4 getHigherMsb (host)
+inline uint32_t higher_msb(uint32_t n) {
+  uint32_t msb = sizeof(n) * 4, step = msb;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb) msb += step; else msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+inline int ceil_log2(uint32_t n) {
+  int b = 0;
+  while ((1ull << b) < n) b++;
+  return b;
+}
+
+// ---- private layout of the opaque scratch buffers (public view: gsr_layout) -------------------
+struct GeomLayout {
+  size_t rec, depths, clamped, tiles_touched, point_offsets;
+  size_t depth_keys, order, depth_keys_alt, order_alt;    // two-level binning only (sorted result
+                                                          // lands back in depth_keys / order)
+  size_t status;                                          // int32[2]: trap flag, spare
+  size_t temp, temp_bytes;                                // scan + depth-sort temp
+  size_t bytes;
+};
+struct ImageLayout {
+  size_t final_T, n_contrib, ranges, bytes;
+};
+struct BinningLayout {
+  size_t point_list;       // uint32[N]  (final, sorted)
+  size_t vals_alt;         // uint32[N]
+  size_t keys_a, keys_b;   // KeyT[N] each (u32 tile ids, or u64 tile|depth)
+  size_t temp, temp_bytes; // sort temp
+  size_t bytes;
+};
+GeomLayout geom_layout(int P, uint32_t flags);
+ImageLayout image_layout(int W, int H);
+BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags);
+
+// ---- host launchers (one per translation unit) --------------------------------------------------
+void set_error(const char* msg);
+
+cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* means3D,
+                              const float* scales, const float* rotations, const float* opacities,
+                              const float* shs, const float* cov3D_precomp,
+                              const float* colors_precomp, const Camera& cam, int prefiltered,
+                              int32_t* radii, float4* rec, float* depths, uint8_t* clamped,
+                              uint32_t* tiles_touched, uint32_t* depth_keys, int32_t* status);
+cudaError_t launch_mark_visible(cudaStream_t s, int P, const float* means3D, const float* view,
+                                uint8_t* present);
+
+size_t scan_temp_bytes(int64_t n);
+cudaError_t launch_inclusive_scan(cudaStream_t s, int64_t n, const uint32_t* in,
+                                  const uint32_t* gather, uint32_t* out, char* temp);
+size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit);
+// vals_in may be NULL: values are then the element indices 0..n-1
+cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* keys_in,
+                                  const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                                  uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
+cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint64_t* keys_in,
+                                  const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
+                                  uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
+
+cudaError_t launch_duplicate_key64(cudaStream_t s, int P, const float4* rec, const float* depths,
+                                   const uint32_t* offsets, const int32_t* radii, int grid_x,
+                                   int grid_y, uint64_t* keys, uint32_t* vals);
+cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order, const float4* rec,
+                                   const uint32_t* offsets, const int32_t* radii, int grid_x,
+                                   int grid_y, uint32_t* tile_keys, uint32_t* vals);
+cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t N, const uint64_t* keys, int G, uint2* ranges);
+cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t N, const uint32_t* keys, int G, uint2* ranges);
+
+cudaError_t launch_blend_forward(cudaStream_t s, int W, int H, const uint2* ranges,
+                                 const uint32_t* point_list, const float4* rec, const float* depths,
+                                 const float* bg, float* out_color, float* out_depth,
+                                 float* final_T, uint32_t* n_contrib, bool fast_exp);
+cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ranges,
+                                  const uint32_t* point_list, const float4* rec, const float* bg,
+                                  const float* final_T, const uint32_t* n_contrib,
+                                  const float* dL_dpix, float* gacc /*[P][12]*/, bool fast_exp);
+cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const float* means3D,
+                                 const int32_t* radii, const float* shs, const uint8_t* clamped,
+                                 const float* scales, const float* rotations,
+                                 const float* cov3D_precomp, const float* colors_precomp,
+                                 const Camera& cam, const float4* rec, const float* gacc,
+                                 float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                                 float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                                 float* dL_dsh, float* dL_dscale, float* dL_drot);
+
+}  // namespace gsr

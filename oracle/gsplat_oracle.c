@@ -24,8 +24,9 @@ static inline float SUB(float a, float b) { return a - b; }
 static inline float DIV(float a, float b) { return a / b; }
 static inline float FMA(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float SQRT(float a) { return sqrtf(a); }
-static inline float MINF(float a, float b) { return a < b ? a : b; } /* operands never NaN here  */
-static inline float MAXF(float a, float b) { return a > b ? a : b; }
+/* fminf/fmaxf return the non-NaN operand, like CUDA's min/max float overloads */
+static inline float MINF(float a, float b) { return fminf(a, b); }
+static inline float MAXF(float a, float b) { return fmaxf(a, b); }
 
 /* float -> int32 with the semantics of PTX cvt.rzi.s32.f32 (truncate, saturate, NaN -> 0) */
 static inline int32_t f2i_rz_sat(float f) {

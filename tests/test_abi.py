@@ -1,0 +1,92 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/gsrast_b200.h declares; layouts can be queried without a GPU; the Python surface has the
+names and argument lists the reference call sites use (gaussian_renderer/__init__.py:36-51,85-93)."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from multiview_inpaint_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "gsrast_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gsr_[a-z0-9_]+)\s*\(", hdr)) - {"gsr_alloc_fn"})
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(built)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    from multiview_inpaint_b200 import _C
+    assert set(_C.EXPORTED_SYMBOLS) == set(declared)
+
+
+def test_version_and_layout_without_gpu(built):
+    from multiview_inpaint_b200 import _C
+    assert _C._lib.gsr_version() == 1
+    for flags in (0, _C.FLAG_BINNING_KEY64):
+        lay = _C.get_layout(1000, 256, 256, 5000, flags)
+        assert lay.geom_bytes >= 1000 * (48 + 4 + 1 + 4 + 4)
+        assert lay.image_bytes >= 256 * 256 * 8 + 256 * 8
+        assert lay.binning_bytes >= 5000 * 4 * 2
+        assert lay.rec % 256 == 0 and lay.ranges % 256 == 0 and lay.point_list % 256 == 0
+    assert _C._lib.gsr_backward_scratch_bytes(1000) >= 48000
+    with pytest.raises(RuntimeError):
+        _C.get_layout(-1, 256, 256, 0)
+
+
+def test_sort_temp_sizes(built):
+    from multiview_inpaint_b200 import _C
+    a = _C._lib.gsr_sort_temp_bytes(1 << 20, 8, 45)
+    b = _C._lib.gsr_sort_temp_bytes(1 << 20, 4, 13)
+    assert a > (1 << 20) * 12 and b > (1 << 20) * 8 and a > b
+
+
+def test_python_surface_matches_reference_call_sites():
+    import diff_gaussian_rasterization as dgr
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    fields = GaussianRasterizationSettings._fields
+    # the 11 keyword fields of gaussian_renderer/__init__.py:36-49, in upstream order
+    assert fields[:11] == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier",
+                           "viewmatrix", "projmatrix", "sh_degree", "campos", "prefiltered")
+    # debug is commented out at :48 -> must not be required
+    assert GaussianRasterizationSettings._field_defaults == {"debug": False}
+    sig = inspect.signature(GaussianRasterizer.forward)
+    assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                        "rotations", "cov3D_precomp"]
+    assert hasattr(GaussianRasterizer, "markVisible")
+    for fn, n in (("rasterize_gaussians", 18), ("rasterize_gaussians_backward", 20), ("mark_visible", 3)):
+        params = [p for p in inspect.signature(getattr(dgr._C, fn)).parameters.values()
+                  if p.default is inspect.Parameter.empty]
+        assert len(params) == n, (fn, len(params))
+
+
+def test_argument_validation_raises_like_reference():
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    rs = GaussianRasterizationSettings(image_height=16, image_width=16, tanfovx=1.0, tanfovy=1.0,
+                                       bg=torch.zeros(3), scale_modifier=1.0, viewmatrix=torch.eye(4),
+                                       projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3),
+                                       prefiltered=False)
+    r = GaussianRasterizer(raster_settings=rs)
+    x = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=x, means2D=x, opacities=x[:, :1], scales=x, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=x, means2D=x, opacities=x[:, :1], shs=x[:, None], colors_precomp=x, scales=x,
+          rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=x, means2D=x, opacities=x[:, :1], shs=x[:, None])
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=x, means2D=x, opacities=x[:, :1], shs=x[:, None], scales=x, rotations=torch.zeros(4, 4),
+          cov3D_precomp=torch.zeros(4, 6))
+    # CPU tensors are refused loudly: there is no fallback path
+    with pytest.raises(RuntimeError, match="CUDA"):
+        r(means3D=x, means2D=x, opacities=x[:, :1], shs=x[:, None], scales=x, rotations=torch.zeros(4, 4))

@@ -1,0 +1,99 @@
+"""BASELINE.json full sizes, checked through size-independent properties (the oracle would take
+minutes here): sortedness of every tile list by (depth, index), range/tile consistency,
+sum(tiles_touched) == N, both binning modes identical, linearity of the backward in dL/dcolor,
+background linearity colour(bg) = colour(0) + T_final * bg, forward idempotence."""
+import numpy as np
+import pytest
+import torch
+
+from multiview_inpaint_b200 import scenes as S
+from tests.util import cuda_backward, cuda_forward
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mip360():
+    return S.make_config_scene("mip360")       # configs[1]: 1M Gaussians, 1296x928, SH degree 3
+
+
+def _state(out, sc, flags):
+    from multiview_inpaint_b200 import _C
+    n, color, radii, geom, binning, img, depth = out
+    return _C.unpack_state(sc["P"], sc["W"], sc["H"], n, geom, binning, img, flags)
+
+
+def test_mip360_integer_properties_and_mode_equivalence(mip360):
+    sc = mip360
+    out0, d, cam, bg = cuda_forward(sc, flags=0)
+    st0 = _state(out0, sc, 0)
+    n = out0[0]
+    radii = out0[2]
+    tt = st0["tiles_touched"].long()
+    assert n == int(tt.sum()) and n > 1_000_000
+    assert ((radii > 0) == (tt > 0)).all()
+    pl = st0["point_list"].long()
+    ranges = st0["ranges"].long()
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == n and (lens >= 0).all()
+    nz = lens > 0
+    starts = ranges[nz, 0]
+    assert (starts[1:] == ranges[nz, 1][:-1]).all() and starts[0] == 0          # contiguous, tile-ordered
+    # every tile list sorted by (depth bits, index): check adjacent pairs not crossing a tile boundary
+    depth_bits = st0["depths"].view(torch.int32)[pl].long()
+    same_tile = torch.ones(n - 1, dtype=torch.bool, device=pl.device)
+    same_tile[(ranges[nz, 1][:-1] - 1)] = False
+    ok = (depth_bits[1:] > depth_bits[:-1]) | ((depth_bits[1:] == depth_bits[:-1]) & (pl[1:] > pl[:-1]))
+    assert ok[same_tile].all()
+    # each instance's tile lies inside its Gaussian's rect (recomputed from the record)
+    G = ranges.shape[0]
+    tile_of = torch.repeat_interleave(torch.arange(G, device=pl.device), lens)
+    gx = (sc["W"] + 15) // 16
+    m2d = st0["means2D"][pl]
+    r = radii.long()[pl].float()
+    tx, ty = (tile_of % gx).float(), (tile_of // gx).float()
+    assert ((tx >= torch.floor((m2d[:, 0] - r) / 16).clamp(min=0)) & (tx < torch.floor((m2d[:, 0] + r + 15) / 16 + 1e-3).clamp(min=0) + 1)).all()
+    assert ((ty >= torch.floor((m2d[:, 1] - r) / 16).clamp(min=0)) & (ty < torch.floor((m2d[:, 1] + r + 15) / 16 + 1e-3).clamp(min=0) + 1)).all()
+    # reference-structure binning (one 64-bit sort) gives the identical list, ranges and image
+    out1, *_ = cuda_forward(sc, flags=1)
+    st1 = _state(out1, sc, 1)
+    assert out1[0] == n
+    assert torch.equal(st1["point_list"], st0["point_list"]) and torch.equal(st1["ranges"], st0["ranges"])
+    assert torch.equal(out1[1], out0[1]) and torch.equal(out1[6], out0[6]) and torch.equal(out1[2], out0[2])
+    # idempotence
+    out2, *_ = cuda_forward(sc, flags=0)
+    assert torch.equal(out2[1], out0[1]) and torch.equal(out2[6], out0[6])
+
+
+def test_mip360_background_linearity_and_backward_linearity(mip360):
+    sc = mip360
+    out0, d, cam, bg0 = cuda_forward(sc, bg=np.zeros(3, np.float32))
+    bgv = np.array([0.25, 0.5, 1.0], np.float32)
+    out1, _, _, bg1 = cuda_forward(sc, bg=bgv)
+    T = _state(out0, sc, 0)["final_T"]
+    want = out0[1] + T.unsqueeze(0) * torch.from_numpy(bgv).cuda().view(3, 1, 1)
+    assert (out1[1] - want).abs().max() < 1e-6
+    assert torch.equal(out0[6], out1[6])                                      # depth independent of bg
+    w1 = S.loss_weights(sc["W"], sc["H"], 1)
+    w2 = S.loss_weights(sc["W"], sc["H"], 2)
+    g1 = cuda_backward(out0, d, cam, bg0, sc, w1)
+    g2 = cuda_backward(out0, d, cam, bg0, sc, w2)
+    g12 = cuda_backward(out0, d, cam, bg0, sc, 2.0 * w1 - 0.5 * w2)
+    for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dmeans2D"):
+        want = 2.0 * g1[k] - 0.5 * g2[k]
+        scale = want.abs().max()
+        assert torch.isfinite(g12[k]).all()
+        assert (g12[k] - want).abs().max() <= 2e-3 * scale, k
+    vis = out0[2] > 0
+    assert (g1["dL_dmeans3D"][~vis] == 0).all() and (g1["dL_dsh"][~vis] == 0).all()
+
+
+def test_inference_shape_partial_tiles_1080p():
+    """configs[3] shape (1920x1080: H not a multiple of 16) at 1/6 of the Gaussians, fwd only."""
+    sc = S.make_config_scene("inference", scale=1 / 6)
+    out, *_ = cuda_forward(sc)
+    n, color, radii, geom, binning, img, depth = out
+    assert color.shape == (3, 1080, 1920) and depth.shape == (1, 1080, 1920)
+    assert torch.isfinite(color).all() and (depth > 0.2).all() and (depth <= 15.0).all()
+    st = _state(out, sc, 0)
+    assert st["ranges"].shape[0] == 120 * 68 and int((st["ranges"][:, 1] - st["ranges"][:, 0]).sum()) == n
