@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd views/s of the differentiable Gaussian rasterizer (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload headline]
+
+A "step" is one pass of the hot path over one batch of synthetic views: every rank runs
+forward + backward for `--views-per-rank` views of the named scene (gradients ADDED into one flat
+arena), then the arena is all-reduced (N > 1).  Weak scaling: per-GPU work is fixed.
+
+Prints ONE JSON line (rank 0).  `value` = views/s with inputs resident in HBM; `e2e` = the same
+through the public API with that step's camera + loss-weight image copied from pinned host memory
+and the scalar loss read back, inside the timed region.  `roofline` is for the dominant kernel,
+timed live with CUDA events on the launching stream (gsr_profile_* hooks of the C ABI);
+`cpu_baseline` / `--impl reference` time the CPU oracle (the reference's rasterizer source is not
+in the tree and cannot be built here -- DESIGN.md), on a bounded tile-strided sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd views/s"
+UNIT = "views/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline")
+    ap.add_argument("--views-per-rank", type=int, default=4)
+    ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def algorithmic_bytes(P, V, N, G, W, H, M):
+    """SURVEY.md section 8(d) per-view figures, per stage (bytes per launch-bracket)."""
+    pre_b = {1: 190, 4: 260, 16: 550}.get(M, 119 + 27 * M)
+    return {
+        "preprocess": P * (119 + 12 * M),
+        "scan": 8 * P,
+        "duplicate": 20 * P + 12 * N,
+        "tile_sort": N * (8 + 6 * 24),
+        "tile_ranges": 8 * N + 8 * G,
+        "blend_forward": 44 * N + 24 * W * H,
+        "blend_backward": 44 * N + 20 * W * H + 36 * N,
+        "geom_backward": P * pre_b,
+    }
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksThrottleReason") or k.startswith("nvmlClocksEventReason")}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) == bit and "None" not in name and "All" not in name:
+                        self.reasons.add(name.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle on the host cores
+# -------------------------------------------------------------------------------------------------
+def cpu_view_seconds(sc, cam, wt, tile_step):
+    """One fwd+bwd view on the CPU: full preprocess + binning, blend fwd/bwd on every
+    `tile_step`-th tile; returns (estimated seconds for the full view, measured seconds, parts)."""
+    import numpy as np
+    from oracle import oracle as O
+    kw = dict(means3D=sc["means3D"].numpy(), opacities=sc["opacities"].numpy(),
+              viewmatrix=cam.world_view_transform.numpy(), projmatrix=cam.full_proj_transform.numpy(),
+              campos=cam.camera_center.contiguous().numpy(), W=cam.image_width, H=cam.image_height,
+              tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, sh_degree=sc["sh_degree"], shs=sc["shs"].numpy(),
+              scales=sc["scales"].numpy(), rotations=sc["rotations"].numpy())
+    t0 = time.perf_counter()
+    f = O.bin_and_sort(O.preprocess(**kw))
+    t1 = time.perf_counter()
+    O.blend(f, np.zeros(3, np.float32), 0, tile_step)
+    O.backward(f, wt, 0, tile_step)          # blend backward on the sample + full per-Gaussian backward
+    t2 = time.perf_counter()
+    # the per-Gaussian backward inside O.backward is not strided: time it alone to avoid scaling it
+    t3 = time.perf_counter()
+    g = O.backward(f, wt, 0, 1 << 30)        # tile_step >= G: only tile 0 blended, full K8+K9
+    t4 = time.perf_counter()
+    geom_bwd = t4 - t3
+    blend_sample = max((t2 - t1) - geom_bwd, 0.0)
+    est = (t1 - t0) + blend_sample * tile_step + geom_bwd
+    return est, (t2 - t0), dict(preprocess_bin_s=t1 - t0, blend_sample_s=blend_sample, geom_bwd_s=geom_bwd,
+                                N=int(f.num_rendered), V=int((f.radii > 0).sum()))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from multiview_inpaint_b200 import scenes as S
+    from oracle import oracle as O
+    O.build()
+    cfg = S.CONFIGS[args.workload]
+    sc = S.make_config_scene(args.workload)
+    cams = S.orbit_cameras(max(args.views_per_rank, 2), cfg["W"], cfg["H"])
+    wt = S.loss_weights(cfg["W"], cfg["H"], cfg["seed"]).numpy()
+    G = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
+    tile_step = args.cpu_tile_step or 8
+    cores = O.num_threads()
+    for i in range(args.warmup):
+        cpu_view_seconds(sc, cams[i % len(cams)], wt, tile_step)
+    ests, t0 = [], time.perf_counter()
+    parts = {}
+    for i in range(args.steps):
+        est, _, parts = cpu_view_seconds(sc, cams[i % len(cams)], wt, tile_step)
+        ests.append(est)
+    wall = time.perf_counter() - t0
+    est_view = sum(ests) / len(ests)
+    value = 1.0 / est_view
+    sample = (f"per step: 1 view of '{args.workload}' (P={cfg['P']}, {cfg['W']}x{cfg['H']}, SH deg {cfg['sh_degree']}): full "
+              f"preprocess+binning+per-Gaussian backward, blend fwd+bwd on every {tile_step}-th of {G} tiles, "
+              f"blend time scaled x{tile_step}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, **cfg, "note": "CPU oracle port of the rasterizer (reference source not in tree)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **parts},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from multiview_inpaint_b200 import _C, multiview as mv, scenes as S
+    from multiview_inpaint_b200.rasterizer import GaussianRasterizationSettings
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = dict(S.CONFIGS[args.workload])
+    sc = S.make_config_scene(args.workload)
+    P, W, H, M, D = sc["P"], sc["W"], sc["H"], sc["M"], sc["sh_degree"]
+    G = ((W + 15) // 16) * ((H + 15) // 16)
+    gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    vpr = args.views_per_rank
+    n_views = vpr * world
+    cams_cpu = S.orbit_cameras(n_views, W, H)
+    mine = mv.shard_views(n_views, rank, world)
+    bg = torch.zeros(3, device=dev)
+
+    def settings(cam):
+        return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                             bg=bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+                                             projmatrix=cam.full_proj_transform, sh_degree=D, campos=cam.camera_center,
+                                             prefiltered=False)
+
+    # device-resident inputs (for `value`) and pinned host copies (for `e2e`)
+    cams_dev = {v: cams_cpu[v].to(dev) for v in mine}
+    wts_cpu = {v: S.loss_weights(W, H, cfg["seed"] + v).pin_memory() for v in mine}
+    wts_dev = {v: wts_cpu[v].to(dev) for v in mine}
+    cam_pinned = {}
+    for v in mine:
+        c = cams_cpu[v]
+        buf = torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
+        cam_pinned[v] = buf
+    arena = mv.GradArena(P, M, dev)
+    stats = {}
+
+    def step_resident():
+        arena.zero_()
+        for v in mine:
+            wt = wts_dev[v]
+            r = mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=args.flags)
+            stats["N"], stats["radii"] = r.num_rendered, r.radii
+        arena.all_reduce()
+
+    cam_stage = torch.empty(35, device=dev)
+    wt_stage = torch.empty(3, H, W, device=dev)
+
+    def step_e2e():
+        arena.zero_()
+        loss = torch.zeros((), device=dev)
+        for v in mine:
+            cam_stage.copy_(cam_pinned[v], non_blocking=True)             # H2D: camera
+            wt_stage.copy_(wts_cpu[v], non_blocking=True)                 # H2D: loss weights (the "GT image")
+            c = cams_cpu[v]
+            rs = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                                               scale_modifier=1.0, viewmatrix=cam_stage[:16].view(4, 4),
+                                               projmatrix=cam_stage[16:32].view(4, 4), sh_degree=D, campos=cam_stage[32:35],
+                                               prefiltered=False)
+            res = mv.cuda_view_fwd_bwd(gauss, rs, lambda col: wt_stage, arena, flags=args.flags)
+            loss = loss + (res.color * wt_stage).sum()
+        arena.all_reduce()
+        return float(loss.item())                                          # D2H: the step's result
+    h2d = len(mine) * (35 * 4 + 3 * H * W * 4)
+    d2h = 4 + len(mine) * 4   # loss scalar + num_rendered per view
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    V = int((stats["radii"] > 0).sum().item())
+    N = int(stats["N"])
+
+    # ---- timed: resident ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    _C.profile_enable(True)
+    _C.profile_collect()
+    l0 = _C.kernel_launches()
+    ms_total = timed(step_resident, args.steps)
+    launches = _C.kernel_launches() - l0
+    _C.profile_enable(False)
+    stage_ms, stage_cnt = _C.profile_collect()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- timed: end to end ----
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    views_total = n_views * args.steps
+    value = views_total / (ms_total / 1000.0)
+    e2e_value = views_total / (ms_e2e / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_kind = peaks()
+    alg = algorithmic_bytes(P, V, N, G, W, H, M)
+    per_launch = {k: stage_ms[k] / max(stage_cnt[k], 1) for k in stage_ms}
+    dom = max((k for k in per_launch if k in alg), key=lambda k: stage_ms[k])
+    ach = alg[dom] / (per_launch[dom] / 1000.0) / 1e9 if per_launch[dom] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    b_view = sum(alg.values())
+    ms_view = ms_total / views_total * world   # per-GPU time per view
+    stages = {k: {"ms_per_view": round(per_launch[k], 4), "alg_bytes": alg.get(k),
+                  "gbps": (round(alg[k] / (per_launch[k] / 1000.0) / 1e9, 1) if k in alg and per_launch[k] > 0 else None)}
+              for k in per_launch}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "P": P, "V": V, "N": N,
+                   "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce",
+                   "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": traffic, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": alg[dom],
+                     "ms_per_launch": per_launch[dom],
+                     "view": {"alg_bytes": b_view, "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
+                              "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
+        "stages": stages,
+    }
+
+    # ---- cpu_baseline: rank 0, N = 1 only ----
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as O
+            O.build()
+            tile_step = args.cpu_tile_step or 4
+            est, measured, parts = cpu_view_seconds(sc, cams_cpu[0], wts_cpu[mine[0]].numpy(), tile_step)
+            line["cpu_baseline"] = {"value": 1.0 / est, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+                                    "sample": f"1 view of '{args.workload}': full preprocess+binning+per-Gaussian backward, blend "
+                                              f"fwd+bwd on every {tile_step}-th of {G} tiles scaled x{tile_step}; {measured:.1f} s measured",
+                                    **parts}
+        except Exception as ex:  # the baseline is a reported number, never a reason to lose the bench line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -42,6 +42,12 @@ extern "C" {
                                      depth-sort P Gaussians, emit in depth order, 2-pass tile sort.
                                      Both produce bit-identical point lists and tile ranges.          */
 #define GSR_FLAG_FAST_EXP      2u /* blend with ex2.approx instead of expf (off = parity build)   */
+/* flag for gsr_backward: ADD the per-Gaussian parameter gradients (dL_dmean3D, dL_dsh, dL_dcolor,
+ * dL_dopacity, dL_dcov3D, dL_dscale, dL_drot) into the output buffers instead of overwriting them, and
+ * leave culled Gaussians untouched.  Used by the view-sharded multi-view step, where the outputs are
+ * slices of one flat gradient arena summed over views and then all-reduced over ranks.
+ * dL_dmean2D / dL_dconic stay per-view (densification reads the per-view norm, gaussian_model.py:483). */
+#define GSR_FLAG_ACCUMULATE    8u
 
 /* Buffer grower, replaces `std::function<char*(size_t)>` of the reference core: must return a
  * device allocation of at least `bytes` bytes, 256-byte aligned, that stays alive until the
@@ -125,6 +131,18 @@ typedef struct {
   size_t binning_bytes;
 } gsr_layout;
 int gsr_get_layout(int P, int width, int height, int64_t num_rendered, uint32_t flags, gsr_layout* out);
+
+/* ---- measurement hooks (bench.py) ---- */
+#define GSR_NUM_STAGES 10
+/* stage ids: 0 preprocess(K1) 1 depth sort 2 scan(K2) 3 duplicate(K3) 4 tile/key sort(K4) 5 ranges(K5)
+ *            6 blend forward(K6) 7 accumulator clear 8 blend backward(K7) 9 per-Gaussian backward(K8+K9) */
+/* When enabled, gsr_forward/gsr_backward bracket every stage with CUDA events on the launching stream. */
+void gsr_profile_enable(int on);
+/* Synchronises the recorded events, ADDS each stage's elapsed milliseconds and launch-bracket count
+ * into ms[GSR_NUM_STAGES] / counts[GSR_NUM_STAGES], and clears the recording. */
+int gsr_profile_collect(double* ms_host, int64_t* counts_host);
+/* Number of CUDA kernels this library has launched in this process (monotonic). */
+uint64_t gsr_kernel_launches(void);
 
 const char* gsr_last_error(void);
 int gsr_version(void);

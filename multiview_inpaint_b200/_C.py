@@ -15,6 +15,7 @@ CPU or eager fallback: if the library is missing, importing this module raises.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 
 import torch
@@ -24,6 +25,10 @@ LIB_PATH = os.path.join(_HERE, "libgsrast_b200.so")
 
 FLAG_BINNING_KEY64 = 1
 FLAG_FAST_EXP = 2
+FLAG_ACCUMULATE = 8
+NUM_STAGES = 10
+STAGE_NAMES = ("preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward",
+               "accum_clear", "blend_backward", "geom_backward")
 #: default kernel flags (see include/gsrast_b200.h); override with GSR_FLAGS=<int>
 DEFAULT_FLAGS = int(os.environ.get("GSR_FLAGS", "0"))
 
@@ -70,10 +75,16 @@ _lib.gsr_inclusive_scan_u32.restype = _i
 _lib.gsr_inclusive_scan_u32.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _sz]
 _lib.gsr_get_layout.restype = _i
 _lib.gsr_get_layout.argtypes = [_i, _i, _i, _i64, _u32, C.POINTER(GsrLayout)]
+_lib.gsr_kernel_launches.restype = C.c_uint64
+_lib.gsr_profile_enable.restype = None
+_lib.gsr_profile_enable.argtypes = [_i]
+_lib.gsr_profile_collect.restype = _i
+_lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
+                    "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches",
                     "gsr_last_error", "gsr_version")
 
 
@@ -168,7 +179,9 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
                                  cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
                                  dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
-                                 imageBuffer, debug=False, flags=None, return_conic=False):
+                                 imageBuffer, debug=False, flags=None, return_conic=False, out=None):
+    """`out` (optional): dict of preallocated gradient tensors keyed dL_dmeans3D, dL_dsh, dL_dcolors,
+    dL_dopacity, dL_dcov3D, dL_dscales, dL_drotations -- with FLAG_ACCUMULATE they are added into."""
     flags = DEFAULT_FLAGS if flags is None else int(flags)
     P = means3D.shape[0]
     H, W = dL_dout_color.shape[1], dL_dout_color.shape[2]
@@ -176,9 +189,19 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
     M = sh.shape[1] if sh.numel() != 0 else 0
     with torch.cuda.device(dev):
         e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        dL_dmeans3D, dL_dmeans2D, dL_dcolors = e(P, 3), e(P, 3), e(P, 3)
-        dL_dconic, dL_dopacity, dL_dcov3D = e(P, 2, 2), e(P, 1), e(P, 6)
-        dL_dsh, dL_dscales, dL_drotations = e(P, M, 3), e(P, 3), e(P, 4)
+        out = out or {}
+        acc = bool(flags & FLAG_ACCUMULATE)
+
+        def o(name, *shape):
+            t = out.get(name)
+            if t is None:
+                return torch.zeros(*shape, dtype=torch.float32, device=dev) if acc else e(*shape)
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == math.prod(shape), name
+            return t
+        dL_dmeans2D, dL_dconic = e(P, 3), e(P, 2, 2)
+        dL_dmeans3D, dL_dcolors = o("dL_dmeans3D", P, 3), o("dL_dcolors", P, 3)
+        dL_dopacity, dL_dcov3D = o("dL_dopacity", P, 1), o("dL_dcov3D", P, 6)
+        dL_dsh, dL_dscales, dL_drotations = o("dL_dsh", P, M, 3), o("dL_dscales", P, 3), o("dL_drotations", P, 4)
         if P != 0:
             background = _f32c(background, "background")
             means3D = _f32c(means3D, "means3D")
@@ -211,6 +234,24 @@ def mark_visible(means3D, viewmatrix, projmatrix):
             _check(_lib.gsr_mark_visible(_stream(dev), P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix),
                                          present.data_ptr()), "mark_visible")
     return present
+
+
+# ---- measurement hooks ---------------------------------------------------------------------------
+
+def kernel_launches() -> int:
+    return int(_lib.gsr_kernel_launches())
+
+
+def profile_enable(on: bool):
+    _lib.gsr_profile_enable(int(bool(on)))
+
+
+def profile_collect():
+    """-> ({stage: total ms}, {stage: brackets}) accumulated since the last collect."""
+    ms = (C.c_double * NUM_STAGES)()
+    cnt = (_i64 * NUM_STAGES)()
+    _check(_lib.gsr_profile_collect(ms, cnt), "gsr_profile_collect")
+    return ({STAGE_NAMES[i]: ms[i] for i in range(NUM_STAGES)}, {STAGE_NAMES[i]: int(cnt[i]) for i in range(NUM_STAGES)})
 
 
 # ---- stage-level access for parity tests (not part of the reference's _C surface) ----------------

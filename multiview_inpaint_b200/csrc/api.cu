@@ -8,9 +8,11 @@
 //   forward : K1 preprocess -> [depth sort] -> K2 scan -> (N to host) -> K3 duplicate -> K4 sort
 //             -> K5 ranges -> K6 blend
 //   backward: K7 blend backward -> K8+K9 per-Gaussian backward
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -18,6 +20,30 @@ namespace gsr {
 
 static thread_local std::string g_last_error;
 void set_error(const char* msg) { g_last_error = msg; }
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- stage profiler: CUDA events on the launching stream around every stage ----
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;   // created lazily, reused
+  std::vector<int> stage;          // stage id of mark i, -1 = end of a bracket
+  size_t used = 0;
+  void mark(cudaStream_t s, int st) {
+    if (!on) return;
+    if (used == pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      pool.push_back(e);
+    }
+    cudaEventRecord(pool[used], s);
+    if (stage.size() <= used) stage.push_back(st); else stage[used] = st;
+    used++;
+  }
+};
+static Profiler g_prof;
+#define PROF(st) g_prof.mark(s, (st))
 
 static int fail_cuda(cudaError_t e, const char* where) {
   g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
@@ -145,6 +171,22 @@ using namespace gsr;
 extern "C" {
 
 const char* gsr_last_error(void) { return g_last_error.c_str(); }
+uint64_t gsr_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+void gsr_profile_enable(int on) { g_prof.on = on != 0; }
+int gsr_profile_collect(double* ms_host, int64_t* counts_host) {
+  if (!ms_host || !counts_host) return fail(GSR_E_INVALID, "gsr_profile_collect: null argument");
+  for (size_t i = 0; i + 1 < g_prof.used; i++) {
+    const int st = g_prof.stage[i];
+    if (st < 0 || st >= GSR_NUM_STAGES) continue;
+    GSR_CUDA(cudaEventSynchronize(g_prof.pool[i + 1]), "profile sync");
+    float ms = 0.f;
+    GSR_CUDA(cudaEventElapsedTime(&ms, g_prof.pool[i], g_prof.pool[i + 1]), "profile elapsed");
+    ms_host[st] += ms;
+    counts_host[st] += 1;
+  }
+  g_prof.used = 0;
+  return 0;
+}
 int gsr_version(void) { return GSR_VERSION; }
 
 size_t gsr_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * 48); }
@@ -226,12 +268,15 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   if (P > 0) {
     GSR_CUDA(cudaMemsetAsync(status, 0, 16, s), "memset status");
     uint32_t* depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(geom + gl.depth_keys);
+    PROF(0);
     GSR_CUDA(launch_preprocess(s, P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
                                colors_precomp, cam, prefiltered, radii, rec, depths, clamped,
                                tiles_touched, depth_keys, status), "preprocess");
     if (k64) {
+      PROF(2);
       GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, nullptr, offsets, geom + gl.temp), "scan");
     } else {
+      PROF(1);
       // stable sort of (depth bits, index) over all P Gaussians; culled ones carry 0xFFFFFFFF and
       // end up last.  32 bits = 4 passes (even): a -> b -> a -> b -> a, the sorted pairs land back
       // in (depth_keys, order); pass 0 takes the element index as the value.
@@ -241,8 +286,10 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       uint32_t* vb = reinterpret_cast<uint32_t*>(geom + gl.order_alt);
       GSR_CUDA(launch_sort_pairs_u32(s, P, ka, nullptr, ka, va, kb, vb, 32, geom + gl.temp), "depth sort");
       order = va;
+      PROF(2);
       GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, order, offsets, geom + gl.temp), "scan");
     }
+    PROF(-1);
     // ---- the one host round trip per view (the reference has the same one) ----
     pin.result[0] = 0;
     pin.result[1] = 0;
@@ -270,11 +317,14 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       // emitted into "a" == the buffer that is NOT the final one for odd pass counts
       uint32_t* va = (passes & 1) ? vals_alt : point_list;
       uint32_t* vb = (passes & 1) ? point_list : vals_alt;
+      PROF(3);
       GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, va), "duplicateWithKeys");
       uint64_t* kout = (passes & 1) ? kb : ka;
       uint64_t* kalt = (passes & 1) ? ka : kb;
+      PROF(4);
       GSR_CUDA(launch_sort_pairs_u64(s, N, ka, va, kout, point_list, kalt, vals_alt, end_bit, bin + bl.temp), "sort");
       (void)vb;
+      PROF(5);
       GSR_CUDA(launch_tile_ranges_u64(s, N, kout, G, ranges), "identifyTileRanges");
     } else {
       const int end_bit = tile_bits(width, height);
@@ -282,18 +332,23 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       uint32_t* ka = reinterpret_cast<uint32_t*>(bin + bl.keys_a);
       uint32_t* kb = reinterpret_cast<uint32_t*>(bin + bl.keys_b);
       uint32_t* va = (passes & 1) ? vals_alt : point_list;
+      PROF(3);
       GSR_CUDA(launch_duplicate_tiles(s, P, order, rec, offsets, radii, cam.grid_x, cam.grid_y, ka, va), "duplicate (depth order)");
       uint32_t* kout = (passes & 1) ? kb : ka;
       uint32_t* kalt = (passes & 1) ? ka : kb;
+      PROF(4);
       GSR_CUDA(launch_sort_pairs_u32(s, N, ka, va, kout, point_list, kalt, vals_alt, end_bit, bin + bl.temp), "tile sort");
+      PROF(5);
       GSR_CUDA(launch_tile_ranges_u32(s, N, kout, G, ranges), "identifyTileRanges");
     }
   } else {
     GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
   }
 
+  PROF(6);
   GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
                                 out_depth, final_T, n_contrib, (flags & GSR_FLAG_FAST_EXP) != 0), "blend forward");
+  PROF(-1);
   return 0;
 }
 
@@ -332,13 +387,18 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   const uint32_t* point_list = reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list);
   float* gacc = reinterpret_cast<float*>(scratch);
 
+  PROF(7);
   GSR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, s), "memset accumulator");
+  PROF(8);
   if (num_rendered > 0)
     GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
                                    dL_dpix, gacc, (flags & GSR_FLAG_FAST_EXP) != 0), "blend backward");
+  PROF(9);
   GSR_CUDA(launch_geom_backward(s, P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp,
                                 colors_precomp, cam, rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
-                                dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot), "per-Gaussian backward");
+                                dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot,
+                                (flags & GSR_FLAG_ACCUMULATE) != 0), "per-Gaussian backward");
+  PROF(-1);
   return 0;
 }
 

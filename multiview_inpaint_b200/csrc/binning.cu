@@ -84,6 +84,7 @@ cudaError_t launch_duplicate_key64(cudaStream_t s, int P, const float4* rec, con
                                    int grid_y, uint64_t* keys, uint32_t* vals) {
   if (P == 0) return cudaSuccess;
   duplicate_key64_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, rec, depths, offsets, radii, grid_x, grid_y, keys, vals);
+  count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order, const float4* rec,
@@ -91,18 +92,21 @@ cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order,
                                    int grid_y, uint32_t* tile_keys, uint32_t* vals) {
   if (P == 0) return cudaSuccess;
   duplicate_tiles_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, order, rec, offsets, radii, grid_x, grid_y, tile_keys, vals);
+  count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t N, const uint64_t* keys, int G, uint2* ranges) {
   cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s);
   if (e != cudaSuccess || N == 0) return e;
   tile_ranges_kernel<uint64_t><<<cdiv(N, 256), 256, 0, s>>>(N, keys, ranges);
+  count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t N, const uint32_t* keys, int G, uint2* ranges) {
   cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s);
   if (e != cudaSuccess || N == 0) return e;
   tile_ranges_kernel<uint32_t><<<cdiv(N, 256), 256, 0, s>>>(N, keys, ranges);
+  count_launch();
   return cudaGetLastError();
 }
 

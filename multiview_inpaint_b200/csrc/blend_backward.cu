@@ -209,6 +209,7 @@ cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ran
   else
     blend_backward_kernel<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
                                                          n_contrib, dL_dpix, gacc);
+  count_launch();
   return cudaGetLastError();
 }
 

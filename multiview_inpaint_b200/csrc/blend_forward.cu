@@ -147,6 +147,7 @@ cudaError_t launch_blend_forward(cudaStream_t s, int W, int H, const uint2* rang
   else
     blend_forward_kernel<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, depths, bg,
                                                         out_color, out_depth, final_T, n_contrib);
+  count_launch();
   return cudaGetLastError();
 }
 

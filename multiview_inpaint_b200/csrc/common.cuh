@@ -118,6 +118,7 @@ BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags);
 
 // ---- host launchers (one per translation unit) --------------------------------------------------
 void set_error(const char* msg);
+void count_launch(int n = 1);  // bumps the counter behind gsr_kernel_launches()
 
 cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* means3D,
                               const float* scales, const float* rotations, const float* opacities,
@@ -164,6 +165,6 @@ cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const floa
                                  const Camera& cam, const float4* rec, const float* gacc,
                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
-                                 float* dL_dsh, float* dL_dscale, float* dL_drot);
+                                 float* dL_dsh, float* dL_dscale, float* dL_drot, bool accumulate);
 
 }  // namespace gsr

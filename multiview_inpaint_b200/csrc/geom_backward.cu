@@ -13,7 +13,7 @@
 
 namespace gsr {
 
-template <int DEG>
+template <int DEG, bool ACC>
 __device__ __forceinline__ void sh_backward(const float* __restrict__ sh, float* __restrict__ dsh,
                                             int M, float x, float y, float z, const float dRGB[3],
                                             float ddir[3]) {
@@ -59,9 +59,15 @@ __device__ __forceinline__ void sh_backward(const float* __restrict__ sh, float*
   ddir[0] = ddir[1] = ddir[2] = 0.f;
 #pragma unroll
   for (int k = 0; k < NCO; k++) {
-    dsh[3 * k + 0] = w[k] * dRGB[0];
-    dsh[3 * k + 1] = w[k] * dRGB[1];
-    dsh[3 * k + 2] = w[k] * dRGB[2];
+    if (ACC) {
+      dsh[3 * k + 0] += w[k] * dRGB[0];
+      dsh[3 * k + 1] += w[k] * dRGB[1];
+      dsh[3 * k + 2] += w[k] * dRGB[2];
+    } else {
+      dsh[3 * k + 0] = w[k] * dRGB[0];
+      dsh[3 * k + 1] = w[k] * dRGB[1];
+      dsh[3 * k + 2] = w[k] * dRGB[2];
+    }
     if (k > 0) {
       const float s = __ldg(sh + 3 * k) * dRGB[0] + __ldg(sh + 3 * k + 1) * dRGB[1] + __ldg(sh + 3 * k + 2) * dRGB[2];
       ddir[0] += dwx[k] * s;
@@ -70,11 +76,13 @@ __device__ __forceinline__ void sh_backward(const float* __restrict__ sh, float*
     }
   }
   // coefficients above the active degree receive zero gradient
+  if (!ACC)
   for (int k = NCO; k < M; k++) {
     dsh[3 * k + 0] = 0.f; dsh[3 * k + 1] = 0.f; dsh[3 * k + 2] = 0.f;
   }
 }
 
+template <bool ACC>
 __global__ void __launch_bounds__(256)
 geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
                      const int32_t* __restrict__ radii, const float* __restrict__ shs,
@@ -96,6 +104,7 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
   if (!(radii[i] > 0)) {
     dL_dmean2D[i3] = 0.f; dL_dmean2D[i3 + 1] = 0.f; dL_dmean2D[i3 + 2] = 0.f;
     if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ACC) return;  // accumulate mode: a culled Gaussian adds nothing to the arena
     dL_dopacity[i] = 0.f;
     dL_dcolor[i3] = 0.f; dL_dcolor[i3 + 1] = 0.f; dL_dcolor[i3 + 2] = 0.f;
     dL_dmean3D[i3] = 0.f; dL_dmean3D[i3 + 1] = 0.f; dL_dmean3D[i3 + 2] = 0.f;
@@ -120,8 +129,13 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const float gcx = g1.y, gcy = g1.z, gcw = g1.w;
   dL_dmean2D[i3] = gm2x; dL_dmean2D[i3 + 1] = gm2y; dL_dmean2D[i3 + 2] = 0.f;
   if (dL_dconic) reinterpret_cast<float4*>(dL_dconic)[i] = make_float4(gcx, gcy, 0.f, gcw);
-  dL_dopacity[i] = g2.x;
-  dL_dcolor[i3] = g0.x; dL_dcolor[i3 + 1] = g0.y; dL_dcolor[i3 + 2] = g0.z;
+  if (ACC) {
+    dL_dopacity[i] += g2.x;
+    if (colors_precomp != nullptr) { dL_dcolor[i3] += g0.x; dL_dcolor[i3 + 1] += g0.y; dL_dcolor[i3 + 2] += g0.z; }
+  } else {
+    dL_dopacity[i] = g2.x;
+    dL_dcolor[i3] = g0.x; dL_dcolor[i3 + 1] = g0.y; dL_dcolor[i3 + 2] = g0.z;
+  }
 
   const float m[3] = {__ldg(means3D + i3), __ldg(means3D + i3 + 1), __ldg(means3D + i3 + 2)};
   const float* V = s_cam;
@@ -228,8 +242,14 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
     dmean[1] = V[4] * dtx + V[5] * dty + V[6] * dtz;
     dmean[2] = V[8] * dtx + V[9] * dty + V[10] * dtz;
   }
+  if (ACC) {
+    if (cov3D_precomp != nullptr)
 #pragma unroll
-  for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)i + k] = dcov[k];
+      for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)i + k] += dcov[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)i + k] = dcov[k];
+  }
 
   // ---- K9: perspective projection of the mean ----
   {
@@ -255,20 +275,24 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
     float* dsh = dL_dsh + (size_t)i * M * 3;
     float ddir[3];
     switch (D) {
-      case 0: sh_backward<0>(sh, dsh, M, x, y, z, dRGB, ddir); break;
-      case 1: sh_backward<1>(sh, dsh, M, x, y, z, dRGB, ddir); break;
-      case 2: sh_backward<2>(sh, dsh, M, x, y, z, dRGB, ddir); break;
-      default: sh_backward<3>(sh, dsh, M, x, y, z, dRGB, ddir); break;
+      case 0: sh_backward<0, ACC>(sh, dsh, M, x, y, z, dRGB, ddir); break;
+      case 1: sh_backward<1, ACC>(sh, dsh, M, x, y, z, dRGB, ddir); break;
+      case 2: sh_backward<2, ACC>(sh, dsh, M, x, y, z, dRGB, ddir); break;
+      default: sh_backward<3, ACC>(sh, dsh, M, x, y, z, dRGB, ddir); break;
     }
     const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
     const float* v = dorig;
     dmean[0] += ((sum2 - v[0] * v[0]) * ddir[0] - v[1] * v[0] * ddir[1] - v[2] * v[0] * ddir[2]) * invsum32;
     dmean[1] += (-v[0] * v[1] * ddir[0] + (sum2 - v[1] * v[1]) * ddir[1] - v[2] * v[1] * ddir[2]) * invsum32;
     dmean[2] += (-v[0] * v[2] * ddir[0] - v[1] * v[2] * ddir[1] + (sum2 - v[2] * v[2]) * ddir[2]) * invsum32;
-  } else if (dL_dsh != nullptr) {
+  } else if (dL_dsh != nullptr && !ACC) {
     for (int k = 0; k < 3 * M; k++) dL_dsh[(size_t)i * M * 3 + k] = 0.f;
   }
-  dL_dmean3D[i3] = dmean[0]; dL_dmean3D[i3 + 1] = dmean[1]; dL_dmean3D[i3 + 2] = dmean[2];
+  if (ACC) {
+    dL_dmean3D[i3] += dmean[0]; dL_dmean3D[i3 + 1] += dmean[1]; dL_dmean3D[i3 + 2] += dmean[2];
+  } else {
+    dL_dmean3D[i3] = dmean[0]; dL_dmean3D[i3 + 1] = dmean[1]; dL_dmean3D[i3 + 2] = dmean[2];
+  }
 
   // ---- K9: cov3D backward ----
   if (cov3D_precomp == nullptr) {
@@ -282,8 +306,10 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
       for (int k = 0; k < 3; k++)
         dM[a][k] = 2.0f * (Gs[a][0] * R[0][k] + Gs[a][1] * R[1][k] + Gs[a][2] * R[2][k]) * s[k];
 #pragma unroll
-    for (int k = 0; k < 3; k++)
-      dL_dscale[i3 + k] = R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k];
+    for (int k = 0; k < 3; k++) {
+      const float ds = R[0][k] * dM[0][k] + R[1][k] * dM[1][k] + R[2][k] * dM[2][k];
+      if (ACC) dL_dscale[i3 + k] += ds; else dL_dscale[i3 + k] = ds;
+    }
 #pragma unroll
     for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -294,8 +320,12 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
     dq.y = 2.f * y * (g[0][1] + g[1][0]) + 2.f * z * (g[0][2] + g[2][0]) + 2.f * r * (g[2][1] - g[1][2]) - 4.f * x * (g[1][1] + g[2][2]);
     dq.z = 2.f * x * (g[0][1] + g[1][0]) + 2.f * r * (g[0][2] - g[2][0]) + 2.f * z * (g[1][2] + g[2][1]) - 4.f * y * (g[0][0] + g[2][2]);
     dq.w = 2.f * r * (g[1][0] - g[0][1]) + 2.f * x * (g[0][2] + g[2][0]) + 2.f * y * (g[1][2] + g[2][1]) - 4.f * z * (g[0][0] + g[1][1]);
+    if (ACC) {
+      const float4 o = reinterpret_cast<float4*>(dL_drot)[i];
+      dq.x += o.x; dq.y += o.y; dq.z += o.z; dq.w += o.w;
+    }
     reinterpret_cast<float4*>(dL_drot)[i] = dq;
-  } else {
+  } else if (!ACC) {
     dL_dscale[i3] = 0.f; dL_dscale[i3 + 1] = 0.f; dL_dscale[i3 + 2] = 0.f;
     reinterpret_cast<float4*>(dL_drot)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -308,12 +338,19 @@ cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const floa
                                  const Camera& cam, const float4* rec, const float* gacc,
                                  float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
-                                 float* dL_dsh, float* dL_dscale, float* dL_drot) {
+                                 float* dL_dsh, float* dL_dscale, float* dL_drot, bool accumulate) {
   if (P == 0) return cudaSuccess;
-  geom_backward_kernel<<<cdiv(P, 256), 256, 0, s>>>(
-      P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp, colors_precomp, cam,
-      rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
-      dL_dscale, dL_drot);
+  if (accumulate)
+    geom_backward_kernel<true><<<cdiv(P, 256), 256, 0, s>>>(
+        P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp, colors_precomp, cam,
+        rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
+        dL_dscale, dL_drot);
+  else
+    geom_backward_kernel<false><<<cdiv(P, 256), 256, 0, s>>>(
+        P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp, colors_precomp, cam,
+        rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
+        dL_dscale, dL_drot);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -271,6 +271,7 @@ cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* 
                                                  cov3D_precomp, colors_precomp, cam, prefiltered,
                                                  radii, rec, depths, clamped, tiles_touched,
                                                  depth_keys, status);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -278,6 +279,7 @@ cudaError_t launch_mark_visible(cudaStream_t s, int P, const float* means3D, con
                                 uint8_t* present) {
   if (P == 0) return cudaSuccess;
   mark_visible_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, means3D, view, present);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -113,6 +113,7 @@ cudaError_t launch_inclusive_scan(cudaStream_t s, int64_t n, const uint32_t* in,
   cudaError_t e = cudaMemsetAsync(temp, 0, scan_temp_bytes(n), s);
   if (e != cudaSuccess) return e;
   scan_kernel<<<(unsigned)tiles, SCAN_THREADS, 0, s>>>(in, gather, out, n, status, ticket);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -339,6 +340,7 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const KeyT* keys_i
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
   rs_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys_in, n, end_bit, hist);
   rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
+  count_launch(2 + passes);
 
   const size_t smem = sizeof(KeyT) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 16);
   static bool attr_set = false;

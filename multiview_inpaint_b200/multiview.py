@@ -1,0 +1,130 @@
+"""View-sharded multi-view step: the one place this path shards.
+
+The reference renders one camera per iteration in one process (gs-simp/train.py:78,86;
+inpaint_rec.py:100,108) and fans scenes out over GPUs with shell jobs (gs-simp/train.sh:1), no
+communication.  Its multi-view consumers -- SVD's 14/25-frame orbits (scene/__init__.py:129-198),
+SDS view batches, test-set renders (render.py:32-39) -- iterate views that are independent given
+the Gaussians.  Here one process per GPU holds a replica of the Gaussians, view v of a batch goes
+to rank v mod R, every rank accumulates its views' parameter gradients into ONE flat fp32 arena
+(the kernels add in place: GSR_FLAG_ACCUMULATE), and a single all-reduce (NCCL over NVLink, or
+gloo in the CPU tests) sums the arena.  Densification statistics keep the reference's per-view
+semantics (scene/gaussian_model.py:482-484, train.py:115): sum over views of ||means2D.grad[:, :2]||,
+sum of visibility counts, max of radii -- reduced with SUM / SUM / MAX.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> list[int]:
+    """Round-robin: view v -> rank v mod R (25 views on 8 ranks -> 4/3 per rank)."""
+    return list(range(rank, n_views, world))
+
+
+class GradArena:
+    """Flat fp32 buffer [dL_dmeans3D | dL_dsh | dL_dopacity | dL_dscales | dL_drotations] =
+    3 + 3M + 1 + 3 + 4 floats per Gaussian (14 / 23 / 59 at M = 1 / 4 / 16), plus typed views."""
+
+    def __init__(self, P: int, M: int, device):
+        self.P, self.M = P, M
+        sizes = [("dL_dmeans3D", (P, 3)), ("dL_dsh", (P, M, 3)), ("dL_dopacity", (P, 1)),
+                 ("dL_dscales", (P, 3)), ("dL_drotations", (P, 4))]
+        # each slice starts on a 16-byte boundary (float4 stores in the kernels)
+        offs, off = [], 0
+        for _, shp in sizes:
+            offs.append(off)
+            n = 1
+            for s in shp:
+                n *= s
+            off += (n + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        self.views = {name: self.flat[o:o + _numel(shp)].view(*shp) for (name, shp), o in zip(sizes, offs)}
+        # densification statistics (kept out of the float arena: different reductions)
+        self.grad_norm_accum = torch.zeros(P, dtype=torch.float32, device=device)
+        self.visible_count = torch.zeros(P, dtype=torch.int32, device=device)
+        self.max_radii = torch.zeros(P, dtype=torch.int32, device=device)
+
+    def zero_(self):
+        self.flat.zero_()
+        self.grad_norm_accum.zero_()
+        self.visible_count.zero_()
+        self.max_radii.zero_()
+
+    def add_view_stats(self, dL_dmeans2D: torch.Tensor, radii: torch.Tensor):
+        vis = radii > 0
+        self.grad_norm_accum += torch.norm(dL_dmeans2D[:, :2], dim=-1) * vis   # gaussian_model.py:483
+        self.visible_count += vis.to(torch.int32)                               # gaussian_model.py:484
+        torch.maximum(self.max_radii, radii, out=self.max_radii)                # train.py:115
+
+    def all_reduce(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.grad_norm_accum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.visible_count, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
+
+    @property
+    def bytes(self) -> int:
+        return self.flat.numel() * 4
+
+
+def _numel(shp):
+    n = 1
+    for s in shp:
+        n *= s
+    return n
+
+
+@dataclass
+class ViewResult:
+    color: torch.Tensor
+    depth: torch.Tensor
+    radii: torch.Tensor
+    num_rendered: int
+
+
+def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor],
+                      arena: GradArena, flags: int = 0) -> ViewResult:
+    """One view through the CUDA path: forward, loss gradient, backward ADDING into `arena`.
+    `gaussians`: means3D, shs, opacities, scales, rotations (post-activation, as render() passes them);
+    `settings`: GaussianRasterizationSettings."""
+    from . import _C
+    rs = settings
+    e = torch.empty(0, device=gaussians["means3D"].device)
+    n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
+        rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
+        rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+        rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags)
+    dL = dL_dcolor_fn(color)
+    out = _C.rasterize_gaussians_backward(
+        rs.bg, gaussians["means3D"], radii, e, gaussians["scales"], gaussians["rotations"], rs.scale_modifier, e,
+        rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, dL, gaussians["shs"], rs.sh_degree, rs.campos,
+        geom, n, binning, img, flags=flags | _C.FLAG_ACCUMULATE, out=arena.views)
+    arena.add_view_stats(out[0], radii)
+    return ViewResult(color, depth, radii, n)
+
+
+def sharded_step(view_fwd_bwd: Callable[[int], None], n_views: int, arena: GradArena, group=None,
+                 rank: int | None = None, world: int | None = None) -> list[int]:
+    """Runs `view_fwd_bwd(v)` for this rank's share of the views (each call accumulates into
+    `arena`), then all-reduces.  Returns the view indices this rank processed."""
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    mine = shard_views(n_views, rank, world)
+    for v in mine:
+        view_fwd_bwd(v)
+    arena.all_reduce(group)
+    return mine
+
+
+def render_views_sharded(render_one: Callable[[int], Sequence[torch.Tensor]], n_views: int,
+                         rank: int = 0, world: int = 1) -> dict[int, Sequence[torch.Tensor]]:
+    """Inference (render.py / render_depth.py loops): no collective, rank r renders views r, r+R, ..."""
+    with torch.no_grad():
+        return {v: render_one(v) for v in shard_views(n_views, rank, world)}

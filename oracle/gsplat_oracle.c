@@ -388,14 +388,17 @@ static inline float gauss_power(float cx, float cy, float cz, float dx, float dy
 }
 
 /* ---- K6 ------------------------------------------------------------------------------------ */
-void gso_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
-                       const float* means2D, const float* rgb, const float* depths,
-                       const float* conic_opacity, const float* bg, float* out_color,
-                       float* out_depth, float* final_T, uint32_t* n_contrib) {
+void gso_blend_forward_tiles(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
+                             const float* means2D, const float* rgb, const float* depths,
+                             const float* conic_opacity, const float* bg, float* out_color,
+                             float* out_depth, float* final_T, uint32_t* n_contrib, int tile_start,
+                             int tile_step) {
   const int gx = (W + GSO_BLOCK_X - 1) / GSO_BLOCK_X, gy = (H + GSO_BLOCK_Y - 1) / GSO_BLOCK_Y;
   const size_t HW = (size_t)H * W;
+  const int n_sel = (gx * gy - tile_start + tile_step - 1) / tile_step;
 #pragma omp parallel for schedule(dynamic, 4)
-  for (int tile = 0; tile < gx * gy; tile++) {
+  for (int ts = 0; ts < n_sel; ts++) {
+    const int tile = tile_start + ts * tile_step;
     const int bx = tile % gx, by = tile / gx;
     const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
     for (int ly = 0; ly < GSO_BLOCK_Y; ly++)
@@ -432,12 +435,29 @@ void gso_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* poi
   }
 }
 
+void gso_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
+                       const float* means2D, const float* rgb, const float* depths,
+                       const float* conic_opacity, const float* bg, float* out_color,
+                       float* out_depth, float* final_T, uint32_t* n_contrib) {
+  gso_blend_forward_tiles(W, H, ranges, point_list, means2D, rgb, depths, conic_opacity, bg, out_color,
+                          out_depth, final_T, n_contrib, 0, 1);
+}
+
 /* ---- K7 ------------------------------------------------------------------------------------ */
 void gso_blend_backward(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
                         const float* means2D, const float* rgb, const float* conic_opacity,
                         const float* bg, const float* final_T, const uint32_t* n_contrib,
                         const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic,
                         float* dL_dopacity, float* dL_dcolors) {
+  gso_blend_backward_tiles(W, H, ranges, point_list, means2D, rgb, conic_opacity, bg, final_T, n_contrib,
+                           dL_dpixels, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolors, 0, 1);
+}
+
+void gso_blend_backward_tiles(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
+                              const float* means2D, const float* rgb, const float* conic_opacity,
+                              const float* bg, const float* final_T, const uint32_t* n_contrib,
+                              const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic,
+                              float* dL_dopacity, float* dL_dcolors, int tile_start, int tile_step) {
   const int gx = (W + GSO_BLOCK_X - 1) / GSO_BLOCK_X, gy = (H + GSO_BLOCK_Y - 1) / GSO_BLOCK_Y;
   const size_t HW = (size_t)H * W;
   const int G = gx * gy;
@@ -449,8 +469,10 @@ void gso_blend_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
    * 9 slots: color 0..2, mean2D 3..4, conic 5..7, opacity 8 */
   double* part = (double*)calloc((size_t)N * 9, sizeof(double));
   const float ddelx_dx = MUL(0.5f, (float)W), ddely_dy = MUL(0.5f, (float)H);
+  const int n_sel = (G - tile_start + tile_step - 1) / tile_step;
 #pragma omp parallel for schedule(dynamic, 4)
-  for (int tile = 0; tile < G; tile++) {
+  for (int ts = 0; ts < n_sel; ts++) {
+    const int tile = tile_start + ts * tile_step;
     const int bx = tile % gx, by = tile / gx;
     const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
     if (r1 <= r0) continue;
@@ -505,15 +527,22 @@ void gso_blend_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
         }
       }
   }
-  /* fixed-order reduction per Gaussian: walk instances in sorted order, accumulate in double */
+  /* fixed-order reduction per Gaussian: walk the selected tiles' instances in sorted order,
+   * accumulate in double */
   int P = 0;
-  for (uint32_t k = 0; k < N; k++)
-    if ((int)point_list[k] + 1 > P) P = (int)point_list[k] + 1;
-  double* acc = (double*)calloc((size_t)P * 9, sizeof(double));
-  for (uint32_t k = 0; k < N; k++) {
-    double* a = acc + (size_t)point_list[k] * 9;
-    const double* ps = part + (size_t)k * 9;
-    for (int j = 0; j < 9; j++) a[j] += ps[j];
+  for (int ts = 0; ts < n_sel; ts++) {
+    const int tile = tile_start + ts * tile_step;
+    for (uint32_t k = ranges[2 * tile]; k < ranges[2 * tile + 1]; k++)
+      if ((int)point_list[k] + 1 > P) P = (int)point_list[k] + 1;
+  }
+  double* acc = (double*)calloc((size_t)(P > 0 ? P : 1) * 9, sizeof(double));
+  for (int ts = 0; ts < n_sel; ts++) {
+    const int tile = tile_start + ts * tile_step;
+    for (uint32_t k = ranges[2 * tile]; k < ranges[2 * tile + 1]; k++) {
+      double* a = acc + (size_t)point_list[k] * 9;
+      const double* ps = part + (size_t)k * 9;
+      for (int j = 0; j < 9; j++) a[j] += ps[j];
+    }
   }
 #pragma omp parallel for schedule(static)
   for (int g = 0; g < P; g++) {

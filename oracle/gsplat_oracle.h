@@ -87,6 +87,19 @@ void gso_blend_backward(int W, int H, const uint32_t* ranges, const uint32_t* po
                         float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
                         float* dL_dcolors);
 
+/* Tile-strided variants (tiles tile_start, tile_start+tile_step, ...): bench.py times a bounded
+ * sample of the blend with these; pixels of unselected tiles are left untouched. */
+void gso_blend_forward_tiles(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
+                             const float* means2D, const float* rgb, const float* depths,
+                             const float* conic_opacity, const float* bg, float* out_color,
+                             float* out_depth, float* final_T, uint32_t* n_contrib, int tile_start,
+                             int tile_step);
+void gso_blend_backward_tiles(int W, int H, const uint32_t* ranges, const uint32_t* point_list,
+                              const float* means2D, const float* rgb, const float* conic_opacity,
+                              const float* bg, const float* final_T, const uint32_t* n_contrib,
+                              const float* dL_dpixels, float* dL_dmean2D, float* dL_dconic,
+                              float* dL_dopacity, float* dL_dcolors, int tile_start, int tile_step);
+
 /* Appendix A.7 (K8 + K9): per-Gaussian chain rule.  dL_dmeans3D (3P), dL_dcov3D (6P),
  * dL_dsh (3MP), dL_dscales (3P), dL_drots (4P) are WRITTEN for visible Gaussians (callers zero). */
 void gso_preprocess_backward(int P, int D, int M,

@@ -150,7 +150,7 @@ def bin_and_sort(f: Forward) -> Forward:
     return f
 
 
-def blend(f: Forward, bg) -> Forward:
+def blend(f: Forward, bg, tile_start: int = 0, tile_step: int = 1) -> Forward:
     W, H = f.W, f.H
     bg = _f32(bg)
     f.inputs["bg"] = bg
@@ -158,9 +158,10 @@ def blend(f: Forward, bg) -> Forward:
     f.depth = np.zeros((1, H, W), np.float32)
     f.final_T = np.zeros((H, W), np.float32)
     f.n_contrib = np.zeros((H, W), np.uint32)
-    lib().gso_blend_forward(C.c_int(W), C.c_int(H), _p(f.ranges), _p(f.point_list), _p(f.means2D),
-                            _p(f.rgb), _p(f.depths), _p(f.conic_opacity), _p(bg), _p(f.color),
-                            _p(f.depth), _p(f.final_T), _p(f.n_contrib))
+    lib().gso_blend_forward_tiles(C.c_int(W), C.c_int(H), _p(f.ranges), _p(f.point_list), _p(f.means2D),
+                                  _p(f.rgb), _p(f.depths), _p(f.conic_opacity), _p(bg), _p(f.color),
+                                  _p(f.depth), _p(f.final_T), _p(f.n_contrib), C.c_int(tile_start),
+                                  C.c_int(tile_step))
     return f
 
 
@@ -169,7 +170,7 @@ def forward(bg, **kw) -> Forward:
     return blend(bin_and_sort(preprocess(**kw)), bg)
 
 
-def backward(f: Forward, dL_dcolor) -> dict:
+def backward(f: Forward, dL_dcolor, tile_start: int = 0, tile_step: int = 1) -> dict:
     """K7 -> K8 -> K9.  Returns the eight gradient tensors of
     `rasterize_gaussians_backward` plus dL_dconic."""
     P, W, H = f.P, f.W, f.H
@@ -184,10 +185,11 @@ def backward(f: Forward, dL_dcolor) -> dict:
         dL_drotations=np.zeros((P, 4), np.float32))
     if P == 0:
         return g
-    lib().gso_blend_backward(C.c_int(W), C.c_int(H), _p(f.ranges), _p(f.point_list), _p(f.means2D),
-                             _p(f.rgb), _p(f.conic_opacity), _p(i["bg"]), _p(f.final_T),
-                             _p(f.n_contrib), _p(dL_dcolor), _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]),
-                             _p(g["dL_dopacity"]), _p(g["dL_dcolors"]))
+    lib().gso_blend_backward_tiles(C.c_int(W), C.c_int(H), _p(f.ranges), _p(f.point_list), _p(f.means2D),
+                                   _p(f.rgb), _p(f.conic_opacity), _p(i["bg"]), _p(f.final_T),
+                                   _p(f.n_contrib), _p(dL_dcolor), _p(g["dL_dmeans2D"]), _p(g["dL_dconic"]),
+                                   _p(g["dL_dopacity"]), _p(g["dL_dcolors"]), C.c_int(tile_start),
+                                   C.c_int(tile_step))
     lib().gso_preprocess_backward(
         C.c_int(P), C.c_int(i["sh_degree"]), C.c_int(M), _p(i["means3D"]), _p(f.radii), _p(i["shs"]),
         _p(f.clamped), _p(i["scales"]), _p(i["rotations"]), C.c_float(i["scale_modifier"]),
