@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
     ap.add_argument("--views-per-rank", type=int, default=4)
+    ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
     ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
@@ -149,7 +150,7 @@ def run_reference(args):
     O.build()
     cfg = S.CONFIGS[args.workload]
     sc = S.make_config_scene(args.workload)
-    cams = S.orbit_cameras(max(args.views_per_rank, 2), cfg["W"], cfg["H"])
+    cams = S.orbit_cameras(max(args.views_per_rank, 2), cfg["W"], cfg["H"], max_deg=args.orbit_deg)
     wt = S.loss_weights(cfg["W"], cfg["H"], cfg["seed"]).numpy()
     G = ((cfg["W"] + 15) // 16) * ((cfg["H"] + 15) // 16)
     tile_step = args.cpu_tile_step or 8
@@ -204,7 +205,7 @@ def run_ours(args):
     gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
     vpr = args.views_per_rank
     n_views = vpr * world
-    cams_cpu = S.orbit_cameras(n_views, W, H)
+    cams_cpu = S.orbit_cameras(n_views, W, H, max_deg=args.orbit_deg)
     mine = mv.shard_views(n_views, rank, world)
     bg = torch.zeros(3, device=dev)
 
@@ -225,13 +226,25 @@ def run_ours(args):
         cam_pinned[v] = buf
     arena = mv.GradArena(P, M, dev)
     stats = {}
+    av = mv.AsyncViews(n_views)
 
-    def step_resident():
+    def step_learn():
+        """first step: exact-size path, learns each view's num_rendered for the capacity hints"""
         arena.zero_()
         for v in mine:
             wt = wts_dev[v]
-            r = mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=args.flags)
+            r = mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=args.flags, capacity=0)
             stats["N"], stats["radii"] = r.num_rendered, r.radii
+            av.learn(v, r.num_rendered)
+        arena.all_reduce()
+
+    def step_resident():
+        """steady state: nothing blocks the host (GSR_FLAG_ASYNC); overflow is checked after the timed region"""
+        arena.zero_()
+        for v in mine:
+            wt = wts_dev[v]
+            mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=args.flags,
+                                 capacity=av.capacity(v), async_result=av.slot(v))
         arena.all_reduce()
 
     cam_stage = torch.empty(35, device=dev)
@@ -248,10 +261,13 @@ def run_ours(args):
                                                scale_modifier=1.0, viewmatrix=cam_stage[:16].view(4, 4),
                                                projmatrix=cam_stage[16:32].view(4, 4), sh_degree=D, campos=cam_stage[32:35],
                                                prefiltered=False)
-            res = mv.cuda_view_fwd_bwd(gauss, rs, lambda col: wt_stage, arena, flags=args.flags)
+            res = mv.cuda_view_fwd_bwd(gauss, rs, lambda col: wt_stage, arena, flags=args.flags,
+                                       capacity=av.capacity(v), async_result=av.slot(v))
             loss = loss + (res.color * wt_stage).sum()
         arena.all_reduce()
-        return float(loss.item())                                          # D2H: the step's result
+        out = float(loss.item())                                           # D2H: the step's result (syncs)
+        assert not av.check(mine), "capacity overflow inside the timed region"
+        return out
     h2d = len(mine) * (35 * 4 + 3 * H * W * 4)
     d2h = 4 + len(mine) * 4   # loss scalar + num_rendered per view
 
@@ -274,24 +290,31 @@ def run_ours(args):
         return float(ms.item())
 
     # ---- warm-up ----
+    step_learn()
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
+    assert not av.check(mine)
     V = int((stats["radii"] > 0).sum().item())
     N = int(stats["N"])
 
-    # ---- timed: resident ----
+    # ---- timed: resident (the headline `value`) ----
     sampler = ClockSampler(local)
     sampler.start()
-    _C.profile_enable(True)
-    _C.profile_collect()
     l0 = _C.kernel_launches()
     ms_total = timed(step_resident, args.steps)
     launches = _C.kernel_launches() - l0
-    _C.profile_enable(False)
-    stage_ms, stage_cnt = _C.profile_collect()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    assert not av.check(mine), "capacity overflow inside the timed region"
+
+    # ---- the same loop once more with the stage profiler on: CUDA events on the launching stream
+    #      around every kernel stage (events between kernels cost a few %, so it is a separate pass) ----
+    _C.profile_enable(True)
+    _C.profile_collect()
+    ms_prof = timed(step_resident, args.steps)
+    _C.profile_enable(False)
+    stage_ms, stage_cnt = _C.profile_collect()
 
     # ---- timed: end to end ----
     for _ in range(2):
@@ -330,12 +353,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "P": P, "V": V, "N": N,
+        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "P": P, "V": V, "N": N,
                    "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce",
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
+        "profiled_ms_per_step": ms_prof / args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": alg[dom],
                      "ms_per_launch": per_launch[dom],

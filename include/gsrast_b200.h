@@ -41,13 +41,15 @@ extern "C" {
                                      sort (Appendix A.3/A.4).  Default (0) is the two-level scheme:
                                      depth-sort P Gaussians, emit in depth order, 2-pass tile sort.
                                      Both produce bit-identical point lists and tile ranges.          */
-#define GSR_FLAG_FAST_EXP      2u /* blend with ex2.approx instead of expf (off = parity build)   */
+#define GSR_FLAG_PRECISE       2u /* blend with the oracle's exact op order, expf and IEEE division
+                                     (parity build); default is ex2.approx / rcp.approx, ~2e-7 in colour */
 /* flag for gsr_backward: ADD the per-Gaussian parameter gradients (dL_dmean3D, dL_dsh, dL_dcolor,
  * dL_dopacity, dL_dcov3D, dL_dscale, dL_drot) into the output buffers instead of overwriting them, and
  * leave culled Gaussians untouched.  Used by the view-sharded multi-view step, where the outputs are
  * slices of one flat gradient arena summed over views and then all-reduced over ranks.
  * dL_dmean2D / dL_dconic stay per-view (densification reads the per-view norm, gaussian_model.py:483). */
 #define GSR_FLAG_ACCUMULATE    8u
+#define GSR_FLAG_ASYNC        16u /* gsr_forward: never block the host (see gsr_forward)           */
 
 /* Buffer grower, replaces `std::function<char*(size_t)>` of the reference core: must return a
  * device allocation of at least `bytes` bytes, 256-byte aligned, that stays alive until the
@@ -60,7 +62,19 @@ typedef char* (*gsr_alloc_fn)(void* user, size_t bytes);
  *         viewmatrix/projmatrix (4,4) as stored by scene/cameras.py:60-62 (column-major),
  *         cam_pos (3,), background (3,)
  * Out:    out_color (3,H,W)  out_depth (1,H,W) [median depth, 15.0f where none: gen_seq.py:50]
- *         radii (P,) int32  *num_rendered_host = number of (tile, Gaussian) instances          */
+ *         radii (P,) int32  *num_rendered_host = number of (tile, Gaussian) instances
+ *
+ * capacity_hint = 0: the binning buffer is sized exactly, which costs one host round trip in the
+ *   middle of the pipeline (the reference does the same: cudaMemcpy of point_offsets[P-1]).
+ * capacity_hint > 0 (an upper estimate of num_rendered, e.g. last frame's value + 25 %): binning
+ *   and blend are queued for that capacity BEFORE N is known -- every kernel reads N on the device
+ *   -- so the GPU never idles on the host; the call still returns the exact N and transparently
+ *   re-bins at the exact size in the rare case N > capacity_hint.
+ * GSR_FLAG_ASYNC (needs capacity_hint > 0): the call does not wait at all.  num_rendered_host must
+ *   then be PINNED host memory for two int64: [0] = N, [1] = status bits (low word: prefiltered
+ *   trap, high word: capacity overflow), valid after the caller synchronises the stream.  On
+ *   overflow the outputs are invalid and the caller must call again with a larger hint.
+ * The sorted point list always sits at offset 0 of the binning buffer.                            */
 int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_alloc_fn binning_alloc,
                 void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
                 const float* background, int width, int height, const float* means3D,
@@ -69,7 +83,7 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                 const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
                 float* out_color, float* out_depth, int32_t* radii, int64_t* num_rendered_host,
-                uint32_t flags);
+                int64_t capacity_hint, uint32_t flags);
 
 /* Replaces CudaRasterizer::Rasterizer::backward (called by rasterize_gaussians_backward).
  * dL_dpix (3,H,W).  Every output is fully WRITTEN (zeros for culled Gaussians), callers need not

@@ -24,8 +24,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgsrast_b200.so")
 
 FLAG_BINNING_KEY64 = 1
-FLAG_FAST_EXP = 2
+FLAG_PRECISE = 2
 FLAG_ACCUMULATE = 8
+FLAG_ASYNC = 16
 NUM_STAGES = 10
 STAGE_NAMES = ("preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward",
                "accum_clear", "blend_backward", "geom_backward")
@@ -54,7 +55,7 @@ _lib.gsr_version.restype = _i
 _lib.gsr_forward.restype = _i
 _lib.gsr_forward.argtypes = [_vp, _ALLOC_FN, _vp, _ALLOC_FN, _vp, _ALLOC_FN, _vp, _i, _i, _i, _vp, _i, _i,
                              _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _f, _f, _i,
-                             _vp, _vp, _vp, C.POINTER(_i64), _u32]
+                             _vp, _vp, _vp, _vp, _i64, _u32]
 _lib.gsr_backward_scratch_bytes.restype = _sz
 _lib.gsr_backward_scratch_bytes.argtypes = [_i]
 _lib.gsr_backward.restype = _i
@@ -135,9 +136,29 @@ class _Grower:
             return 0
 
 
+#: running high-water mark of num_rendered per device -> capacity hint of the next call, so that the
+#: binning + blend kernels are queued before N reaches the host (no GPU bubble).  GSR_SPECULATE=0
+#: restores the reference's exact-size behaviour (one mid-pipeline host round trip).
+_SPECULATE = os.environ.get("GSR_SPECULATE", "1") != "0"
+_hwm: dict = {}
+
+
+def capacity_hint(device) -> int:
+    h = _hwm.get(device.index, 0)
+    return int(h * 1.25) + 65536 if (h > 0 and _SPECULATE) else 0
+
+
+def _note_rendered(device, n: int):
+    _hwm[device.index] = max(int(n), int(_hwm.get(device.index, 0) * 0.97))
+
+
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
-                        image_width, sh, degree, campos, prefiltered, debug=False, flags=None):
+                        image_width, sh, degree, campos, prefiltered, debug=False, flags=None,
+                        capacity=None, async_result=None):
+    """`capacity` / `async_result` (extensions): with `async_result` (a pinned int64[2] tensor) the
+    call never blocks the host -- GSR_FLAG_ASYNC -- and returns num_rendered = -1; the caller reads
+    async_result after a stream sync ([0] = N must be <= capacity, [1] must be 0)."""
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     flags = DEFAULT_FLAGS if flags is None else int(flags)
@@ -166,13 +187,25 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         radii = torch.empty(P, dtype=torch.int32, device=dev)
         geom, binning, img = _Grower(dev), _Grower(dev), _Grower(dev)
         n = _i64(0)
+        if async_result is not None:
+            assert async_result.is_pinned() and async_result.dtype == torch.int64 and async_result.numel() >= 2
+            assert capacity is not None and capacity > 0
+            flags |= FLAG_ASYNC
+            n_ptr = async_result.data_ptr()
+        else:
+            n_ptr = C.addressof(n)
+            if capacity is None:
+                capacity = capacity_hint(dev)
         rc = _lib.gsr_forward(
             _stream(dev), geom.cb, None, binning.cb, None, img.cb, None, P, int(degree), M,
             _ptr(background), W, H, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity), _ptr(scales),
             float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
             _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
-            _ptr(out_color), _ptr(out_depth), _ptr(radii), C.byref(n), flags)
+            _ptr(out_color), _ptr(out_depth), _ptr(radii), n_ptr, int(capacity), flags)
         _check(rc, "rasterize_gaussians")
+    if async_result is not None:
+        return -1, out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
+    _note_rendered(dev, n.value)
     return int(n.value), out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
 
 
@@ -212,7 +245,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
             nscratch = int(_lib.gsr_backward_scratch_bytes(P))
             scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
             rc = _lib.gsr_backward(
-                _stream(dev), P, int(degree), M, int(R), _ptr(background), W, H, _ptr(means3D), _ptr(sh),
+                _stream(dev), P, int(degree), M, max(int(R), 0), _ptr(background), W, H, _ptr(means3D), _ptr(sh),
                 _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
                 _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy),
                 _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), _ptr(dL_dout_color),

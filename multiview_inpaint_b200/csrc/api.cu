@@ -113,20 +113,19 @@ static int key64_end_bit(int W, int H) {
 }
 
 BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags) {
+  // N is the CAPACITY the buffer is sized for.  The sorted list always lands at offset 0
+  // (point_list), so the backward never needs to know the capacity.
   BinningLayout L{};
   size_t off = 0;
   const size_t n = (size_t)(N > 0 ? N : 1);
   auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
   const bool k64 = key64(flags);
   const int end_bit = k64 ? key64_end_bit(W, H) : tile_bits(W, H);
-  const int passes = (end_bit + 7) / 8;
   const size_t kb = k64 ? 8 : 4;
-  // buffers a (emitted into) and b; the sorted result lands in b for odd pass counts, a for even
-  const size_t va = take(n * 4), vb = take(n * 4);
+  L.point_list = take(n * 4);
+  L.vals_alt = take(n * 4);
   L.keys_a = take(n * kb);
   L.keys_b = take(n * kb);
-  L.point_list = (passes & 1) ? vb : va;
-  L.vals_alt = (passes & 1) ? va : vb;
   L.temp_bytes = sort_temp_bytes(N, (int)kb, end_bit);
   L.temp = take(L.temp_bytes);
   L.bytes = off;
@@ -172,7 +171,15 @@ extern "C" {
 
 const char* gsr_last_error(void) { return g_last_error.c_str(); }
 uint64_t gsr_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
-void gsr_profile_enable(int on) { g_prof.on = on != 0; }
+void gsr_profile_enable(int on) {
+  g_prof.on = on != 0;
+  // create the event pool up front so that no cudaEventCreate lands inside a timed region
+  while (g_prof.on && g_prof.pool.size() < 8192) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) break;
+    g_prof.pool.push_back(e);
+  }
+}
 int gsr_profile_collect(double* ms_host, int64_t* counts_host) {
   if (!ms_host || !counts_host) return fail(GSR_E_INVALID, "gsr_profile_collect: null argument");
   for (size_t i = 0; i + 1 < g_prof.used; i++) {
@@ -226,7 +233,7 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
                 const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
                 const float* cam_pos, float tan_fovx, float tan_fovy, int prefiltered,
                 float* out_color, float* out_depth, int32_t* radii, int64_t* num_rendered_host,
-                uint32_t flags) {
+                int64_t capacity_hint, uint32_t flags) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (P < 0 || width <= 0 || height <= 0 || D < 0 || D > 3) return fail(GSR_E_INVALID, "gsr_forward: bad P/width/height/degree");
   if (!geom_alloc || !binning_alloc || !image_alloc || !out_color || !out_depth || !background ||
@@ -265,6 +272,9 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
 
   int64_t N = 0;
   const uint32_t* order = nullptr;
+  const bool async = (flags & GSR_FLAG_ASYNC) != 0;
+  int64_t* result = async ? num_rendered_host : pin.result;  // [0] = N, [1] = status bits
+  if (async && capacity_hint <= 0) return fail(GSR_E_INVALID, "gsr_forward: GSR_FLAG_ASYNC needs a capacity_hint");
   if (P > 0) {
     GSR_CUDA(cudaMemsetAsync(status, 0, 16, s), "memset status");
     uint32_t* depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(geom + gl.depth_keys);
@@ -284,72 +294,110 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       uint32_t* va = reinterpret_cast<uint32_t*>(geom + gl.order);
       uint32_t* kb = reinterpret_cast<uint32_t*>(geom + gl.depth_keys_alt);
       uint32_t* vb = reinterpret_cast<uint32_t*>(geom + gl.order_alt);
-      GSR_CUDA(launch_sort_pairs_u32(s, P, ka, nullptr, ka, va, kb, vb, 32, geom + gl.temp), "depth sort");
+      GSR_CUDA(launch_sort_pairs_u32(s, P, nullptr, ka, nullptr, ka, va, kb, vb, 32, geom + gl.temp), "depth sort");
       order = va;
       PROF(2);
       GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, order, offsets, geom + gl.temp), "scan");
     }
     PROF(-1);
-    // ---- the one host round trip per view (the reference has the same one) ----
-    pin.result[0] = 0;
-    pin.result[1] = 0;
-    GSR_CUDA(cudaMemcpyAsync(pin.result, offsets + (P - 1), 4, cudaMemcpyDeviceToHost, s), "memcpy num_rendered");
-    GSR_CUDA(cudaMemcpyAsync(pin.result + 1, status, 4, cudaMemcpyDeviceToHost, s), "memcpy status");
+  }
+  const uint32_t* n_dev = P > 0 ? offsets + (P - 1) : nullptr;
+
+  // ---- binning + blend for a given capacity; every kernel reads the true N on the device ----
+  char* bin = nullptr;
+  auto bin_and_blend = [&](int64_t cap) -> int {
+    const BinningLayout bl = binning_layout(cap, width, height, flags);
+    bin = binning_alloc(binning_user, bl.bytes);
+    if (!bin) return fail(GSR_E_ALLOC, "gsr_forward: binning buffer allocation failed");
+    uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
+    uint32_t* vals_alt = reinterpret_cast<uint32_t*>(bin + bl.vals_alt);
+    if (P > 0 && cap > 0) {
+      const int end_bit = k64 ? key64_end_bit(width, height) : tile_bits(width, height);
+      const int passes = (end_bit + 7) / 8;
+      // emit into "a"; with an even pass count the sorted result lands back in "a", with an odd
+      // one in "b" -- pick a so that the result is always point_list (offset 0)
+      uint32_t* va = (passes & 1) ? vals_alt : point_list;
+      uint32_t* valt = (passes & 1) ? va : vals_alt;
+      if (k64) {
+        uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
+        uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
+        PROF(3);
+        GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, va, cap, status), "duplicateWithKeys");
+        uint64_t* kout = (passes & 1) ? kb : ka;
+        uint64_t* kalt = (passes & 1) ? ka : kb;
+        PROF(4);
+        GSR_CUDA(launch_sort_pairs_u64(s, cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, bin + bl.temp), "sort");
+        PROF(5);
+        GSR_CUDA(launch_tile_ranges_u64(s, cap, n_dev, kout, G, ranges), "identifyTileRanges");
+      } else {
+        uint32_t* ka = reinterpret_cast<uint32_t*>(bin + bl.keys_a);
+        uint32_t* kb = reinterpret_cast<uint32_t*>(bin + bl.keys_b);
+        PROF(3);
+        GSR_CUDA(launch_duplicate_tiles(s, P, order, rec, offsets, radii, cam.grid_x, cam.grid_y, ka, va, cap, status), "duplicate (depth order)");
+        uint32_t* kout = (passes & 1) ? kb : ka;
+        uint32_t* kalt = (passes & 1) ? ka : kb;
+        PROF(4);
+        GSR_CUDA(launch_sort_pairs_u32(s, cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, bin + bl.temp), "tile sort");
+        PROF(5);
+        GSR_CUDA(launch_tile_ranges_u32(s, cap, n_dev, kout, G, ranges), "identifyTileRanges");
+      }
+    } else {
+      GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
+    }
+    PROF(6);
+    GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
+                                  out_depth, final_T, n_contrib, (flags & GSR_FLAG_PRECISE) != 0), "blend forward");
+    PROF(-1);
+    return 0;
+  };
+  auto fetch_result = [&]() -> int {  // N and the status word to (pinned) host memory, asynchronously
+    result[0] = 0;
+    result[1] = 0;
+    if (P > 0) {
+      GSR_CUDA(cudaMemcpyAsync(result, n_dev, 4, cudaMemcpyDeviceToHost, s), "memcpy num_rendered");
+      GSR_CUDA(cudaMemcpyAsync(result + 1, status, 8, cudaMemcpyDeviceToHost, s), "memcpy status");
+    }
+    return 0;
+  };
+
+  if (capacity_hint > 0 && capacity_hint < (1ll << 30)) {
+    // Speculative path: queue binning + blend for the hinted capacity BEFORE learning N, so the
+    // GPU never idles on the host.  The host then waits for N only (copied right after the scan,
+    // early in the queue) while the GPU keeps working, or does not wait at all (GSR_FLAG_ASYNC).
+    cudaEvent_t ev = nullptr;
+    if (!async) {
+      if (int rc = fetch_result()) return rc;
+      GSR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create");
+      GSR_CUDA(cudaEventRecord(ev, s), "event record");
+    }
+    if (int rc = bin_and_blend(capacity_hint)) { if (ev) cudaEventDestroy(ev); return rc; }
+    if (async) {
+      if (int rc = fetch_result()) return rc;   // includes the overflow bit set by the duplicate kernel
+      return 0;                                 // caller checks result[0] <= capacity_hint && result[1] == 0 after a sync
+    }
+    GSR_CUDA(cudaEventSynchronize(ev), "sync num_rendered");
+    cudaEventDestroy(ev);
+    N = (int64_t)(uint32_t)result[0];
+    if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
+    if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
+    if (N > capacity_hint) {  // rare: the hint was too small, redo binning + blend at the exact size
+      GSR_CUDA(cudaMemsetAsync(status + 1, 0, 4, s), "clear overflow");
+      if (int rc = bin_and_blend(N)) return rc;
+    }
+    *num_rendered_host = N;
+    return 0;
+  }
+
+  // Exact-size path (what the reference does): one host round trip mid-pipeline.
+  if (P > 0) {
+    if (int rc = fetch_result()) return rc;
     GSR_CUDA(cudaStreamSynchronize(s), "sync num_rendered");
-    N = (int64_t)(uint32_t)pin.result[0];
-    if ((int32_t)pin.result[1] != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
+    N = (int64_t)(uint32_t)result[0];
+    if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
     if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
   }
   *num_rendered_host = N;
-
-  const BinningLayout bl = binning_layout(N, width, height, flags);
-  char* bin = binning_alloc(binning_user, bl.bytes);
-  if (!bin) return fail(GSR_E_ALLOC, "gsr_forward: binning buffer allocation failed");
-  uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
-  uint32_t* vals_alt = reinterpret_cast<uint32_t*>(bin + bl.vals_alt);
-
-  if (N > 0) {
-    if (k64) {
-      const int end_bit = key64_end_bit(width, height);
-      const int passes = (end_bit + 7) / 8;
-      uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
-      uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
-      // emitted into "a" == the buffer that is NOT the final one for odd pass counts
-      uint32_t* va = (passes & 1) ? vals_alt : point_list;
-      uint32_t* vb = (passes & 1) ? point_list : vals_alt;
-      PROF(3);
-      GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, va), "duplicateWithKeys");
-      uint64_t* kout = (passes & 1) ? kb : ka;
-      uint64_t* kalt = (passes & 1) ? ka : kb;
-      PROF(4);
-      GSR_CUDA(launch_sort_pairs_u64(s, N, ka, va, kout, point_list, kalt, vals_alt, end_bit, bin + bl.temp), "sort");
-      (void)vb;
-      PROF(5);
-      GSR_CUDA(launch_tile_ranges_u64(s, N, kout, G, ranges), "identifyTileRanges");
-    } else {
-      const int end_bit = tile_bits(width, height);
-      const int passes = (end_bit + 7) / 8;
-      uint32_t* ka = reinterpret_cast<uint32_t*>(bin + bl.keys_a);
-      uint32_t* kb = reinterpret_cast<uint32_t*>(bin + bl.keys_b);
-      uint32_t* va = (passes & 1) ? vals_alt : point_list;
-      PROF(3);
-      GSR_CUDA(launch_duplicate_tiles(s, P, order, rec, offsets, radii, cam.grid_x, cam.grid_y, ka, va), "duplicate (depth order)");
-      uint32_t* kout = (passes & 1) ? kb : ka;
-      uint32_t* kalt = (passes & 1) ? ka : kb;
-      PROF(4);
-      GSR_CUDA(launch_sort_pairs_u32(s, N, ka, va, kout, point_list, kalt, vals_alt, end_bit, bin + bl.temp), "tile sort");
-      PROF(5);
-      GSR_CUDA(launch_tile_ranges_u32(s, N, kout, G, ranges), "identifyTileRanges");
-    }
-  } else {
-    GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
-  }
-
-  PROF(6);
-  GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
-                                out_depth, final_T, n_contrib, (flags & GSR_FLAG_FAST_EXP) != 0), "blend forward");
-  PROF(-1);
-  return 0;
+  return bin_and_blend(N);
 }
 
 int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const float* background,
@@ -372,8 +420,9 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   if (scratch_bytes < gsr_backward_scratch_bytes(P)) return fail(GSR_E_INVALID, "gsr_backward: scratch too small");
   if (shs && !dL_dsh) return fail(GSR_E_INVALID, "gsr_backward: dL_dsh missing");
   if ((reinterpret_cast<uintptr_t>(dL_drot) & 15) || (dL_dconic && (reinterpret_cast<uintptr_t>(dL_dconic) & 15)) ||
-      (reinterpret_cast<uintptr_t>(scratch) & 15) || (rotations && (reinterpret_cast<uintptr_t>(rotations) & 15)))
-    return fail(GSR_E_INVALID, "gsr_backward: dL_drot / dL_dconic / scratch / rotations must be 16-byte aligned");
+      (reinterpret_cast<uintptr_t>(scratch) & 15) || (rotations && (reinterpret_cast<uintptr_t>(rotations) & 15)) ||
+      (shs && (reinterpret_cast<uintptr_t>(shs) & 15)) || (dL_dsh && (reinterpret_cast<uintptr_t>(dL_dsh) & 15)))
+    return fail(GSR_E_INVALID, "gsr_backward: dL_drot / dL_dconic / dL_dsh / scratch / rotations / shs must be 16-byte aligned");
   const Camera cam = make_camera(width, height, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, scale_modifier);
 
   const GeomLayout gl = geom_layout(P, flags);
@@ -390,9 +439,10 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   PROF(7);
   GSR_CUDA(cudaMemsetAsync(gacc, 0, (size_t)P * 48, s), "memset accumulator");
   PROF(8);
-  if (num_rendered > 0)
-    GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
-                                   dL_dpix, gacc, (flags & GSR_FLAG_FAST_EXP) != 0), "blend backward");
+  // always launched: the tile ranges, not num_rendered, bound the work (num_rendered may be unknown
+  // to the host after an asynchronous forward)
+  GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
+                                   dL_dpix, gacc, (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
   PROF(9);
   GSR_CUDA(launch_geom_backward(s, P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp,
                                 colors_precomp, cam, rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
@@ -420,7 +470,7 @@ int gsr_sort_pairs_u64(void* stream, int64_t n, const uint64_t* keys_in, const u
   const size_t t0 = sort_temp_bytes(n, 8, end_bit);
   uint64_t* kalt = reinterpret_cast<uint64_t*>(temp + t0);
   uint32_t* valt = reinterpret_cast<uint32_t*>(temp + t0 + align_up((size_t)n * 8));
-  GSR_CUDA(launch_sort_pairs_u64(reinterpret_cast<cudaStream_t>(stream), n, keys_in, vals_in, keys_out, vals_out,
+  GSR_CUDA(launch_sort_pairs_u64(reinterpret_cast<cudaStream_t>(stream), n, nullptr, keys_in, vals_in, keys_out, vals_out,
                                  kalt, valt, end_bit, temp), "sort_pairs_u64");
   return 0;
 }
@@ -435,7 +485,7 @@ int gsr_sort_pairs_u32(void* stream, int64_t n, const uint32_t* keys_in, const u
   const size_t t0 = sort_temp_bytes(n, 4, end_bit);
   uint32_t* kalt = reinterpret_cast<uint32_t*>(temp + t0);
   uint32_t* valt = reinterpret_cast<uint32_t*>(temp + t0 + align_up((size_t)n * 4));
-  GSR_CUDA(launch_sort_pairs_u32(reinterpret_cast<cudaStream_t>(stream), n, keys_in, vals_in, keys_out, vals_out,
+  GSR_CUDA(launch_sort_pairs_u32(reinterpret_cast<cudaStream_t>(stream), n, nullptr, keys_in, vals_in, keys_out, vals_out,
                                  kalt, valt, end_bit, temp), "sort_pairs_u32");
   return 0;
 }

@@ -15,9 +15,11 @@ namespace gsr {
 __global__ void __launch_bounds__(256)
 duplicate_key64_kernel(int P, const float4* __restrict__ rec, const float* __restrict__ depths,
                        const uint32_t* __restrict__ offsets, const int32_t* __restrict__ radii,
-                       int gx, int gy, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                       int gx, int gy, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                       uint32_t cap, int32_t* __restrict__ status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
+  if (i == P - 1 && offsets[i] > cap) atomicExch(status + 1, 1);  // capacity overflow
   const int r = radii[i];
   if (r <= 0) return;
   uint32_t off = (i == 0) ? 0u : offsets[i - 1];
@@ -27,8 +29,10 @@ duplicate_key64_kernel(int P, const float4* __restrict__ rec, const float* __res
   const uint64_t dbits = __float_as_uint(depths[i]);
   for (int y = y0; y < y1; y++)
     for (int x = x0; x < x1; x++) {
-      keys[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
-      vals[off] = (uint32_t)i;
+      if (off < cap) {
+        keys[off] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
+        vals[off] = (uint32_t)i;
+      }
       off++;
     }
 }
@@ -38,9 +42,11 @@ duplicate_key64_kernel(int P, const float4* __restrict__ rec, const float* __res
 __global__ void __launch_bounds__(256)
 duplicate_tiles_kernel(int P, const uint32_t* __restrict__ order, const float4* __restrict__ rec,
                        const uint32_t* __restrict__ offsets, const int32_t* __restrict__ radii,
-                       int gx, int gy, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals) {
+                       int gx, int gy, uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals,
+                       uint32_t cap, int32_t* __restrict__ status) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= P) return;
+  if (k == P - 1 && offsets[k] > cap) atomicExch(status + 1, 1);  // capacity overflow
   const uint32_t i = order[k];
   const int r = radii[i];
   if (r <= 0) return;  // culled Gaussians carry key 0xFFFFFFFF and sit at the end of `order`
@@ -50,8 +56,10 @@ duplicate_tiles_kernel(int P, const uint32_t* __restrict__ order, const float4* 
   get_rect(q0.x, q0.y, r, gx, gy, x0, y0, x1, y1);
   for (int y = y0; y < y1; y++)
     for (int x = x0; x < x1; x++) {
-      tile_keys[off] = (uint32_t)(y * gx + x);
-      vals[off] = i;
+      if (off < cap) {
+        tile_keys[off] = (uint32_t)(y * gx + x);
+        vals[off] = i;
+      }
       off++;
     }
 }
@@ -63,7 +71,9 @@ template <> __device__ __forceinline__ uint32_t tile_of<uint32_t>(uint32_t k) { 
 
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(int64_t N, const KeyT* __restrict__ keys, uint2* __restrict__ ranges) {
+tile_ranges_kernel(int64_t cap, const uint32_t* __restrict__ n_dev, const KeyT* __restrict__ keys,
+                   uint2* __restrict__ ranges) {
+  const int64_t N = n_dev ? min((int64_t)*n_dev, cap) : cap;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N) return;
   const uint32_t cur = tile_of<KeyT>(keys[idx]);
@@ -81,31 +91,33 @@ tile_ranges_kernel(int64_t N, const KeyT* __restrict__ keys, uint2* __restrict__
 
 cudaError_t launch_duplicate_key64(cudaStream_t s, int P, const float4* rec, const float* depths,
                                    const uint32_t* offsets, const int32_t* radii, int grid_x,
-                                   int grid_y, uint64_t* keys, uint32_t* vals) {
+                                   int grid_y, uint64_t* keys, uint32_t* vals, int64_t cap, int32_t* status) {
   if (P == 0) return cudaSuccess;
-  duplicate_key64_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, rec, depths, offsets, radii, grid_x, grid_y, keys, vals);
+  duplicate_key64_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, rec, depths, offsets, radii, grid_x, grid_y, keys, vals,
+                                                      (uint32_t)cap, status);
   count_launch();
   return cudaGetLastError();
 }
 cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order, const float4* rec,
                                    const uint32_t* offsets, const int32_t* radii, int grid_x,
-                                   int grid_y, uint32_t* tile_keys, uint32_t* vals) {
+                                   int grid_y, uint32_t* tile_keys, uint32_t* vals, int64_t cap, int32_t* status) {
   if (P == 0) return cudaSuccess;
-  duplicate_tiles_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, order, rec, offsets, radii, grid_x, grid_y, tile_keys, vals);
+  duplicate_tiles_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, order, rec, offsets, radii, grid_x, grid_y, tile_keys, vals,
+                                                      (uint32_t)cap, status);
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t N, const uint64_t* keys, int G, uint2* ranges) {
+cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t N, const uint32_t* n_dev, const uint64_t* keys, int G, uint2* ranges) {
   cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s);
   if (e != cudaSuccess || N == 0) return e;
-  tile_ranges_kernel<uint64_t><<<cdiv(N, 256), 256, 0, s>>>(N, keys, ranges);
+  tile_ranges_kernel<uint64_t><<<cdiv(N, 256), 256, 0, s>>>(N, n_dev, keys, ranges);
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t N, const uint32_t* keys, int G, uint2* ranges) {
+cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t N, const uint32_t* n_dev, const uint32_t* keys, int G, uint2* ranges) {
   cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s);
   if (e != cudaSuccess || N == 0) return e;
-  tile_ranges_kernel<uint32_t><<<cdiv(N, 256), 256, 0, s>>>(N, keys, ranges);
+  tile_ranges_kernel<uint32_t><<<cdiv(N, 256), 256, 0, s>>>(N, n_dev, keys, ranges);
   count_launch();
   return cudaGetLastError();
 }

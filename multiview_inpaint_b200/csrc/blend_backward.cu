@@ -17,7 +17,9 @@
 //       [5..7] dL/dconic (xx, xy, yy)               [8] dL/dopacity
 //     dL/dmean2D = -(cx A + cy B) * W/2, -(cz B + cy A) * H/2 is formed once per Gaussian in K8/K9
 //     (cx,cy,cz are per-Gaussian constants, so this is the same sum the reference accumulates).
-#include "common.cuh"
+// Like K6 the kernel is instruction-issue bound; the default (non-PRECISE) flavour replaces the
+// two IEEE divisions per pair by one rcp.approx and expf by ex2.approx (blend_common.cuh).
+#include "blend_common.cuh"
 
 namespace gsr {
 
@@ -27,11 +29,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// Reduces v[0..7] over the warp; on return lane l holds the total of value index (l >> 2).
-__device__ __forceinline__ float warp_transpose_reduce8(const float v[8], int lane) {
+// Reduces v0..v7 over the warp; on return lane l holds the total of value index (l >> 2).
+__device__ __forceinline__ float warp_transpose_reduce8(float v0, float v1, float v2, float v3,
+                                                        float v4, float v5, float v6, float v7, int lane) {
   const bool h16 = lane & 16;
-  float a0 = h16 ? v[4] : v[0], a1 = h16 ? v[5] : v[1], a2 = h16 ? v[6] : v[2], a3 = h16 ? v[7] : v[3];
-  const float b0 = h16 ? v[0] : v[4], b1 = h16 ? v[1] : v[5], b2 = h16 ? v[2] : v[6], b3 = h16 ? v[3] : v[7];
+  float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
+  const float b0 = h16 ? v0 : v4, b1 = h16 ? v1 : v5, b2 = h16 ? v2 : v6, b3 = h16 ? v3 : v7;
   a0 += __shfl_xor_sync(0xffffffffu, b0, 16);
   a1 += __shfl_xor_sync(0xffffffffu, b1, 16);
   a2 += __shfl_xor_sync(0xffffffffu, b2, 16);
@@ -50,19 +53,18 @@ __device__ __forceinline__ float warp_transpose_reduce8(const float v[8], int la
   return e0;
 }
 
-template <bool FAST_EXP>
+template <bool PRECISE>
 __global__ void __launch_bounds__(256)
 blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                       const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
                       const float* __restrict__ bg, const float* __restrict__ final_T,
                       const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
                       float* __restrict__ gacc) {
-  __shared__ float4 s_q0[256];
-  __shared__ float4 s_q1[256];
-  __shared__ float4 s_q2[256];
-  __shared__ uint32_t s_id[256];
-  __shared__ uint32_t s_mask[8][8];
+  __shared__ __align__(16) unsigned char s_entries[BLEND_BATCH * ENTRY_BYTES];
+  __shared__ uint32_t s_mask_arr[64];
   __shared__ uint32_t s_wmax[8];
+  const uint32_t s_ent = (uint32_t)__cvta_generic_to_shared(s_entries);
+  const uint32_t s_mask = (uint32_t)__cvta_generic_to_shared(s_mask_arr);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -86,6 +88,7 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
     dLp2 = __ldg(dL_dpix + 2 * HW + pix);
   }
   const float bg_dot = FMA(__ldg(bg + 2), dLp2, FMA(__ldg(bg + 1), dLp1, MUL(__ldg(bg + 0), dLp0)));
+  const float neg_Tf_bg = -T_final * bg_dot;
   float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;   // accum_rec
   float lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;      // last_color
   float last_alpha = 0.0f;
@@ -97,98 +100,76 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
 #pragma unroll
   for (int w = 0; w < 8; w++) cta_last = max(cta_last, s_wmax[w]);
   if (cta_last == 0) return;  // nothing contributed anywhere in this tile (uniform exit)
-  const int nb = (int)((cta_last + 255) / 256);
+  const int nb = (int)((cta_last + BLEND_BATCH - 1) / BLEND_BATCH);
 
   for (int b = nb - 1; b >= 0; b--) {
-    __syncthreads();  // WAR on the staging buffers
-    const uint32_t pos = (uint32_t)b * 256 + tid;
-    uint32_t bits = 0;
-    if (pos < cta_last) {
-      const uint32_t id = point_list[range.x + pos];
-      const float4 q0 = __ldg(rec + 3 * (size_t)id);
-      const float4 q1 = __ldg(rec + 3 * (size_t)id + 1);
-      const float4 q2 = __ldg(rec + 3 * (size_t)id + 2);
-      s_q0[tid] = q0;
-      s_q1[tid] = q1;
-      s_q2[tid] = q2;
-      s_id[tid] = id;
-      const float xlo = q0.x - q1.z, xhi = q0.x + q1.z, ylo = q0.y - q1.w, yhi = q0.y + q1.w;
-      const float tx = (float)tile_x0, ty = (float)tile_y0;
-      const uint32_t cx = ((xhi >= tx && xlo <= tx + 7.0f) ? 1u : 0u) |
-                          ((xhi >= tx + 8.0f && xlo <= tx + 15.0f) ? 2u : 0u);
-      uint32_t cy = 0;
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-        cy |= (yhi >= ty + 4.0f * r && ylo <= ty + 4.0f * r + 3.0f) ? (1u << r) : 0u;
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-        if (cy & (1u << r)) bits |= cx << (2 * r);
-    }
-#pragma unroll
-    for (int v = 0; v < 8; v++) {
-      const unsigned m = __ballot_sync(0xffffffffu, (bits >> v) & 1u);
-      if (lane == 0) s_mask[v][warp] = m;
-    }
+    __syncthreads();  // WAR on the staging buffer
+    const uint32_t pos = (uint32_t)b * BLEND_BATCH + tid;
+    const uint32_t bits = stage_entry<PRECISE>(pos < cta_last, range.x + pos, point_list, rec,
+                                               s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
+    publish_masks(bits, s_mask, warp, lane);
     __syncthreads();
 
-    if (warp_last > (uint32_t)b * 256) {
+    if (warp_last > (uint32_t)b * BLEND_BATCH) {
 #pragma unroll 1
       for (int ws = 7; ws >= 0; ws--) {
-        unsigned m = s_mask[warp][ws];
-        const uint32_t gbase = (uint32_t)b * 256 + ws * 32;
+        unsigned m = lds32(s_mask + (warp * 8 + ws) * 4);
+        const uint32_t gbase = (uint32_t)b * BLEND_BATCH + ws * 32;
         if (gbase >= warp_last) continue;
         if (warp_last - gbase < 32) m &= (1u << (warp_last - gbase)) - 1;  // entries >= warp_last
+        const uint32_t ebase = s_ent + ws * 32 * ENTRY_BYTES;
         while (m) {
           const int j = 31 - __clz(m);
           m &= ~(1u << j);
-          const int e = ws * 32 + j;
+          const uint32_t ea = ebase + j * ENTRY_BYTES;
           const uint32_t epos = gbase + j;  // 0-based list position == contributor index
-          const float4 q0 = s_q0[e];
-          const float4 q1 = s_q1[e];
-          const float4 q2 = s_q2[e];
-          const float dx = SUB(q0.x, pxf), dy = SUB(q0.y, pyf);
-          const float q = FMA(MUL(q1.x, dy), dy, MUL(MUL(q0.z, dx), dx));
-          const float power = FMA(-0.5f, q, -MUL(MUL(q0.w, dx), dy));
-          bool contrib = (epos < last) && !(power > 0.0f || power < q2.w);
+          const float4 e0 = lds128(ea);
+          const float4 e1 = lds128(ea + 16);
+          float dx, dy;
+          const float power = pair_power<PRECISE>(e0, e1, pxf, pyf, dx, dy);
+          bool contrib = (epos < last) && !(power > 0.0f || power < e1.z);
           float G = 0.0f, alpha = 0.0f;
           if (contrib) {
-            G = FAST_EXP ? __expf(power) : expf(power);
-            alpha = fminf(0.99f, MUL(q1.y, G));
+            G = pair_gauss<PRECISE>(power);
+            alpha = fminf(0.99f, MUL(e1.y, G));
             contrib = !(alpha < 1.0f / 255.0f);
           }
           if (!__any_sync(0xffffffffu, contrib)) continue;
 
-          float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          float v8 = 0.0f;
-          if (contrib) {
-            const float one_m_alpha = SUB(1.0f, alpha);
-            T = DIV(T, one_m_alpha);
-            const float dch = MUL(alpha, T);
-            acc0 = FMA(last_alpha, lc0, MUL(SUB(1.0f, last_alpha), acc0));
-            acc1 = FMA(last_alpha, lc1, MUL(SUB(1.0f, last_alpha), acc1));
-            acc2 = FMA(last_alpha, lc2, MUL(SUB(1.0f, last_alpha), acc2));
-            lc0 = q2.x; lc1 = q2.y; lc2 = q2.z;
-            float dL_dalpha = MUL(SUB(q2.x, acc0), dLp0);
-            dL_dalpha = FMA(SUB(q2.y, acc1), dLp1, dL_dalpha);
-            dL_dalpha = FMA(SUB(q2.z, acc2), dLp2, dL_dalpha);
-            v[0] = MUL(dch, dLp0);
-            v[1] = MUL(dch, dLp1);
-            v[2] = MUL(dch, dLp2);
-            dL_dalpha = MUL(dL_dalpha, T);
-            last_alpha = alpha;
-            dL_dalpha = FMA(DIV(-T_final, one_m_alpha), bg_dot, dL_dalpha);
-            const float dL_dG = MUL(q1.y, dL_dalpha);
-            const float gdx = MUL(G, dx), gdy = MUL(G, dy);
-            v[3] = MUL(dL_dG, gdx);
-            v[4] = MUL(dL_dG, gdy);
-            v[5] = MUL(MUL(MUL(-0.5f, gdx), dx), dL_dG);
-            v[6] = MUL(MUL(MUL(-0.5f, gdx), dy), dL_dG);
-            v[7] = MUL(MUL(MUL(-0.5f, gdy), dy), dL_dG);
-            v8 = MUL(G, dL_dalpha);
+          const float4 e2 = lds128(ea + 32);
+          // per-lane partials; lanes that do not contribute add exact zeros
+          const float one_m_alpha = SUB(1.0f, alpha);
+          float Tn, dchT;  // new T, and -T_final/(1-alpha)*bg_dot
+          if (PRECISE) {
+            Tn = DIV(T, one_m_alpha);
+            dchT = MUL(DIV(-T_final, one_m_alpha), bg_dot);
+          } else {
+            const float inv = rcp_approx(one_m_alpha);
+            Tn = T * inv;
+            dchT = neg_Tf_bg * inv;
           }
-          const float r8 = warp_transpose_reduce8(v, lane);
-          const float r1 = warp_sum(v8);
-          float* dst = gacc + (size_t)s_id[e] * 12;
+          const float dch = contrib ? MUL(alpha, Tn) : 0.0f;
+          const float na0 = FMA(last_alpha, lc0, MUL(SUB(1.0f, last_alpha), acc0));
+          const float na1 = FMA(last_alpha, lc1, MUL(SUB(1.0f, last_alpha), acc1));
+          const float na2 = FMA(last_alpha, lc2, MUL(SUB(1.0f, last_alpha), acc2));
+          float dL_dalpha = MUL(SUB(e2.x, na0), dLp0);
+          dL_dalpha = FMA(SUB(e2.y, na1), dLp1, dL_dalpha);
+          dL_dalpha = FMA(SUB(e2.z, na2), dLp2, dL_dalpha);
+          dL_dalpha = FMA(dL_dalpha, Tn, dchT);
+          if (contrib) {
+            T = Tn;
+            acc0 = na0; acc1 = na1; acc2 = na2;
+            lc0 = e2.x; lc1 = e2.y; lc2 = e2.z;
+            last_alpha = alpha;
+          } else {
+            dL_dalpha = 0.0f;
+          }
+          const float w = MUL(MUL(e1.y, dL_dalpha), G);  // dL_dG * G
+          const float wx = MUL(w, dx), wy = MUL(w, dy);
+          const float r8 = warp_transpose_reduce8(MUL(dch, dLp0), MUL(dch, dLp1), MUL(dch, dLp2), wx, wy,
+                                                  MUL(-0.5f * dx, wx), MUL(-0.5f * dy, wx), MUL(-0.5f * dy, wy), lane);
+          const float r1 = warp_sum(MUL(G, dL_dalpha));
+          float* dst = gacc + (size_t)__float_as_uint(e1.w) * 12;
           if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), r8);
           if (lane == 1) atomicAdd(dst + 8, r1);
         }
@@ -200,10 +181,10 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
 cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ranges,
                                   const uint32_t* point_list, const float4* rec, const float* bg,
                                   const float* final_T, const uint32_t* n_contrib,
-                                  const float* dL_dpix, float* gacc, bool fast_exp) {
+                                  const float* dL_dpix, float* gacc, bool precise) {
   const int gx = cdiv(W, TILE_X), gy = cdiv(H, TILE_Y);
   if (gx * gy == 0) return cudaSuccess;
-  if (fast_exp)
+  if (precise)
     blend_backward_kernel<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
                                                         n_contrib, dL_dpix, gacc);
   else

@@ -3,35 +3,37 @@
 // Restates SURVEY.md Appendix A.5.  The depth sentinel 15.0f and the (1,H,W) depth output are
 // pinned by the reference callers gs-simp/gen_seq.py:50, vis_render.py:45, render_depth.py:37.
 //
-// B200 design (differs from the public kernel, same per-pixel arithmetic and order):
+// B200 design (differs from the public kernel, same per-pixel recurrence and order):
 //   * one CTA = one tile = 8 warps; warp w owns an 8x4 pixel sub-tile, so a warp is a compact
 //     screen-space box and can be culled as a unit;
-//   * the tile's list is staged 256 entries at a time into shared memory as the 48-byte blend
+//   * the tile's list is staged 256 entries at a time into shared memory from the 48-byte blend
 //     records written by K1 (3 x LDG.128 per entry, 2 sectors);
 //   * while staging, each thread tests its Gaussian's alpha>=1/255 bounding box against the eight
 //     sub-tiles and the CTA publishes, per warp, a 256-bit "touches my sub-tile" mask (ballots);
 //     a warp then walks only the set bits (warp-uniform loop, no divergence on the skip);
 //   * the exp is only evaluated for pairs whose power is above the Gaussian's cut-off.
-//   Both culls are conservative (GSR_POWER_SLACK), i.e. they only drop pairs the reference would
-//   have dropped with `alpha < 1/255`, so n_contrib / final_T / colour / depth are unchanged.
+//   Both culls are conservative (GSR_POWER_SLACK): they only drop pairs the reference would have
+//   dropped with `alpha < 1/255`, so n_contrib / final_T / colour / depth are unchanged.
 //   * saturated pixels: per-lane `done`, warp-level __all_sync to stop walking, CTA-level
 //     __syncthreads_and to stop staging (the reference's __syncthreads_count early exit).
-#include "common.cuh"
+// The kernel is instruction-issue bound (ncu: issue slots ~89 % busy, DRAM ~1 %), so the inner
+// loop is written for instruction count: 2 x LDS.128 + 5 FP + EX2 before the alpha test, the
+// colour float4 only for contributing lanes (see blend_common.cuh).
+#include "blend_common.cuh"
 
 namespace gsr {
 
-template <bool FAST_EXP>
+template <bool PRECISE>
 __global__ void __launch_bounds__(256)
 blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                      const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
                      const float* __restrict__ depths, const float* __restrict__ bg,
                      float* __restrict__ out_color, float* __restrict__ out_depth,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
-  __shared__ float4 s_q0[256];
-  __shared__ float4 s_q1[256];
-  __shared__ float4 s_q2[256];
-  __shared__ uint32_t s_id[256];
-  __shared__ uint32_t s_mask[8][8];  // [target warp][staging warp]
+  __shared__ __align__(16) unsigned char s_entries[BLEND_BATCH * ENTRY_BYTES];
+  __shared__ uint32_t s_mask_arr[64];  // [target warp][staging warp]
+  const uint32_t s_ent = (uint32_t)__cvta_generic_to_shared(s_entries);
+  const uint32_t s_mask = (uint32_t)__cvta_generic_to_shared(s_mask_arr);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -43,81 +45,52 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
 
   const uint2 range = ranges[tile];
   const int todo = (int)(range.y - range.x);
-  const int rounds = (todo + 255) / 256;
+  const int rounds = (todo + BLEND_BATCH - 1) / BLEND_BATCH;
 
   float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dm = 15.0f;
   uint32_t last = 0;
   bool done = !inside;
 
   for (int b = 0; b < rounds; b++) {
-    // all pixels of the tile saturated -> stop (also the WAR barrier for the staging buffers)
+    // all pixels of the tile saturated -> stop (also the WAR barrier for the staging buffer)
     if (__syncthreads_and(done)) break;
-
-    // ---- stage 256 list entries + cull masks ----
-    const int pos = b * 256 + tid;
-    uint32_t bits = 0;
-    if (pos < todo) {
-      const uint32_t id = point_list[range.x + pos];
-      const float4 q0 = __ldg(rec + 3 * (size_t)id);
-      const float4 q1 = __ldg(rec + 3 * (size_t)id + 1);
-      const float4 q2 = __ldg(rec + 3 * (size_t)id + 2);
-      s_q0[tid] = q0;
-      s_q1[tid] = q1;
-      s_q2[tid] = q2;
-      s_id[tid] = id;
-      // bounding box of {alpha >= 1/255} : [x - hx, x + hx] x [y - hy, y + hy]
-      const float xlo = q0.x - q1.z, xhi = q0.x + q1.z, ylo = q0.y - q1.w, yhi = q0.y + q1.w;
-      const float tx = (float)tile_x0, ty = (float)tile_y0;
-      const uint32_t cx = ((xhi >= tx && xlo <= tx + 7.0f) ? 1u : 0u) |
-                          ((xhi >= tx + 8.0f && xlo <= tx + 15.0f) ? 2u : 0u);
-      uint32_t cy = 0;
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-        cy |= (yhi >= ty + 4.0f * r && ylo <= ty + 4.0f * r + 3.0f) ? (1u << r) : 0u;
-      // warp v = (row r)*2 + col c
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-        if (cy & (1u << r)) bits |= cx << (2 * r);
-    }
-#pragma unroll
-    for (int v = 0; v < 8; v++) {
-      const unsigned m = __ballot_sync(0xffffffffu, (bits >> v) & 1u);
-      if (lane == 0) s_mask[v][warp] = m;
-    }
+    const int pos = b * BLEND_BATCH + tid;
+    const uint32_t bits = stage_entry<PRECISE>(pos < todo, range.x + pos, point_list, rec,
+                                               s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
+    publish_masks(bits, s_mask, warp, lane);
     __syncthreads();
 
     // ---- walk the entries that can touch this warp's sub-tile ----
     if (!__all_sync(0xffffffffu, done)) {
 #pragma unroll 1
       for (int ws = 0; ws < 8; ws++) {
-        unsigned m = s_mask[warp][ws];
+        unsigned m = lds32(s_mask + (warp * 8 + ws) * 4);
+        const uint32_t ebase = s_ent + ws * 32 * ENTRY_BYTES;
         while (m) {
           const int j = __ffs(m) - 1;
           m &= m - 1;
-          if (done) continue;
-          const int e = ws * 32 + j;
-          const float4 q0 = s_q0[e];
-          const float4 q1 = s_q1[e];
-          const float4 q2 = s_q2[e];
-          const float dx = SUB(q0.x, pxf), dy = SUB(q0.y, pyf);
-          const float q = FMA(MUL(q1.x, dy), dy, MUL(MUL(q0.z, dx), dx));
-          const float power = FMA(-0.5f, q, -MUL(MUL(q0.w, dx), dy));
-          if (power > 0.0f || power < q2.w) continue;
-          const float G = FAST_EXP ? __expf(power) : expf(power);
-          const float alpha = fminf(0.99f, MUL(q1.y, G));
+          const uint32_t ea = ebase + j * ENTRY_BYTES;
+          const float4 e0 = lds128(ea);
+          const float4 e1 = lds128(ea + 16);
+          float dx, dy;
+          const float power = pair_power<PRECISE>(e0, e1, pxf, pyf, dx, dy);
+          if (done || power > 0.0f || power < e1.z) continue;
+          const float G = pair_gauss<PRECISE>(power);
+          const float alpha = fminf(0.99f, MUL(e1.y, G));
           if (alpha < 1.0f / 255.0f) continue;
           const float test_T = MUL(T, SUB(1.0f, alpha));
           if (test_T < 0.0001f) {
             done = true;
             continue;
           }
+          const float4 e2 = lds128(ea + 32);
           const float wgt = MUL(alpha, T);
-          C0 = FMA(q2.x, wgt, C0);
-          C1 = FMA(q2.y, wgt, C1);
-          C2 = FMA(q2.z, wgt, C2);
-          if (T > 0.5f && test_T < 0.5f) Dm = __ldg(depths + s_id[e]);  // median depth
+          C0 = FMA(e2.x, wgt, C0);
+          C1 = FMA(e2.y, wgt, C1);
+          C2 = FMA(e2.z, wgt, C2);
+          if (T > 0.5f && test_T < 0.5f) Dm = __ldg(depths + __float_as_uint(e1.w));  // median depth
           T = test_T;
-          last = (uint32_t)(b * 256 + e + 1);
+          last = (uint32_t)(b * BLEND_BATCH + ws * 32 + j + 1);
         }
       }
     }
@@ -138,10 +111,10 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
 cudaError_t launch_blend_forward(cudaStream_t s, int W, int H, const uint2* ranges,
                                  const uint32_t* point_list, const float4* rec, const float* depths,
                                  const float* bg, float* out_color, float* out_depth,
-                                 float* final_T, uint32_t* n_contrib, bool fast_exp) {
+                                 float* final_T, uint32_t* n_contrib, bool precise) {
   const int gx = cdiv(W, TILE_X), gy = cdiv(H, TILE_Y);
   if (gx * gy == 0) return cudaSuccess;
-  if (fast_exp)
+  if (precise)
     blend_forward_kernel<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, depths, bg,
                                                        out_color, out_depth, final_T, n_contrib);
   else

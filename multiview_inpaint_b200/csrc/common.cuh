@@ -133,31 +133,36 @@ size_t scan_temp_bytes(int64_t n);
 cudaError_t launch_inclusive_scan(cudaStream_t s, int64_t n, const uint32_t* in,
                                   const uint32_t* gather, uint32_t* out, char* temp);
 size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit);
-// vals_in may be NULL: values are then the element indices 0..n-1
-cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* keys_in,
+// vals_in may be NULL: values are then the element indices 0..n-1.
+// n_dev may be NULL; otherwise the element count is min(*n_dev, n) read on the device and `n` only
+// sizes the grid and the temp storage (capacity).
+cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint32_t* keys_in,
                                   const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                                   uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
-cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint64_t* keys_in,
+cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
 
+// `cap` = capacity of the key/value arrays: instances beyond it are dropped and status[1] is set
+// (the host then re-runs the binning with a larger buffer).
 cudaError_t launch_duplicate_key64(cudaStream_t s, int P, const float4* rec, const float* depths,
                                    const uint32_t* offsets, const int32_t* radii, int grid_x,
-                                   int grid_y, uint64_t* keys, uint32_t* vals);
+                                   int grid_y, uint64_t* keys, uint32_t* vals, int64_t cap, int32_t* status);
 cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order, const float4* rec,
                                    const uint32_t* offsets, const int32_t* radii, int grid_x,
-                                   int grid_y, uint32_t* tile_keys, uint32_t* vals);
-cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t N, const uint64_t* keys, int G, uint2* ranges);
-cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t N, const uint32_t* keys, int G, uint2* ranges);
+                                   int grid_y, uint32_t* tile_keys, uint32_t* vals, int64_t cap, int32_t* status);
+// N = min(*n_dev, cap) when n_dev is given, else cap
+cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t cap, const uint32_t* n_dev, const uint64_t* keys, int G, uint2* ranges);
+cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t cap, const uint32_t* n_dev, const uint32_t* keys, int G, uint2* ranges);
 
 cudaError_t launch_blend_forward(cudaStream_t s, int W, int H, const uint2* ranges,
                                  const uint32_t* point_list, const float4* rec, const float* depths,
                                  const float* bg, float* out_color, float* out_depth,
-                                 float* final_T, uint32_t* n_contrib, bool fast_exp);
+                                 float* final_T, uint32_t* n_contrib, bool precise);
 cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ranges,
                                   const uint32_t* point_list, const float4* rec, const float* bg,
                                   const float* final_T, const uint32_t* n_contrib,
-                                  const float* dL_dpix, float* gacc /*[P][12]*/, bool fast_exp);
+                                  const float* dL_dpix, float* gacc /*[P][12]*/, bool precise);
 cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const float* means3D,
                                  const int32_t* radii, const float* shs, const uint8_t* clamped,
                                  const float* scales, const float* rotations,

@@ -147,8 +147,10 @@ size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
 
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-rs_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int end_bit, uint32_t* __restrict__ hist) {
+rs_histogram_kernel(const KeyT* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ n_dev,
+                    int end_bit, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_h[RS_MAX_PASSES * RS_RADIX];
+  const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
   const int passes = (end_bit + 7) / 8;
   for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x) s_h[i] = 0;
   __syncthreads();
@@ -200,10 +202,15 @@ __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift, uint32_t mask) {
 template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                   KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
-                   int shift, int nbits, const uint32_t* __restrict__ global_base,
-                   volatile uint32_t* status, uint32_t* ticket) {
+                   KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
+                   const uint32_t* __restrict__ n_dev, int shift, int nbits,
+                   const uint32_t* __restrict__ global_base, volatile uint32_t* status,
+                   uint32_t* ticket) {
   constexpr int TILE = RS_THREADS * ITEMS;
+  // the element count may live on the device (no host round trip): grid is sized by capacity and
+  // surplus CTAs retire before taking a ticket
+  const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+  if ((int64_t)blockIdx.x * TILE >= n) return;
   extern __shared__ __align__(16) unsigned char rs_smem[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                  // [TILE]
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * TILE);    // [TILE]
@@ -321,7 +328,7 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
 }
 
 template <typename KeyT>
-static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const KeyT* keys_in,
+static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_dev, const KeyT* keys_in,
                                    const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out,
                                    KeyT* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
   if (n <= 0) return cudaSuccess;
@@ -338,7 +345,7 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const KeyT* keys_i
 
   int hist_blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
   if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-  rs_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys_in, n, end_bit, hist);
+  rs_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys_in, n, n_dev, end_bit, hist);
   rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
   count_launch(2 + passes);
 
@@ -358,7 +365,7 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const KeyT* keys_i
     uint32_t* vout = to_out ? vals_out : vals_alt;
     const int bits = (end_bit - 8 * p) < 8 ? (end_bit - 8 * p) : 8;
     rs_onesweep_kernel<KeyT, ITEMS><<<(unsigned)tiles, RS_THREADS, smem, s>>>(
-        kin, vin, kout, vout, n, 8 * p, bits, hist + p * RS_RADIX,
+        kin, vin, kout, vout, n, n_dev, 8 * p, bits, hist + p * RS_RADIX,
         status + (size_t)p * tiles * RS_RADIX, tickets + p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -368,15 +375,15 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const KeyT* keys_i
   return cudaSuccess;
 }
 
-cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* keys_in,
+cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint32_t* keys_in,
                                   const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                                   uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
-  return sort_pairs_impl<uint32_t>(s, n, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp);
+  return sort_pairs_impl<uint32_t>(s, n, n_dev, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp);
 }
-cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint64_t* keys_in,
+cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
-  return sort_pairs_impl<uint64_t>(s, n, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp);
+  return sort_pairs_impl<uint64_t>(s, n, n_dev, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp);
 }
 
 }  // namespace gsr

@@ -88,17 +88,20 @@ class ViewResult:
 
 
 def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor],
-                      arena: GradArena, flags: int = 0) -> ViewResult:
+                      arena: GradArena, flags: int = 0, capacity: int | None = None,
+                      async_result: torch.Tensor | None = None) -> ViewResult:
     """One view through the CUDA path: forward, loss gradient, backward ADDING into `arena`.
     `gaussians`: means3D, shs, opacities, scales, rotations (post-activation, as render() passes them);
-    `settings`: GaussianRasterizationSettings."""
+    `settings`: GaussianRasterizationSettings.  With `async_result` (pinned int64[2]) + `capacity`
+    nothing in this call blocks the host; check the result with `AsyncViews.check()` after the step."""
     from . import _C
     rs = settings
     e = torch.empty(0, device=gaussians["means3D"].device)
     n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
         rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
         rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
-        rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags)
+        rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags,
+        capacity=capacity, async_result=async_result)
     dL = dL_dcolor_fn(color)
     out = _C.rasterize_gaussians_backward(
         rs.bg, gaussians["means3D"], radii, e, gaussians["scales"], gaussians["rotations"], rs.scale_modifier, e,
@@ -106,6 +109,41 @@ def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.T
         geom, n, binning, img, flags=flags | _C.FLAG_ACCUMULATE, out=arena.views)
     arena.add_view_stats(out[0], radii)
     return ViewResult(color, depth, radii, n)
+
+
+class AsyncViews:
+    """Host-side bookkeeping for fully asynchronous view steps: one pinned (N, status) slot and one
+    capacity per view.  Usage per step:  for v: cuda_view_fwd_bwd(..., capacity=a.capacity(v),
+    async_result=a.slot(v));  <sync / all-reduce>;  redo = a.check(views)  -> views whose capacity
+    overflowed (their contribution is invalid: zero the arena and redo the step)."""
+
+    def __init__(self, n_views: int, margin: float = 1.25):
+        self.slots = torch.zeros(n_views, 2, dtype=torch.int64)
+        if torch.cuda.is_available():
+            self.slots = self.slots.pin_memory()
+        self.cap = [0] * n_views
+        self.margin = margin
+
+    def slot(self, v: int) -> torch.Tensor:
+        return self.slots[v]
+
+    def capacity(self, v: int) -> int:
+        return self.cap[v]
+
+    def learn(self, v: int, n: int):
+        self.cap[v] = max(self.cap[v], int(n * self.margin) + 65536)
+
+    def check(self, views) -> list[int]:
+        """Call after the stream is synchronised.  Returns the views that must be redone."""
+        bad = []
+        for v in views:
+            n, status = int(self.slots[v, 0]), int(self.slots[v, 1])
+            if status & 0xffffffff:
+                raise RuntimeError("rasterize_gaussians: point filtered by culling but 'prefiltered' was set")
+            if n > self.cap[v] or (status >> 32):
+                bad.append(v)
+            self.learn(v, n)
+        return bad
 
 
 def sharded_step(view_fwd_bwd: Callable[[int], None], n_views: int, arena: GradArena, group=None,

@@ -27,7 +27,7 @@ def oracle_forward(O, sc, bg=None, cam=None, use_cov3D=False, use_colors=False, 
 
 
 def cuda_forward(sc, bg=None, cam=None, flags=0, use_cov3D=False, use_colors=False, scale_modifier=1.0,
-                 prefiltered=False, device="cuda"):
+                 prefiltered=False, device="cuda", **extra):
     """-> (num_rendered, color, radii, geom, binning, img, depth), tensors dict on device."""
     from multiview_inpaint_b200 import _C
     cam = (sc["camera"] if cam is None else cam).to(device)
@@ -39,7 +39,7 @@ def cuda_forward(sc, bg=None, cam=None, flags=0, use_cov3D=False, use_colors=Fal
         e if use_cov3D else d["scales"], e if use_cov3D else d["rotations"], scale_modifier,
         d["cov3D_precomp"] if use_cov3D else e, cam.world_view_transform, cam.full_proj_transform,
         cam.tanfovx, cam.tanfovy, cam.image_height, cam.image_width, e if use_colors else d["shs"],
-        sc["sh_degree"], cam.camera_center, prefiltered, flags=flags)
+        sc["sh_degree"], cam.camera_center, prefiltered, flags=flags, **extra)
     return out, d, cam, bg
 
 
