@@ -121,7 +121,12 @@ def _stream(device) -> int:
 
 
 class _Grower:
-    """The reference's resizeFunctional(): a callback that (re)allocates a uint8 tensor."""
+    """The reference's resizeFunctional(): a callback that (re)allocates a uint8 tensor.
+
+    The ctypes thunk references a bound method of this object, i.e. a reference cycle that would
+    keep the (hundreds of MB) buffer alive until the next cyclic GC pass -- every view would then
+    force the caching allocator into a fresh cudaMalloc.  `take()` breaks the cycle as soon as the
+    native call has returned, so the buffers are freed by reference counting."""
 
     def __init__(self, device):
         self.device = device
@@ -134,6 +139,10 @@ class _Grower:
             return self.tensor.data_ptr()
         except Exception:  # surfaces as GSR_E_ALLOC
             return 0
+
+    def take(self) -> torch.Tensor:
+        t, self.tensor, self.cb = self.tensor, None, None
+        return t
 
 
 #: running high-water mark of num_rendered per device -> capacity hint of the next call, so that the
@@ -202,11 +211,12 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
             _ptr(projmatrix), _ptr(campos), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
             _ptr(out_color), _ptr(out_depth), _ptr(radii), n_ptr, int(capacity), flags)
+        geom, binning, img = geom.take(), binning.take(), img.take()
         _check(rc, "rasterize_gaussians")
     if async_result is not None:
-        return -1, out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
+        return -1, out_color, radii, geom, binning, img, out_depth
     _note_rendered(dev, n.value)
-    return int(n.value), out_color, radii, geom.tensor, binning.tensor, img.tensor, out_depth
+    return int(n.value), out_color, radii, geom, binning, img, out_depth
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
