@@ -241,7 +241,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 return torch.zeros(*shape, dtype=torch.float32, device=dev) if acc else e(*shape)
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == math.prod(shape), name
             return t
-        dL_dmeans2D, dL_dconic = e(P, 3), e(P, 2, 2)
+        dL_dmeans2D, dL_dconic = e(P, 3), (e(P, 2, 2) if return_conic else None)
         dL_dmeans3D, dL_dcolors = o("dL_dmeans3D", P, 3), o("dL_dcolors", P, 3)
         dL_dopacity, dL_dcov3D = o("dL_dopacity", P, 1), o("dL_dcov3D", P, 6)
         dL_dsh, dL_dscales, dL_drotations = o("dL_dsh", P, M, 3), o("dL_dscales", P, 3), o("dL_drotations", P, 4)

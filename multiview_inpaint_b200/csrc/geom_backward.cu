@@ -132,7 +132,134 @@ __device__ __forceinline__ void span_xfer(float* __restrict__ g, float* s_tile, 
   }
 }
 
-template <bool ACC>
+
+// ---- fast staging for R = 3M with R % 4 == 0 (M = 4, 16): compile-time geometry ------------------
+// A row is R/4 whole float4s, so a 16-byte global access never straddles two Gaussians.  Rows sit in
+// shared memory with an ODD stride in float4 units (13 for R = 48, 3 for R = 12): 16-byte aligned
+// (LDS.128 / STS.128 on both sides) and conflict free for the per-thread row walk (the 8 threads of
+// a quarter warp hit the 8 distinct 4-bank groups).
+__host__ __device__ constexpr int row_stride(int R) { return ((R / 4) % 2 ? R / 4 : R / 4 + 1) * 4; }
+template <int R>
+__device__ __forceinline__ void rows_load(const float* __restrict__ g, float* s_tile, const uint8_t* s_vis, int rows) {
+  constexpr int Q = R / 4, STRIDE = row_stride(R), U = 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const int n4 = rows * Q;
+  for (int base = threadIdx.x; base < n4; base += U * 256) {
+    float4 q[U];
+    int so[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e4 = base + u * 256;
+      const int row = e4 / Q;
+      so[u] = -1;
+      if (e4 < n4 && s_vis[row]) {
+        so[u] = row * STRIDE + (e4 - row * Q) * 4;
+        q[u] = __ldg(g4 + e4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (so[u] >= 0) *reinterpret_cast<float4*>(s_tile + so[u]) = q[u];
+  }
+}
+// ACC: one vector reduction (RED.ADD.F32x4: fire and forget, the L2 does the read-modify-write) per
+// 16 bytes of a visible row, columns >= cols_used (coefficients above the active degree) skipped.
+// !ACC: every element of the span is written, zeros for culled rows.
+template <int R, bool ACC>
+__device__ __forceinline__ void rows_store(float* __restrict__ g, const float* s_tile, const uint8_t* s_vis, int rows,
+                                           int cols_used) {
+  constexpr int Q = R / 4, STRIDE = row_stride(R);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  const int n4 = rows * Q;
+#pragma unroll 4
+  for (int e4 = threadIdx.x; e4 < n4; e4 += 256) {
+    const int row = e4 / Q, c = (e4 - row * Q) * 4;
+    const bool v = s_vis[row] != 0;
+    if (ACC) {
+      if (v && c < cols_used) atomicAdd(g4 + e4, *reinterpret_cast<const float4*>(s_tile + row * STRIDE + c));
+    } else {
+      g4[e4] = v ? *reinterpret_cast<const float4*>(s_tile + row * STRIDE + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// SH backward on a 16-byte aligned staged row (M = 4 or 16): three float4 = four coefficients at a
+// time, sh in, dL/dsh out in place.  Same polynomial as sh_backward<DEG> above.
+template <int DEG, int MT>
+__device__ __forceinline__ void sh_backward_rows(float* row, float x, float y, float z, const float dRGB[3], float ddir[3]) {
+  constexpr int NCO = (DEG + 1) * (DEG + 1);
+  float w[16], dwx[16], dwy[16], dwz[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) { w[k] = 0.f; dwx[k] = 0.f; dwy[k] = 0.f; dwz[k] = 0.f; }
+  w[0] = GSR_SH_C0;
+  if (DEG > 0) {
+    w[1] = -GSR_SH_C1 * y; w[2] = GSR_SH_C1 * z; w[3] = -GSR_SH_C1 * x;
+    dwy[1] = -GSR_SH_C1; dwz[2] = GSR_SH_C1; dwx[3] = -GSR_SH_C1;
+  }
+  if (DEG > 1) {
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    w[4] = GSR_SH_C2_0 * xy; w[5] = GSR_SH_C2_1 * yz; w[6] = GSR_SH_C2_2 * (2.f * zz - xx - yy);
+    w[7] = GSR_SH_C2_3 * xz; w[8] = GSR_SH_C2_4 * (xx - yy);
+    dwx[4] = GSR_SH_C2_0 * y;        dwy[4] = GSR_SH_C2_0 * x;
+    dwy[5] = GSR_SH_C2_1 * z;        dwz[5] = GSR_SH_C2_1 * y;
+    dwx[6] = GSR_SH_C2_2 * -2.f * x; dwy[6] = GSR_SH_C2_2 * -2.f * y; dwz[6] = GSR_SH_C2_2 * 4.f * z;
+    dwx[7] = GSR_SH_C2_3 * z;        dwz[7] = GSR_SH_C2_3 * x;
+    dwx[8] = GSR_SH_C2_4 * 2.f * x;  dwy[8] = GSR_SH_C2_4 * -2.f * y;
+    if (DEG > 2) {
+      w[9] = GSR_SH_C3_0 * y * (3.f * xx - yy);
+      w[10] = GSR_SH_C3_1 * xy * z;
+      w[11] = GSR_SH_C3_2 * y * (4.f * zz - xx - yy);
+      w[12] = GSR_SH_C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy);
+      w[13] = GSR_SH_C3_4 * x * (4.f * zz - xx - yy);
+      w[14] = GSR_SH_C3_5 * z * (xx - yy);
+      w[15] = GSR_SH_C3_6 * x * (xx - 3.f * yy);
+      dwx[9] = GSR_SH_C3_0 * 6.f * xy;                 dwy[9] = GSR_SH_C3_0 * 3.f * (xx - yy);
+      dwx[10] = GSR_SH_C3_1 * yz; dwy[10] = GSR_SH_C3_1 * xz; dwz[10] = GSR_SH_C3_1 * xy;
+      dwx[11] = GSR_SH_C3_2 * -2.f * xy;               dwy[11] = GSR_SH_C3_2 * (4.f * zz - xx - 3.f * yy);
+      dwz[11] = GSR_SH_C3_2 * 8.f * yz;
+      dwx[12] = GSR_SH_C3_3 * -6.f * xz;               dwy[12] = GSR_SH_C3_3 * -6.f * yz;
+      dwz[12] = GSR_SH_C3_3 * 3.f * (2.f * zz - xx - yy);
+      dwx[13] = GSR_SH_C3_4 * (4.f * zz - 3.f * xx - yy); dwy[13] = GSR_SH_C3_4 * -2.f * xy;
+      dwz[13] = GSR_SH_C3_4 * 8.f * xz;
+      dwx[14] = GSR_SH_C3_5 * 2.f * xz;                dwy[14] = GSR_SH_C3_5 * -2.f * yz;
+      dwz[14] = GSR_SH_C3_5 * (xx - yy);
+      dwx[15] = GSR_SH_C3_6 * 3.f * (xx - yy);         dwy[15] = GSR_SH_C3_6 * -6.f * xy;
+    }
+  }
+  ddir[0] = ddir[1] = ddir[2] = 0.f;
+  float4* row4 = reinterpret_cast<float4*>(row);
+  constexpr int GROUPS = MT / 4;              // 4 coefficients (3 float4) per group
+  constexpr int GUSED = (NCO + 3) / 4;        // groups holding an active coefficient
+#pragma unroll
+  for (int gI = 0; gI < GROUPS; gI++) {
+    if (gI < GUSED) {
+      const float4 a = row4[3 * gI], b = row4[3 * gI + 1], c = row4[3 * gI + 2];
+      const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+      float o[12];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int k = 4 * gI + j;
+        if (k > 0 && k < NCO) {
+          const float sdot = v[3 * j] * dRGB[0] + v[3 * j + 1] * dRGB[1] + v[3 * j + 2] * dRGB[2];
+          ddir[0] += dwx[k] * sdot;
+          ddir[1] += dwy[k] * sdot;
+          ddir[2] += dwz[k] * sdot;
+        }
+        const float wk = k < NCO ? w[k] : 0.f;
+        o[3 * j] = wk * dRGB[0]; o[3 * j + 1] = wk * dRGB[1]; o[3 * j + 2] = wk * dRGB[2];
+      }
+      row4[3 * gI] = make_float4(o[0], o[1], o[2], o[3]);
+      row4[3 * gI + 1] = make_float4(o[4], o[5], o[6], o[7]);
+      row4[3 * gI + 2] = make_float4(o[8], o[9], o[10], o[11]);
+    } else {
+      const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
+      row4[3 * gI] = zf; row4[3 * gI + 1] = zf; row4[3 * gI + 2] = zf;
+    }
+  }
+}
+
+// MT = compile-time M for the fast paths (1: no staging, 4 / 16: aligned rows), 0 = generic M.
+template <bool ACC, int MT>
 __global__ void __launch_bounds__(256)
 geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
                      const int32_t* __restrict__ radii, const float* __restrict__ shs,
@@ -147,7 +274,7 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
                      float* __restrict__ dL_drot) {
   __shared__ float s_cam[35];
   __shared__ uint8_t s_vis[256];
-  extern __shared__ float s_tile[];  // [256][3M + 1] when SH gradients are produced
+  extern __shared__ __align__(16) float s_tile[];  // [256][row_stride(3M)] (fast) / [256][3M + 1] (generic)
   load_camera(cam, s_cam);
   const int tid = threadIdx.x;
   const int block_start = blockIdx.x * blockDim.x;
@@ -159,9 +286,13 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const bool use_sh = (colors_precomp == nullptr) && (dL_dsh != nullptr) && (shs != nullptr);
   s_vis[tid] = vis ? 1 : 0;
   __syncthreads();
+  constexpr bool STAGED_FAST = (MT == 4 || MT == 16);
+  const int nco = (D + 1) * (D + 1);
   if (use_sh) {
-    span_xfer<SPAN_LOAD>(const_cast<float*>(shs) + (size_t)block_start * R, s_tile, s_vis, rows, R);
-    __syncthreads();
+    // coefficients above the active degree have no effect on ddir: at degree 0 nothing is read
+    if (STAGED_FAST) { if (D > 0) rows_load<3 * (MT > 0 ? MT : 4)>(shs + (size_t)block_start * R, s_tile, s_vis, rows); }
+    else if (MT == 0) span_xfer<SPAN_LOAD>(const_cast<float*>(shs) + (size_t)block_start * R, s_tile, s_vis, rows, R);
+    if (MT != 1) __syncthreads();
   }
   const size_t i3 = 3 * (size_t)i;
 
@@ -338,13 +469,28 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
       const float x = dorig[0] * inv_len, y = dorig[1] * inv_len, z = dorig[2] * inv_len;
       const uint8_t cb = clamped[i];
       const float dRGB[3] = {(cb & 1) ? 0.f : g0.x, (cb & 2) ? 0.f : g0.y, (cb & 4) ? 0.f : g0.z};
-      float* row = s_tile + tid * (R + 1);
-      float ddir[3];
-      switch (D) {
-        case 0: sh_backward<0>(row, M, x, y, z, dRGB, ddir); break;
-        case 1: sh_backward<1>(row, M, x, y, z, dRGB, ddir); break;
-        case 2: sh_backward<2>(row, M, x, y, z, dRGB, ddir); break;
-        default: sh_backward<3>(row, M, x, y, z, dRGB, ddir); break;
+      float ddir[3] = {0.f, 0.f, 0.f};
+      if (MT == 1) {  // M = 1 (the fork's default sh_degree = 0): three floats per Gaussian, no staging
+        float* o = dL_dsh + i3;
+        if (ACC) { o[0] += GSR_SH_C0 * dRGB[0]; o[1] += GSR_SH_C0 * dRGB[1]; o[2] += GSR_SH_C0 * dRGB[2]; }
+        else { o[0] = GSR_SH_C0 * dRGB[0]; o[1] = GSR_SH_C0 * dRGB[1]; o[2] = GSR_SH_C0 * dRGB[2]; }
+      } else if (STAGED_FAST) {
+        constexpr int MF = STAGED_FAST ? MT : 4;
+        float* row = s_tile + tid * row_stride(3 * MF);
+        switch (D) {
+          case 0: sh_backward_rows<0, MF>(row, x, y, z, dRGB, ddir); break;
+          case 1: sh_backward_rows<1, MF>(row, x, y, z, dRGB, ddir); break;
+          case 2: if (MF >= 9) sh_backward_rows<(MF >= 9 ? 2 : 0), MF>(row, x, y, z, dRGB, ddir); break;
+          default: if (MF >= 16) sh_backward_rows<(MF >= 16 ? 3 : 0), MF>(row, x, y, z, dRGB, ddir); break;
+        }
+      } else {
+        float* row = s_tile + tid * (R + 1);
+        switch (D) {
+          case 0: sh_backward<0>(row, M, x, y, z, dRGB, ddir); break;
+          case 1: sh_backward<1>(row, M, x, y, z, dRGB, ddir); break;
+          case 2: sh_backward<2>(row, M, x, y, z, dRGB, ddir); break;
+          default: sh_backward<3>(row, M, x, y, z, dRGB, ddir); break;
+        }
       }
       const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
       const float* v = dorig;
@@ -398,9 +544,12 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
   // ---- dL/dsh write-out: one coalesced pass over the block's contiguous (rows x 3M) span ----
   if (dL_dsh != nullptr && R > 0) {
     float* gspan = dL_dsh + (size_t)block_start * R;
-    if (use_sh) {
+    if (use_sh && MT == 1) {
+      if (!ACC && valid && !vis) { gspan[3 * tid] = 0.f; gspan[3 * tid + 1] = 0.f; gspan[3 * tid + 2] = 0.f; }
+    } else if (use_sh) {
       __syncthreads();
-      if (ACC) span_xfer<SPAN_ADD>(gspan, s_tile, s_vis, rows, R);
+      if (STAGED_FAST) rows_store<3 * (STAGED_FAST ? MT : 4), ACC>(gspan, s_tile, s_vis, rows, 3 * nco);
+      else if (ACC) span_xfer<SPAN_ADD>(gspan, s_tile, s_vis, rows, R);
       else span_xfer<SPAN_STORE_ALL>(gspan, s_tile, s_vis, rows, R);
     } else if (!ACC) {
       for (int e = tid; e < rows * R; e += blockDim.x) gspan[e] = 0.f;
@@ -418,8 +567,17 @@ cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const floa
                                  float* dL_dsh, float* dL_dscale, float* dL_drot, bool accumulate) {
   if (P == 0) return cudaSuccess;
   const bool use_sh = colors_precomp == nullptr && dL_dsh != nullptr && shs != nullptr;
-  const size_t smem = use_sh ? (size_t)256 * (3 * M + 1) * sizeof(float) : 0;
-  auto kern = accumulate ? geom_backward_kernel<true> : geom_backward_kernel<false>;
+  const int mt = (M == 1 || M == 4 || M == 16) ? M : 0;
+  const size_t row_floats = mt == 1 ? 0 : (mt ? row_stride(3 * M) : 3 * M + 1);
+  const size_t smem = use_sh ? (size_t)256 * row_floats * sizeof(float) : 0;
+  using KernT = void (*)(int, int, int, const float*, const int32_t*, const float*, const uint8_t*, const float*,
+                         const float*, const float*, const float*, const Camera, const float4*, const float*, float*,
+                         float*, float*, float*, float*, float*, float*, float*, float*);
+  KernT kern;
+  if (accumulate) kern = mt == 16 ? geom_backward_kernel<true, 16> : mt == 4 ? geom_backward_kernel<true, 4>
+                       : mt == 1 ? geom_backward_kernel<true, 1> : geom_backward_kernel<true, 0>;
+  else kern = mt == 16 ? geom_backward_kernel<false, 16> : mt == 4 ? geom_backward_kernel<false, 4>
+            : mt == 1 ? geom_backward_kernel<false, 1> : geom_backward_kernel<false, 0>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
