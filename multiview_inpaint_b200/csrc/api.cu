@@ -72,17 +72,18 @@ GeomLayout geom_layout(int P, uint32_t flags) {
   L.clamped = take(n);
   L.tiles_touched = take(n * 4);
   L.point_offsets = take(n * 4);
-  L.status = take(16);
+  L.status = take(32);
   L.temp_bytes = scan_temp_bytes(P);
   if (!key64(flags)) {
     L.depth_keys = take(n * 4);
     L.order = take(n * 4);
     L.depth_keys_alt = take(n * 4);
     L.order_alt = take(n * 4);
+    L.rects = take(n * 8);
     const size_t st = sort_temp_bytes(P, 4, 32);
     if (st > L.temp_bytes) L.temp_bytes = st;
   } else {
-    L.depth_keys = L.order = L.depth_keys_alt = L.order_alt = (size_t)-1;
+    L.depth_keys = L.order = L.depth_keys_alt = L.order_alt = L.rects = (size_t)-1;
   }
   L.temp = take(L.temp_bytes);
   L.bytes = off;
@@ -98,6 +99,7 @@ ImageLayout image_layout(int W, int H) {
   L.final_T = take(hw * 4);
   L.n_contrib = take(hw * 4);
   L.ranges = take((G > 0 ? G : 1) * 8);
+  L.tile_count = take((G > 0 ? G : 1) * 4);
   L.bytes = off;
   return L;
 }
@@ -128,6 +130,7 @@ BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags) {
   L.keys_b = take(n * kb);
   L.temp_bytes = sort_temp_bytes(N, (int)kb, end_bit);
   L.temp = take(L.temp_bytes);
+  L.big_items = k64 ? (size_t)-1 : take((size_t)bin_big_capacity(N) * 16);
   L.bytes = off;
   return L;
 }
@@ -276,12 +279,13 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   int64_t* result = async ? num_rendered_host : pin.result;  // [0] = N, [1] = status bits
   if (async && capacity_hint <= 0) return fail(GSR_E_INVALID, "gsr_forward: GSR_FLAG_ASYNC needs a capacity_hint");
   if (P > 0) {
-    GSR_CUDA(cudaMemsetAsync(status, 0, 16, s), "memset status");
+    GSR_CUDA(cudaMemsetAsync(status, 0, 32, s), "memset status");
     uint32_t* depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(geom + gl.depth_keys);
+    ushort4* rects = k64 ? nullptr : reinterpret_cast<ushort4*>(geom + gl.rects);
     PROF(0);
     GSR_CUDA(launch_preprocess(s, P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
                                colors_precomp, cam, prefiltered, radii, rec, depths, clamped,
-                               tiles_touched, depth_keys, status), "preprocess");
+                               tiles_touched, depth_keys, rects, status), "preprocess");
     if (k64) {
       PROF(2);
       GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, nullptr, offsets, geom + gl.temp), "scan");
@@ -295,13 +299,12 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       uint32_t* kb = reinterpret_cast<uint32_t*>(geom + gl.depth_keys_alt);
       uint32_t* vb = reinterpret_cast<uint32_t*>(geom + gl.order_alt);
       GSR_CUDA(launch_sort_pairs_u32(s, P, nullptr, ka, nullptr, ka, va, kb, vb, 32, geom + gl.temp), "depth sort");
-      order = va;
-      PROF(2);
-      GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, order, offsets, geom + gl.temp), "scan");
+      order = va;  // the scan runs fused with the expansion (launch_bin_expand), once the capacity is known
     }
     PROF(-1);
   }
-  const uint32_t* n_dev = P > 0 ? offsets + (P - 1) : nullptr;
+  // N lives in status[2..3] (uint64, written by K1); the kernels read its low word
+  const uint32_t* n_dev = P > 0 ? reinterpret_cast<const uint32_t*>(status + 2) : nullptr;
 
   // ---- binning + blend for a given capacity; every kernel reads the true N on the device ----
   char* bin = nullptr;
@@ -332,14 +335,17 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       } else {
         uint32_t* ka = reinterpret_cast<uint32_t*>(bin + bl.keys_a);
         uint32_t* kb = reinterpret_cast<uint32_t*>(bin + bl.keys_b);
+        uint32_t* tile_count = reinterpret_cast<uint32_t*>(img + il.tile_count);
         PROF(3);
-        GSR_CUDA(launch_duplicate_tiles(s, P, order, rec, offsets, radii, cam.grid_x, cam.grid_y, ka, va, cap, status), "duplicate (depth order)");
+        GSR_CUDA(launch_bin_expand(s, P, order, reinterpret_cast<const ushort4*>(geom + gl.rects), offsets, ka, va, cap,
+                                   tile_count, G, cam.grid_x, geom + gl.temp, status,
+                                   reinterpret_cast<uint4*>(bin + bl.big_items), bin_big_capacity(cap)), "scan + duplicate (depth order)");
+        PROF(5);
+        GSR_CUDA(launch_tile_prepare(s, G, tile_count, ranges, end_bit, sort_hist_ptr(bin + bl.temp)), "tile ranges + digit bases");
         uint32_t* kout = (passes & 1) ? kb : ka;
         uint32_t* kalt = (passes & 1) ? ka : kb;
         PROF(4);
-        GSR_CUDA(launch_sort_pairs_u32(s, cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, bin + bl.temp), "tile sort");
-        PROF(5);
-        GSR_CUDA(launch_tile_ranges_u32(s, cap, n_dev, kout, G, ranges), "identifyTileRanges");
+        GSR_CUDA(launch_sort_pairs_u32(s, cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, bin + bl.temp, true), "tile sort");
       }
     } else {
       GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
@@ -354,7 +360,7 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
     result[0] = 0;
     result[1] = 0;
     if (P > 0) {
-      GSR_CUDA(cudaMemcpyAsync(result, n_dev, 4, cudaMemcpyDeviceToHost, s), "memcpy num_rendered");
+      GSR_CUDA(cudaMemcpyAsync(result, n_dev, 8, cudaMemcpyDeviceToHost, s), "memcpy num_rendered");
       GSR_CUDA(cudaMemcpyAsync(result + 1, status, 8, cudaMemcpyDeviceToHost, s), "memcpy status");
     }
     return 0;
@@ -377,7 +383,7 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
     }
     GSR_CUDA(cudaEventSynchronize(ev), "sync num_rendered");
     cudaEventDestroy(ev);
-    N = (int64_t)(uint32_t)result[0];
+    N = result[0];  // full 64-bit sum: >= 2^30 is rejected below
     if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
     if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
     if (N > capacity_hint) {  // rare: the hint was too small, redo binning + blend at the exact size
@@ -392,7 +398,7 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   if (P > 0) {
     if (int rc = fetch_result()) return rc;
     GSR_CUDA(cudaStreamSynchronize(s), "sync num_rendered");
-    N = (int64_t)(uint32_t)result[0];
+    N = result[0];  // full 64-bit sum: >= 2^30 is rejected below
     if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
     if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
   }

@@ -64,6 +64,265 @@ duplicate_tiles_kernel(int P, const uint32_t* __restrict__ order, const float4* 
     }
 }
 
+
+// =================================================================================================
+// Fused K2 + K3 for the two-level scheme: ONE pass does the inclusive scan of tiles_touched in
+// depth order (chained tiles, decoupled look-back), the load-balanced expansion into (tile, id)
+// pairs, and the per-tile instance counts.
+//   * K1 stores each Gaussian's tile rect as ushort4 {x0, y0, x1, y1} (zero area when culled), so
+//     nothing is recomputed here and one 8-byte gather per Gaussian replaces radii + mean2D + rect;
+//   * a warp expands 32 Gaussians at a time: output slot j of the round's contiguous span finds its
+//     owner by a 5-step shuffle search over the round's inclusive counts, so the key / value stores
+//     are fully coalesced however unequal the rects are (a thread-per-Gaussian loop serialises on
+//     the largest splat of the warp and writes 32 scattered runs);
+//   * tile_count[tile] += 1 per instance (L2 reductions): K5's ranges are the exclusive scan of
+//     these counts and the tile sort's digit histograms are their marginals (tile_prepare_kernel),
+//     which removes the histogram pass over the keys and the boundary-detection pass of K5.
+// Emission order is unchanged: depth rank, then y-major over the rect (Appendix A.3).
+// =================================================================================================
+constexpr int BE_THREADS = 256;
+constexpr int BE_ROUNDS = 4;
+constexpr int BE_TILE = BE_THREADS * BE_ROUNDS;  // == SCAN_TILE: the look-back status array is the scan's
+constexpr uint32_t BE_BIG = 64;                  // rects with more tiles than this go to the work list
+constexpr unsigned long long BE_FLAG_AGG = 1ull << 62;
+constexpr unsigned long long BE_FLAG_INC = 2ull << 62;
+constexpr unsigned long long BE_VAL_MASK = (1ull << 62) - 1;
+
+// floor(q / w) = umulhi(q, magic(w)) whenever q * w < 2^32 (here q < 2^16 and w < 2^16); w == 1 -> q
+__device__ __forceinline__ uint32_t div_magic(uint32_t w) { return w > 1 ? (0xFFFFFFFFu / w + 1u) : 0u; }
+__device__ __forceinline__ uint32_t tile_of_slot(uint32_t q, uint32_t xy0, uint32_t w, uint32_t magic, uint32_t gx) {
+  const uint32_t row = w > 1 ? __umulhi(q, magic) : q;
+  return ((xy0 >> 16) + row) * gx + (xy0 & 0xffffu) + (q - row * w);
+}
+
+__global__ void __launch_bounds__(BE_THREADS)
+bin_expand_kernel(int P, const uint32_t* __restrict__ order, const ushort4* __restrict__ rects,
+                  uint32_t* __restrict__ offsets, uint32_t* __restrict__ tile_keys,
+                  uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ tile_count, int gx,
+                  volatile unsigned long long* lb_status, uint32_t* ticket, int32_t* __restrict__ status,
+                  uint4* __restrict__ big_items, uint32_t big_cap) {
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_warp[BE_THREADS / 32];
+  __shared__ uint32_t s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t kbase = (int64_t)tile * BE_TILE + warp * (32 * BE_ROUNDS) + lane;
+
+  uint32_t id[BE_ROUNDS], xy0[BE_ROUNDS], wh[BE_ROUNDS], cnt[BE_ROUNDS], incl[BE_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < BE_ROUNDS; r++) {
+    const int64_t k = kbase + r * 32;
+    id[r] = k < P ? __ldg(order + k) : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < BE_ROUNDS; r++) {
+    const int64_t k = kbase + r * 32;
+    ushort4 q = make_ushort4(0, 0, 0, 0);
+    if (k < P) q = __ldg(rects + id[r]);
+    xy0[r] = (uint32_t)q.x | ((uint32_t)q.y << 16);
+    const uint32_t w = (uint32_t)(q.z - q.x), h = (uint32_t)(q.w - q.y);
+    wh[r] = w | (h << 16);
+    cnt[r] = w * h;
+  }
+  // per-round inclusive scans over the warp, then the warp's running total
+  uint32_t warp_total = 0;
+#pragma unroll
+  for (int r = 0; r < BE_ROUNDS; r++) {
+    uint32_t x = cnt[r];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    incl[r] = x;
+    warp_total += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) s_warp[warp] = warp_total;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t wv = lane < BE_THREADS / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < BE_THREADS / 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, wv, o);
+      if (lane >= o) wv += y;
+    }
+    const uint32_t block_total = __shfl_sync(0xffffffffu, wv, BE_THREADS / 32 - 1);
+    if (lane < BE_THREADS / 32) s_warp[lane] = wv;  // inclusive over warps
+    unsigned long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) lb_status[0] = BE_FLAG_INC | block_total;
+    } else {
+      if (lane == 0) lb_status[tile] = BE_FLAG_AGG | block_total;
+      int64_t look = (int64_t)tile - 1;
+      while (true) {  // decoupled look-back, 32 predecessors per step
+        const int64_t t = look - lane;
+        unsigned long long st = BE_FLAG_INC;
+        if (t >= 0) {
+          do { st = lb_status[t]; } while ((st >> 62) == 0);
+        }
+        const unsigned inc_mask = __ballot_sync(0xffffffffu, (st & BE_FLAG_INC) != 0);
+        const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+        unsigned long long val = (lane <= first_inc) ? (st & BE_VAL_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (inc_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) lb_status[tile] = BE_FLAG_INC | ((excl + block_total) & BE_VAL_MASK);
+    }
+    if (lane == 0) {
+      s_prefix = (uint32_t)excl;
+      // the tile holding the last Gaussian knows N: flag a capacity overflow
+      if ((int64_t)tile * BE_TILE + BE_TILE >= P && (uint32_t)excl + block_total > cap) atomicExch(status + 1, 1);
+    }
+  }
+  __syncthreads();
+  uint32_t base = s_prefix + (warp > 0 ? s_warp[warp - 1] : 0);  // exclusive offset of this warp's round 0
+
+#pragma unroll
+  for (int r = 0; r < BE_ROUNDS; r++) {
+    const int64_t k = kbase + r * 32;
+    if (k < P) offsets[k] = base + incl[r];
+    const uint32_t total = __shfl_sync(0xffffffffu, incl[r], 31);
+    const uint32_t start = base + incl[r] - cnt[r];  // this Gaussian's first output slot
+    // Large rects would serialise the warp (depth order puts the nearest = largest splats into the
+    // same few CTAs): they are queued and expanded by bin_expand_big_kernel, one warp per item.
+    const bool big = cnt[r] > BE_BIG;
+    if (big) {
+      const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(status + 4), 1u);
+      if (slot < big_cap) big_items[slot] = make_uint4(id[r], xy0[r], wh[r], start);
+    }
+    // inclusive scan of the counts this warp expands itself
+    const uint32_t c_small = big ? 0u : cnt[r];
+    uint32_t incl_s = c_small;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl_s, o);
+      if (lane >= o) incl_s += y;
+    }
+    const uint32_t total_s = __shfl_sync(0xffffffffu, incl_s, 31);
+    const uint32_t excl_s = incl_s - c_small;
+    const uint32_t w = wh[r] & 0xffffu;
+    const uint32_t magic = div_magic(w);
+    for (uint32_t jb = 0; jb < total_s; jb += 32) {  // warp-uniform trip count
+      const uint32_t j = jb + lane;
+      int lo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl_s, lo + step - 1);
+        if (v <= j) lo += step;
+      }
+      lo = min(lo, 31);  // lanes past the end of the span (j >= total_s) are masked below
+      const uint32_t o_excl = __shfl_sync(0xffffffffu, excl_s, lo);
+      const uint32_t o_start = __shfl_sync(0xffffffffu, start, lo);
+      const uint32_t o_xy = __shfl_sync(0xffffffffu, xy0[r], lo);
+      const uint32_t o_w = __shfl_sync(0xffffffffu, w, lo);
+      const uint32_t o_magic = __shfl_sync(0xffffffffu, magic, lo);
+      const uint32_t o_id = __shfl_sync(0xffffffffu, id[r], lo);
+      const uint32_t q = j - o_excl;
+      const uint32_t off = o_start + q;
+      if (j < total_s && off < cap) {
+        const uint32_t t = tile_of_slot(q, o_xy, o_w, o_magic, (uint32_t)gx);
+        tile_keys[off] = t;
+        vals[off] = o_id;
+        atomicAdd(tile_count + t, 1u);
+      }
+    }
+    base += total;
+  }
+}
+
+// Work-list items {id, x0 | y0 << 16, w | h << 16, first output slot}: one warp per item, coalesced.
+__global__ void __launch_bounds__(256)
+bin_expand_big_kernel(const uint4* __restrict__ big_items, const int32_t* __restrict__ status, uint32_t big_cap,
+                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, uint32_t cap,
+                      uint32_t* __restrict__ tile_count, int gx) {
+  const uint32_t n_items = min((uint32_t)status[4], big_cap);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n_items; it += n_warps) {
+    const uint4 item = __ldg(big_items + it);
+    const uint32_t w = item.z & 0xffffu, c = w * (item.z >> 16);
+    const uint32_t magic = div_magic(w);
+    for (uint32_t q = lane; q < c; q += 32) {
+      const uint32_t off = item.w + q;
+      if (off < cap) {
+        const uint32_t t = tile_of_slot(q, item.y, w, magic, (uint32_t)gx);
+        tile_keys[off] = t;
+        vals[off] = item.x;
+        atomicAdd(tile_count + t, 1u);
+      }
+    }
+  }
+}
+
+// One CTA: ranges = exclusive scan of the per-tile counts ((0,0) for untouched tiles, as the
+// reference's memset leaves them), and the tile sort's per-digit exclusive bases (what the onesweep
+// histogram + scan kernels would produce from the keys).
+__global__ void __launch_bounds__(1024)
+tile_prepare_kernel(int G, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+                    int passes, int end_bit, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_h[4 * 256];
+  __shared__ uint32_t s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < passes * 256; i += 1024) s_h[i] = 0;
+  __syncthreads();
+  const int per = (G + 1023) / 1024;
+  const int t0 = tid * per, t1 = min(G, t0 + per);
+  uint32_t sum = 0;
+  for (int t = t0; t < t1; t++) {
+    const uint32_t c = tile_count[t];
+    sum += c;
+    if (c)
+      for (int p = 0; p < passes; p++) {
+        const int bits = min(8, end_bit - 8 * p);
+        atomicAdd(&s_h[p * 256 + (((uint32_t)t >> (8 * p)) & ((1u << bits) - 1))], c);
+      }
+  }
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += y;
+    }
+    s_w[lane] = v;
+  }
+  __syncthreads();
+  uint32_t run = (warp > 0 ? s_w[warp - 1] : 0) + x - sum;
+  for (int t = t0; t < t1; t++) {
+    const uint32_t c = tile_count[t];
+    ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+    run += c;
+  }
+  // exclusive scan of each digit histogram: warp p handles pass p (8 bins per lane)
+  if (warp < passes) {
+    uint32_t v[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { v[k] = s_h[warp * 256 + lane * 8 + k]; tot += v[k]; }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    uint32_t e = inc - tot;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { hist[warp * 256 + lane * 8 + k] = e; e += v[k]; }
+  }
+}
+
 template <typename KeyT>
 __device__ __forceinline__ uint32_t tile_of(KeyT k);
 template <> __device__ __forceinline__ uint32_t tile_of<uint64_t>(uint64_t k) { return (uint32_t)(k >> 32); }
@@ -104,6 +363,37 @@ cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order,
   if (P == 0) return cudaSuccess;
   duplicate_tiles_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, order, rec, offsets, radii, grid_x, grid_y, tile_keys, vals,
                                                       (uint32_t)cap, status);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_bin_expand(cudaStream_t s, int P, const uint32_t* order, const ushort4* rects, uint32_t* offsets,
+                              uint32_t* tile_keys, uint32_t* vals, int64_t cap, uint32_t* tile_count, int G,
+                              int grid_x, char* scan_temp, int32_t* status, uint4* big_items, int64_t big_cap) {
+  if (P == 0) return cudaSuccess;
+  const int64_t tiles = ((int64_t)P + BE_TILE - 1) / BE_TILE;
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(scan_temp);
+  auto* lb = reinterpret_cast<unsigned long long*>(scan_temp + align_up(16));
+  cudaError_t e = cudaMemsetAsync(scan_temp, 0, scan_temp_bytes(P), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(tile_count, 0, (size_t)G * 4, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(status + 4, 0, 4, s);  // work-list length
+  if (e != cudaSuccess) return e;
+  bin_expand_kernel<<<(unsigned)tiles, BE_THREADS, 0, s>>>(P, order, rects, offsets, tile_keys, vals, (uint32_t)cap,
+                                                           tile_count, grid_x, lb, ticket, status, big_items,
+                                                           (uint32_t)big_cap);
+  bin_expand_big_kernel<<<148 * 4, 256, 0, s>>>(big_items, status, (uint32_t)big_cap, tile_keys, vals, (uint32_t)cap,
+                                                tile_count, grid_x);
+  count_launch(2);
+  return cudaGetLastError();
+}
+// capacity of the work list for `cap` instances: every queued rect has more than BE_BIG tiles
+int64_t bin_big_capacity(int64_t cap) { return cap / (BE_BIG + 1) + 1; }
+cudaError_t launch_tile_prepare(cudaStream_t s, int G, const uint32_t* tile_count, uint2* ranges, int end_bit,
+                                uint32_t* hist) {
+  const int passes = (end_bit + 7) / 8;
+  if (passes > 4) return cudaErrorInvalidValue;
+  tile_prepare_kernel<<<1, 1024, 0, s>>>(G, tile_count, ranges, passes, end_bit, hist);
   count_launch();
   return cudaGetLastError();
 }

@@ -98,18 +98,20 @@ struct GeomLayout {
   size_t rec, depths, clamped, tiles_touched, point_offsets;
   size_t depth_keys, order, depth_keys_alt, order_alt;    // two-level binning only (sorted result
                                                           // lands back in depth_keys / order)
-  size_t status;                                          // int32[2]: trap flag, spare
+  size_t rects;                                           // two-level only: ushort4[P] tile rects
+  size_t status;                                          // int32[8]: trap, overflow, N (u64), work-list length
   size_t temp, temp_bytes;                                // scan + depth-sort temp
   size_t bytes;
 };
 struct ImageLayout {
-  size_t final_T, n_contrib, ranges, bytes;
+  size_t final_T, n_contrib, ranges, tile_count, bytes;
 };
 struct BinningLayout {
   size_t point_list;       // uint32[N]  (final, sorted)
   size_t vals_alt;         // uint32[N]
   size_t keys_a, keys_b;   // KeyT[N] each (u32 tile ids, or u64 tile|depth)
   size_t temp, temp_bytes; // sort temp
+  size_t big_items;        // uint4[bin_big_capacity(N)] work list of large rects (two-level only)
   size_t bytes;
 };
 GeomLayout geom_layout(int P, uint32_t flags);
@@ -125,7 +127,7 @@ cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* 
                               const float* shs, const float* cov3D_precomp,
                               const float* colors_precomp, const Camera& cam, int prefiltered,
                               int32_t* radii, float4* rec, float* depths, uint8_t* clamped,
-                              uint32_t* tiles_touched, uint32_t* depth_keys, int32_t* status);
+                              uint32_t* tiles_touched, uint32_t* depth_keys, ushort4* rects, int32_t* status);
 cudaError_t launch_mark_visible(cudaStream_t s, int P, const float* means3D, const float* view,
                                 uint8_t* present);
 
@@ -136,9 +138,12 @@ size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit);
 // vals_in may be NULL: values are then the element indices 0..n-1.
 // n_dev may be NULL; otherwise the element count is min(*n_dev, n) read on the device and `n` only
 // sizes the grid and the temp storage (capacity).
+// have_bases: the per-digit exclusive bases are already in temp (sort_hist_ptr) -- no histogram pass.
 cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint32_t* keys_in,
                                   const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                                  uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
+                                  uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp,
+                                  bool have_bases = false);
+inline uint32_t* sort_hist_ptr(char* temp) { return reinterpret_cast<uint32_t*>(temp); }
 cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
@@ -151,6 +156,14 @@ cudaError_t launch_duplicate_key64(cudaStream_t s, int P, const float4* rec, con
 cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order, const float4* rec,
                                    const uint32_t* offsets, const int32_t* radii, int grid_x,
                                    int grid_y, uint32_t* tile_keys, uint32_t* vals, int64_t cap, int32_t* status);
+// Two-level scheme: fused scan (offsets in depth order) + load-balanced expansion + per-tile counts;
+// `scan_temp` is the scan's temp (scan_temp_bytes(P)).  Then ranges + the tile sort's digit bases.
+cudaError_t launch_bin_expand(cudaStream_t s, int P, const uint32_t* order, const ushort4* rects, uint32_t* offsets,
+                              uint32_t* tile_keys, uint32_t* vals, int64_t cap, uint32_t* tile_count, int G,
+                              int grid_x, char* scan_temp, int32_t* status, uint4* big_items, int64_t big_cap);
+int64_t bin_big_capacity(int64_t cap);
+cudaError_t launch_tile_prepare(cudaStream_t s, int G, const uint32_t* tile_count, uint2* ranges, int end_bit,
+                                uint32_t* hist);
 // N = min(*n_dev, cap) when n_dev is given, else cap
 cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t cap, const uint32_t* n_dev, const uint64_t* keys, int G, uint2* ranges);
 cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t cap, const uint32_t* n_dev, const uint32_t* keys, int G, uint2* ranges);

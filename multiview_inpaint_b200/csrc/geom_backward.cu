@@ -290,7 +290,7 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
   const int nco = (D + 1) * (D + 1);
   if (use_sh) {
     // coefficients above the active degree have no effect on ddir: at degree 0 nothing is read
-    if (STAGED_FAST) { if (D > 0) rows_load<3 * (MT > 0 ? MT : 4)>(shs + (size_t)block_start * R, s_tile, s_vis, rows); }
+    if (STAGED_FAST) { if (D > 0) rows_load<3 * (STAGED_FAST ? MT : 4)>(shs + (size_t)block_start * R, s_tile, s_vis, rows); }
     else if (MT == 0) span_xfer<SPAN_LOAD>(const_cast<float*>(shs) + (size_t)block_start * R, s_tile, s_vis, rows, R);
     if (MT != 1) __syncthreads();
   }

@@ -94,7 +94,8 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
                   const Camera cam, int prefiltered, int32_t* __restrict__ radii,
                   float4* __restrict__ rec, float* __restrict__ depths,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ depth_keys, int32_t* __restrict__ status) {
+                  uint32_t* __restrict__ depth_keys, ushort4* __restrict__ rects,
+                  int32_t* __restrict__ status) {
   __shared__ float s_cam[35];
   load_camera(cam, s_cam);
   const float* view = s_cam;
@@ -107,6 +108,7 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
   int32_t out_radius = 0;
   uint32_t out_tiles = 0;
   uint32_t out_key = 0xFFFFFFFFu;
+  ushort4 out_rect = make_ushort4(0, 0, 0, 0);
 
   const float p[3] = {__ldg(means3D + 3 * (size_t)i), __ldg(means3D + 3 * (size_t)i + 1),
                       __ldg(means3D + 3 * (size_t)i + 2)};
@@ -237,12 +239,21 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
         out_radius = my_radius;
         out_tiles = tiles;
         out_key = __float_as_uint(pv[2]);
+        out_rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
       }
     }
   }
   radii[i] = out_radius;
   tiles_touched[i] = out_tiles;
   if (depth_keys != nullptr) depth_keys[i] = out_key;
+  if (rects != nullptr) rects[i] = out_rect;  // two-level binning: the fused scan + expansion reads this
+  // N = sum of tiles_touched, known as soon as K1 ends (status[2..3] as one uint64): the host sizes
+  // the binning buffer from it without waiting for the scan.  Any converged subset of the warp
+  // reduces among itself, so divergence above only changes how many partial sums are added.
+  const unsigned am = __activemask();
+  const uint32_t part = __reduce_add_sync(am, out_tiles);
+  if ((threadIdx.x & 31) == __ffs(am) - 1 && part != 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(status + 2), (unsigned long long)part);
 }
 
 __global__ void __launch_bounds__(256)
@@ -265,12 +276,12 @@ cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* 
                               const float* shs, const float* cov3D_precomp,
                               const float* colors_precomp, const Camera& cam, int prefiltered,
                               int32_t* radii, float4* rec, float* depths, uint8_t* clamped,
-                              uint32_t* tiles_touched, uint32_t* depth_keys, int32_t* status) {
+                              uint32_t* tiles_touched, uint32_t* depth_keys, ushort4* rects, int32_t* status) {
   if (P == 0) return cudaSuccess;
   preprocess_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs,
                                                  cov3D_precomp, colors_precomp, cam, prefiltered,
                                                  radii, rec, depths, clamped, tiles_touched,
-                                                 depth_keys, status);
+                                                 depth_keys, rects, status);
   count_launch();
   return cudaGetLastError();
 }

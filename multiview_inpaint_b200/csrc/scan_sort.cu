@@ -330,7 +330,8 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
 template <typename KeyT>
 static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_dev, const KeyT* keys_in,
                                    const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out,
-                                   KeyT* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
+                                   KeyT* keys_alt, uint32_t* vals_alt, int end_bit, char* temp,
+                                   bool have_bases = false) {
   if (n <= 0) return cudaSuccess;
   constexpr int ITEMS = RsCfg<KeyT>::ITEMS;
   constexpr int TILE = RS_THREADS * ITEMS;
@@ -340,14 +341,21 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_
   uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
   uint32_t* tickets = reinterpret_cast<uint32_t*>(temp + align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4));
   uint32_t* status = reinterpret_cast<uint32_t*>(temp + align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4) + align_up(64));
-  cudaError_t e = cudaMemsetAsync(temp, 0, sort_temp_bytes(n, sizeof(KeyT), end_bit), s);
-  if (e != cudaSuccess) return e;
-
-  int hist_blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
-  if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-  rs_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys_in, n, n_dev, end_bit, hist);
-  rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
-  count_launch(2 + passes);
+  cudaError_t e;
+  if (have_bases) {  // the caller has filled `hist` with exclusive digit bases: clear tickets + status only
+    const size_t skip = align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4);
+    e = cudaMemsetAsync(temp + skip, 0, sort_temp_bytes(n, sizeof(KeyT), end_bit) - skip, s);
+    if (e != cudaSuccess) return e;
+    count_launch(passes);
+  } else {
+    e = cudaMemsetAsync(temp, 0, sort_temp_bytes(n, sizeof(KeyT), end_bit), s);
+    if (e != cudaSuccess) return e;
+    int hist_blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
+    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
+    rs_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys_in, n, n_dev, end_bit, hist);
+    rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
+    count_launch(2 + passes);
+  }
 
   const size_t smem = sizeof(KeyT) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 16);
   static bool attr_set = false;
@@ -377,8 +385,9 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_
 
 cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint32_t* keys_in,
                                   const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                                  uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
-  return sort_pairs_impl<uint32_t>(s, n, n_dev, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp);
+                                  uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp, bool have_bases) {
+  return sort_pairs_impl<uint32_t>(s, n, n_dev, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp,
+                                   have_bases);
 }
 cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
