@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--views-per-rank", type=int, default=4)
     ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
     ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
+    ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (ViewPipeline depth; 1 = one stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     return ap.parse_args()
@@ -238,34 +239,48 @@ def run_ours(args):
             av.learn(v, r.num_rendered)
         arena.all_reduce()
 
-    def step_resident():
+    pipe = mv.ViewPipeline(dev, depth=args.streams) if args.streams > 1 else None
+    import contextlib
+
+    def step_resident(pipe=pipe):
         """steady state: nothing blocks the host (GSR_FLAG_ASYNC); overflow is checked after the timed region"""
         arena.zero_()
-        for v in mine:
-            wt = wts_dev[v]
-            mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=args.flags,
-                                 capacity=av.capacity(v), async_result=av.slot(v))
+        with (pipe.step() if pipe else contextlib.nullcontext()):
+            for v in mine:
+                wt = wts_dev[v]
+                mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=args.flags,
+                                     capacity=av.capacity(v), async_result=av.slot(v), pipeline=pipe)
         arena.all_reduce()
 
-    cam_stage = torch.empty(35, device=dev)
-    wt_stage = torch.empty(3, H, W, device=dev)
+    n_slots = max(args.streams, 1)
+    cam_stage = [torch.empty(35, device=dev) for _ in range(n_slots)]
+    wt_stage = [torch.empty(3, H, W, device=dev) for _ in range(n_slots)]
+    loss_parts = [torch.zeros((), device=dev) for _ in range(n_slots)]
 
     def step_e2e():
         arena.zero_()
-        loss = torch.zeros((), device=dev)
-        for v in mine:
-            cam_stage.copy_(cam_pinned[v], non_blocking=True)             # H2D: camera
-            wt_stage.copy_(wts_cpu[v], non_blocking=True)                 # H2D: loss weights (the "GT image")
-            c = cams_cpu[v]
-            rs = GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
-                                               scale_modifier=1.0, viewmatrix=cam_stage[:16].view(4, 4),
-                                               projmatrix=cam_stage[16:32].view(4, 4), sh_degree=D, campos=cam_stage[32:35],
-                                               prefiltered=False)
-            res = mv.cuda_view_fwd_bwd(gauss, rs, lambda col: wt_stage, arena, flags=args.flags,
-                                       capacity=av.capacity(v), async_result=av.slot(v))
-            loss = loss + (res.color * wt_stage).sum()
+        for lp in loss_parts:
+            lp.zero_()
+        with (pipe.step() if pipe else contextlib.nullcontext()):
+            for v in mine:
+                def stage(v=v):   # runs on the view's stream: H2D of this view's camera and loss weights ("GT image")
+                    k = pipe.slot if pipe else 0
+                    cam_stage[k].copy_(cam_pinned[v], non_blocking=True)
+                    wt_stage[k].copy_(wts_cpu[v], non_blocking=True)
+                    c = cams_cpu[v]
+                    return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy,
+                                                         bg=bg, scale_modifier=1.0, viewmatrix=cam_stage[k][:16].view(4, 4),
+                                                         projmatrix=cam_stage[k][16:32].view(4, 4), sh_degree=D,
+                                                         campos=cam_stage[k][32:35], prefiltered=False)
+
+                def loss_grad(col):
+                    k = pipe.slot if pipe else 0
+                    loss_parts[k].add_((col * wt_stage[k]).sum())
+                    return wt_stage[k]
+                mv.cuda_view_fwd_bwd(gauss, stage, loss_grad, arena, flags=args.flags,
+                                     capacity=av.capacity(v), async_result=av.slot(v), pipeline=pipe)
         arena.all_reduce()
-        out = float(loss.item())                                           # D2H: the step's result (syncs)
+        out = float(torch.stack(loss_parts).sum().item())                  # D2H: the step's result (syncs)
         assert not av.check(mine), "capacity overflow inside the timed region"
         return out
     h2d = len(mine) * (35 * 4 + 3 * H * W * 4)
@@ -312,7 +327,7 @@ def run_ours(args):
     #      around every kernel stage (events between kernels cost a few %, so it is a separate pass) ----
     _C.profile_enable(True)
     _C.profile_collect()
-    ms_prof = timed(step_resident, args.steps)
+    ms_prof = timed(lambda: step_resident(None), args.steps)   # one stream: stage brackets must not overlap
     _C.profile_enable(False)
     stage_ms, stage_cnt = _C.profile_collect()
 
@@ -353,7 +368,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "P": P, "V": V, "N": N,
+        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "P": P, "V": V, "N": N,
                    "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce",
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

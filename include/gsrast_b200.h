@@ -109,6 +109,14 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
 int gsr_mark_visible(void* stream, int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present);
 
+/* Densification statistics of one view, fused (the reference does this in torch after backward():
+ * gs-simp/scene/gaussian_model.py:482-484 `xyz_gradient_accum[vis] += norm(viewspace.grad[vis, :2])`,
+ * `denom[vis] += 1`, and gs-simp/train.py:115 `max_radii2D[vis] = max(max_radii2D[vis], radii[vis])`,
+ * vis = radii > 0).  dL_dmean2D is the (P,3) output of gsr_backward.  Any of the three accumulators
+ * may be NULL. */
+int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
+                              float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii);
+
 /* ---- building blocks, exported so that parity tests can drive each stage through the C ABI ---- */
 
 /* Stable LSD onesweep radix sort of (key,value) pairs on key bits [0,end_bit), 8-bit digits.

@@ -64,6 +64,8 @@ _lib.gsr_backward.argtypes = [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp,
                               _vp, _vp, _sz, _u32]
 _lib.gsr_mark_visible.restype = _i
 _lib.gsr_mark_visible.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+_lib.gsr_accumulate_view_stats.restype = _i
+_lib.gsr_accumulate_view_stats.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
 _lib.gsr_sort_temp_bytes.restype = _sz
 _lib.gsr_sort_temp_bytes.argtypes = [_i64, _i, _i]
 _lib.gsr_sort_pairs_u64.restype = _i
@@ -83,6 +85,7 @@ _lib.gsr_profile_collect.restype = _i
 _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
+                    "gsr_accumulate_view_stats",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches",
@@ -277,6 +280,22 @@ def mark_visible(means3D, viewmatrix, projmatrix):
             _check(_lib.gsr_mark_visible(_stream(dev), P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix),
                                          present.data_ptr()), "mark_visible")
     return present
+
+
+def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_count=None, max_radii=None):
+    """One fused kernel for the densification statistics of a view (gaussian_model.py:482-484,
+    train.py:115): grad_norm_accum[vis] += ||dL_dmeans2D[vis, :2]||, visible_count[vis] += 1,
+    max_radii[vis] = max(max_radii[vis], radii[vis]) with vis = radii > 0."""
+    P = radii.shape[0]
+    dev = radii.device
+    for t, dt in ((radii, torch.int32), (dL_dmeans2D, torch.float32), (grad_norm_accum, torch.float32),
+                  (visible_count, torch.int32), (max_radii, torch.int32)):
+        if t is not None and not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise RuntimeError("accumulate_view_stats: tensors must be contiguous CUDA int32 / float32")
+    if P != 0:
+        with torch.cuda.device(dev):
+            _check(_lib.gsr_accumulate_view_stats(_stream(dev), P, _ptr(radii), _ptr(dL_dmeans2D), _ptr(grad_norm_accum),
+                                                  _ptr(visible_count), _ptr(max_radii)), "accumulate_view_stats")
 
 
 # ---- measurement hooks ---------------------------------------------------------------------------

@@ -458,6 +458,15 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   return 0;
 }
 
+int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
+                              float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii) {
+  if (P < 0 || (P > 0 && (!radii || (grad_norm_accum && !dL_dmean2D))))
+    return fail(GSR_E_INVALID, "gsr_accumulate_view_stats: bad argument");
+  GSR_CUDA(launch_view_stats(reinterpret_cast<cudaStream_t>(stream), P, radii, dL_dmean2D, grad_norm_accum,
+                             visible_count, max_radii), "view stats");
+  return 0;
+}
+
 int gsr_mark_visible(void* stream, int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present) {
   (void)projmatrix;  // the reference's frustum test only uses view-space z (x/y test disabled)

@@ -185,4 +185,7 @@ cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const floa
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
                                  float* dL_dsh, float* dL_dscale, float* dL_drot, bool accumulate);
 
+cudaError_t launch_view_stats(cudaStream_t s, int P, const int32_t* radii, const float* dL_dmean2D,
+                              float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii);
+
 }  // namespace gsr

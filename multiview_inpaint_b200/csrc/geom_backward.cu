@@ -557,6 +557,30 @@ geom_backward_kernel(int P, int D, int M, const float* __restrict__ means3D,
   }
 }
 
+__global__ void __launch_bounds__(256)
+view_stats_kernel(int P, const int32_t* __restrict__ radii, const float* __restrict__ dL_dmean2D,
+                  float* __restrict__ grad_norm_accum, int32_t* __restrict__ visible_count,
+                  int32_t* __restrict__ max_radii) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int32_t r = __ldg(radii + i);
+  if (r <= 0) return;
+  if (grad_norm_accum) {
+    const float gx = __ldg(dL_dmean2D + 3 * (size_t)i), gy = __ldg(dL_dmean2D + 3 * (size_t)i + 1);
+    grad_norm_accum[i] += sqrtf(gx * gx + gy * gy);
+  }
+  if (visible_count) visible_count[i] += 1;
+  if (max_radii) max_radii[i] = max(max_radii[i], r);
+}
+
+cudaError_t launch_view_stats(cudaStream_t s, int P, const int32_t* radii, const float* dL_dmean2D,
+                              float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii) {
+  if (P == 0) return cudaSuccess;
+  view_stats_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, radii, dL_dmean2D, grad_norm_accum, visible_count, max_radii);
+  count_launch();
+  return cudaGetLastError();
+}
+
 cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const float* means3D,
                                  const int32_t* radii, const float* shs, const uint8_t* clamped,
                                  const float* scales, const float* rotations,

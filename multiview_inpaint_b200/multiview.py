@@ -55,6 +55,10 @@ class GradArena:
         self.max_radii.zero_()
 
     def add_view_stats(self, dL_dmeans2D: torch.Tensor, radii: torch.Tensor):
+        if radii.is_cuda:  # one fused kernel instead of six torch launches
+            from . import _C
+            _C.accumulate_view_stats(radii, dL_dmeans2D, self.grad_norm_accum, self.visible_count, self.max_radii)
+            return
         vis = radii > 0
         self.grad_norm_accum += torch.norm(dL_dmeans2D[:, :2], dim=-1) * vis   # gaussian_model.py:483
         self.visible_count += vis.to(torch.int32)                               # gaussian_model.py:484
@@ -87,27 +91,102 @@ class ViewResult:
     num_rendered: int
 
 
+class ViewPipeline:
+    """Consecutive views of a step alternate between `depth` CUDA streams, so that the latency-bound
+    front end of view v+1 (K1, the sorts, binning: small grids that leave most of the GPU idle) runs
+    under the issue-bound blend kernels of view v.  Views stay independent up to the gradient arena:
+    the per-Gaussian backward of view v+1 is ordered after that of view v with an event (its plain
+    read-modify-writes of the arena must not interleave), everything before it overlaps freely.
+
+        with pipe.step():                       # side streams wait for the caller's stream ...
+            for v in views:
+                cuda_view_fwd_bwd(..., pipeline=pipe)
+        # ... and the caller's stream waits for them here (arena, outputs and stats are ready in stream order)
+
+    `dL_dcolor_fn` runs on the view's stream; anything else the caller does with a view's outputs
+    belongs after the `with` block."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(depth, 1))]
+        self._k = 0
+        self._prev_bwd = None
+        self.slot = 0
+
+    def step(self):
+        return _PipelineStep(self)
+
+    def _begin(self):
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for st in self.streams:
+            st.wait_event(ev)
+        self._prev_bwd = None
+
+    def _end(self):
+        main = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
+    def next_stream(self):
+        self.slot = self._k % len(self.streams)
+        self._k += 1
+        return torch.cuda.stream(self.streams[self.slot])
+
+    def order_backward(self):
+        if self._prev_bwd is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._prev_bwd)
+
+    def mark_backward_done(self):
+        self._prev_bwd = torch.cuda.Event()
+        self._prev_bwd.record(torch.cuda.current_stream(self.device))
+
+
+class _PipelineStep:
+    def __init__(self, pipe):
+        self.pipe = pipe
+
+    def __enter__(self):
+        self.pipe._begin()
+        return self.pipe
+
+    def __exit__(self, *exc):
+        self.pipe._end()
+        return False
+
+
 def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor],
                       arena: GradArena, flags: int = 0, capacity: int | None = None,
-                      async_result: torch.Tensor | None = None) -> ViewResult:
+                      async_result: torch.Tensor | None = None, pipeline: ViewPipeline | None = None) -> ViewResult:
     """One view through the CUDA path: forward, loss gradient, backward ADDING into `arena`.
     `gaussians`: means3D, shs, opacities, scales, rotations (post-activation, as render() passes them);
-    `settings`: GaussianRasterizationSettings.  With `async_result` (pinned int64[2]) + `capacity`
-    nothing in this call blocks the host; check the result with `AsyncViews.check()` after the step."""
+    `settings`: GaussianRasterizationSettings (a callable returning them is evaluated on the view's
+    stream, e.g. to stage a camera from pinned memory).  With `async_result` (pinned int64[2]) +
+    `capacity` nothing in this call blocks the host; check the result with `AsyncViews.check()` after
+    the step.  With `pipeline` the view runs on the pipeline's next stream (see ViewPipeline)."""
+    import contextlib
     from . import _C
-    rs = settings
-    e = torch.empty(0, device=gaussians["means3D"].device)
-    n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
-        rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
-        rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
-        rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags,
-        capacity=capacity, async_result=async_result)
-    dL = dL_dcolor_fn(color)
-    out = _C.rasterize_gaussians_backward(
-        rs.bg, gaussians["means3D"], radii, e, gaussians["scales"], gaussians["rotations"], rs.scale_modifier, e,
-        rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, dL, gaussians["shs"], rs.sh_degree, rs.campos,
-        geom, n, binning, img, flags=flags | _C.FLAG_ACCUMULATE, out=arena.views)
-    arena.add_view_stats(out[0], radii)
+    with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
+        rs = settings() if callable(settings) else settings
+        e = torch.empty(0, device=gaussians["means3D"].device)
+        n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
+            rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
+            rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+            rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags,
+            capacity=capacity, async_result=async_result)
+        dL = dL_dcolor_fn(color)
+        if pipeline is not None:
+            pipeline.order_backward()
+        out = _C.rasterize_gaussians_backward(
+            rs.bg, gaussians["means3D"], radii, e, gaussians["scales"], gaussians["rotations"], rs.scale_modifier, e,
+            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, dL, gaussians["shs"], rs.sh_degree, rs.campos,
+            geom, n, binning, img, flags=flags | _C.FLAG_ACCUMULATE, out=arena.views)
+        arena.add_view_stats(out[0], radii)
+        if pipeline is not None:
+            pipeline.mark_backward_done()
     return ViewResult(color, depth, radii, n)
 
 

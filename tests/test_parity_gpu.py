@@ -247,3 +247,44 @@ def test_accumulate_flag_adds_into_outputs(oracle):
     assert torch.equal(arena.visible_count, 3 * vis.int()) and torch.equal(arena.max_radii, radii)
     want = 3.0 * torch.norm(g1["dL_dmeans2D"][:, :2], dim=-1)
     assert (arena.grad_norm_accum - want).abs().max() <= 2e-3 * want.max()
+
+
+def test_view_pipeline_matches_single_stream(oracle):
+    """Views alternating over two streams (ViewPipeline) accumulate the same arena and statistics
+    as the one-stream loop (atomic-order noise only), across several steps."""
+    from multiview_inpaint_b200 import multiview as mv
+    from multiview_inpaint_b200.rasterizer import GaussianRasterizationSettings
+    W, H = 192, 128
+    sc = small_scene(20000, W, H, 1, 61, 6.0)
+    dev = torch.device("cuda")
+    gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    cams = [c.to(dev) for c in S.orbit_cameras(5, W, H, max_deg=8.0)]
+    bg = torch.zeros(3, device=dev)
+    wts = [S.loss_weights(W, H, 61 + v).to(dev) for v in range(5)]
+
+    def rs(c):
+        return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                                             scale_modifier=1.0, viewmatrix=c.world_view_transform,
+                                             projmatrix=c.full_proj_transform, sh_degree=sc["sh_degree"],
+                                             campos=c.camera_center, prefiltered=False)
+
+    def run(pipe):
+        arena = mv.GradArena(sc["P"], sc["M"], dev)
+        colors = []
+        for _ in range(3):
+            arena.zero_()
+            colors = []
+            with (pipe.step() if pipe else __import__("contextlib").nullcontext()):
+                for v in range(5):
+                    r = mv.cuda_view_fwd_bwd(gauss, rs(cams[v]), lambda c, v=v: wts[v], arena, pipeline=pipe)
+                    colors.append(r.color)
+        torch.cuda.synchronize()
+        return arena, colors
+
+    a0, c0 = run(None)
+    a1, c1 = run(mv.ViewPipeline(dev, depth=2))
+    for x, y in zip(c0, c1):
+        assert torch.equal(x, y)
+    assert (a0.flat - a1.flat).abs().max() <= 2e-3 * a0.flat.abs().max()
+    assert torch.equal(a0.visible_count, a1.visible_count) and torch.equal(a0.max_radii, a1.max_radii)
+    assert (a0.grad_norm_accum - a1.grad_norm_accum).abs().max() <= 2e-3 * a0.grad_norm_accum.max()
