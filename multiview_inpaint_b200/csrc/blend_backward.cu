@@ -63,8 +63,8 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   __shared__ __align__(16) unsigned char s_entries[BLEND_BATCH * ENTRY_BYTES];
   __shared__ uint32_t s_mask_arr[64];
   __shared__ uint32_t s_wmax[8];
-  const uint32_t s_ent = (uint32_t)__cvta_generic_to_shared(s_entries);
-  const uint32_t s_mask = (uint32_t)__cvta_generic_to_shared(s_mask_arr);
+  const uint32_t s_ent = pin_reg((uint32_t)__cvta_generic_to_shared(s_entries));
+  const uint32_t s_mask = pin_reg((uint32_t)__cvta_generic_to_shared(s_mask_arr));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -107,7 +107,7 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
     const uint32_t pos = (uint32_t)b * BLEND_BATCH + tid;
     const uint32_t bits = stage_entry<PRECISE>(pos < cta_last, range.x + pos, point_list, rec,
                                                s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
-    publish_masks(bits, s_mask, warp, lane);
+    publish_masks<false>(bits, s_mask, warp, lane);
     __syncthreads();
 
     if (warp_last > (uint32_t)b * BLEND_BATCH) {
@@ -119,7 +119,7 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
         if (warp_last - gbase < 32) m &= (1u << (warp_last - gbase)) - 1;  // entries >= warp_last
         const uint32_t ebase = s_ent + ws * 32 * ENTRY_BYTES;
         while (m) {
-          const int j = 31 - __clz(m);
+          const int j = bfind(m);
           m &= ~(1u << j);
           const uint32_t ea = ebase + j * ENTRY_BYTES;
           const uint32_t epos = gbase + j;  // 0-based list position == contributor index

@@ -87,12 +87,28 @@ __device__ __forceinline__ uint32_t stage_entry(bool valid, uint32_t list_index,
 
 // Publishes, for every target warp v, the ballot of "entry touches v's sub-tile" over this warp's
 // 32 staged entries: s_mask[v][warp].
+// REVERSED: bit (31 - i) stands for entry i, so that a front-to-back walk takes the next entry with
+// one count-leading-zeros (FLO.SH) instead of bit-reverse + find-leading-one.
+template <bool REVERSED>
 __device__ __forceinline__ void publish_masks(uint32_t bits, uint32_t s_mask, int warp, int lane) {
 #pragma unroll
   for (int v = 0; v < 8; v++) {
-    const unsigned m = __ballot_sync(0xffffffffu, (bits >> v) & 1u);
+    unsigned m = __ballot_sync(0xffffffffu, (bits >> v) & 1u);
+    if (REVERSED) m = __brev(m);
     if (lane == 0) sts32(s_mask + (v * 8 + warp) * 4, m);
   }
+}
+// index of the most significant set bit (x != 0): one FLO
+__device__ __forceinline__ int bfind(uint32_t x) {
+  int r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+// keeps a shared-window address in a register (nvcc otherwise re-derives it -- S2UR + ULEA + MOV --
+// inside the hot loop)
+__device__ __forceinline__ uint32_t pin_reg(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
 }
 
 // power (PRECISE) or power * log2e (fast) of entry (e0, e1) at pixel (pxf, pyf); also returns d.

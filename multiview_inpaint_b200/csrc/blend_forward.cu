@@ -32,8 +32,8 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
   __shared__ __align__(16) unsigned char s_entries[BLEND_BATCH * ENTRY_BYTES];
   __shared__ uint32_t s_mask_arr[64];  // [target warp][staging warp]
-  const uint32_t s_ent = (uint32_t)__cvta_generic_to_shared(s_entries);
-  const uint32_t s_mask = (uint32_t)__cvta_generic_to_shared(s_mask_arr);
+  const uint32_t s_ent = pin_reg((uint32_t)__cvta_generic_to_shared(s_entries));
+  const uint32_t s_mask = pin_reg((uint32_t)__cvta_generic_to_shared(s_mask_arr));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -41,12 +41,18 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
   const int px = tile_x0 + (warp & 1) * 8 + (lane & 7);
   const int py = tile_y0 + (warp >> 1) * 4 + (lane >> 3);
   const bool inside = px < W && py < H;
-  const float pxf = (float)px, pyf = (float)py;
+  // A finished pixel (outside the image, or saturated) gets a NaN x coordinate: its `power` is NaN,
+  // fails the ordered range test below and is skipped without a separate `done` test per pair.
+  float pxf = inside ? (float)px : __int_as_float(0x7fc00000);
+  const float pyf = (float)py;
 
   const uint2 range = ranges[tile];
   const int todo = (int)(range.y - range.x);
   const int rounds = (todo + BLEND_BATCH - 1) / BLEND_BATCH;
 
+  // == 1, but opaque to ptxas and per-lane (so it lives in a vector register): the shift below then
+  // needs no constant re-materialised per pair
+  const uint32_t one = (uint32_t)(px >= 0);
   float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dm = 15.0f;
   uint32_t last = 0;
   bool done = !inside;
@@ -57,30 +63,32 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
     const int pos = b * BLEND_BATCH + tid;
     const uint32_t bits = stage_entry<PRECISE>(pos < todo, range.x + pos, point_list, rec,
                                                s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
-    publish_masks(bits, s_mask, warp, lane);
+    publish_masks<true>(bits, s_mask, warp, lane);
     __syncthreads();
 
     // ---- walk the entries that can touch this warp's sub-tile ----
     if (!__all_sync(0xffffffffu, done)) {
 #pragma unroll 1
       for (int ws = 0; ws < 8; ws++) {
-        unsigned m = lds32(s_mask + (warp * 8 + ws) * 4);
-        const uint32_t ebase = s_ent + ws * 32 * ENTRY_BYTES;
+        unsigned m = lds32(s_mask + (warp * 8 + ws) * 4);  // bit 31 - j <=> entry j of this group
+        const uint32_t etop = s_ent + (ws * 32 + 31) * ENTRY_BYTES;          // entry 31 of the group
+        const uint32_t last_top = (uint32_t)(b * BLEND_BATCH + ws * 32 + 32);  // its 1-based list position
         while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const uint32_t ea = ebase + j * ENTRY_BYTES;
+          const int jr = bfind(m);  // entry 31 - jr
+          m &= ~(one << jr);
+          const uint32_t ea = etop - jr * ENTRY_BYTES;
           const float4 e0 = lds128(ea);
           const float4 e1 = lds128(ea + 16);
           float dx, dy;
           const float power = pair_power<PRECISE>(e0, e1, pxf, pyf, dx, dy);
-          if (done || power > 0.0f || power < e1.z) continue;
+          if (!(power <= 0.0f && power >= e1.z)) continue;  // power > 0, below the cut-off, or NaN (done)
           const float G = pair_gauss<PRECISE>(power);
           const float alpha = fminf(0.99f, MUL(e1.y, G));
           if (alpha < 1.0f / 255.0f) continue;
           const float test_T = MUL(T, SUB(1.0f, alpha));
           if (test_T < 0.0001f) {
             done = true;
+            pxf = __int_as_float(0x7fc00000);
             continue;
           }
           const float4 e2 = lds128(ea + 32);
@@ -90,7 +98,7 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
           C2 = FMA(e2.z, wgt, C2);
           if (T > 0.5f && test_T < 0.5f) Dm = __ldg(depths + __float_as_uint(e1.w));  // median depth
           T = test_T;
-          last = (uint32_t)(b * BLEND_BATCH + ws * 32 + j + 1);
+          last = last_top - (uint32_t)jr;
         }
       }
     }
