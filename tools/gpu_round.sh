@@ -10,5 +10,5 @@ timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.er
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -1 gpurun_out/bench_ref.json
 timeout 300 python tools/exp_breakdown.py > gpurun_out/breakdown.log 2>&1; cat gpurun_out/breakdown.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'blend_|geom_backward|preprocess_kernel|rs_onesweep|duplicate|scan_kernel|tile_ranges|rs_hist' -s 24 -c 24 -f -o gpurun_out/prof_full python tools/exp_view.py 3 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'blend_|geom_backward|preprocess_kernel|rs_onesweep|bin_expand|tile_prepare|view_stats|rs_hist' -s 32 -c 32 -f -o gpurun_out/prof_full python tools/exp_view.py 3 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
