@@ -109,6 +109,36 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
 int gsr_mark_visible(void* stream, int P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present);
 
+/* ---- multi-view backward (extension; the reference has no counterpart: it renders one camera per
+ * iteration, gs-simp/train.py:78,86) ----------------------------------------------------------------
+ * gsr_backward == gsr_backward_blend (K7: fills the packed per-Gaussian accumulator `scratch`) followed by
+ * the per-Gaussian chain rule (K8+K9).  For a batch of views of the SAME Gaussians the second half can run
+ * once for all views: the parameters are read once, the gradients are summed over the views on chip and
+ * written once (no read-modify-write of the gradient arrays, no memset), together with the densification
+ * statistics.  Requires shs (not colors_precomp), scales + rotations (not cov3D_precomp) and
+ * M in {1, 4, 16}; otherwise GSR_E_INVALID is returned and the caller runs gsr_backward per view.
+ * GSR_FLAG_ACCUMULATE adds to the outputs / statistics instead of overwriting them. */
+typedef struct {
+  const int32_t* radii;      /* (P,) of that view's gsr_forward                                      */
+  const char* geom_buffer;   /* that view's geometry buffer                                          */
+  const char* scratch;       /* that view's accumulator, filled by gsr_backward_blend                */
+  const float* viewmatrix;   /* (4,4)                                                                */
+  const float* projmatrix;   /* (4,4)                                                                */
+  const float* cam_pos;      /* (3,)                                                                 */
+  float* dL_dmean2D;         /* optional per-view (P,3) output (NULL to skip)                        */
+  float tan_fovx, tan_fovy;
+  int width, height;
+} gsr_view_grad;
+int gsr_backward_blend(void* stream, int P, const float* background, int width, int height,
+                       const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                       const float* dL_dpix, char* scratch, size_t scratch_bytes, uint32_t flags);
+int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* means3D, const float* shs,
+                            const float* scales, float scale_modifier, const float* rotations,
+                            const gsr_view_grad* views_host, int n_views, float* dL_dopacity,
+                            float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                            float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
+                            uint32_t flags);
+
 /* Densification statistics of one view, fused (the reference does this in torch after backward():
  * gs-simp/scene/gaussian_model.py:482-484 `xyz_gradient_accum[vis] += norm(viewspace.grad[vis, :2])`,
  * `denom[vis] += 1`, and gs-simp/train.py:115 `max_radii2D[vis] = max(max_radii2D[vis], radii[vis])`,

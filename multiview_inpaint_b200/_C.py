@@ -64,6 +64,16 @@ _lib.gsr_backward.argtypes = [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _vp, _vp,
                               _vp, _vp, _sz, _u32]
 _lib.gsr_mark_visible.restype = _i
 _lib.gsr_mark_visible.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+class GsrViewGrad(C.Structure):
+    _fields_ = [("radii", _vp), ("geom_buffer", _vp), ("scratch", _vp), ("viewmatrix", _vp), ("projmatrix", _vp),
+                ("cam_pos", _vp), ("dL_dmean2D", _vp), ("tan_fovx", _f), ("tan_fovy", _f), ("width", _i), ("height", _i)]
+
+
+_lib.gsr_backward_blend.restype = _i
+_lib.gsr_backward_blend.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _u32]
+_lib.gsr_backward_geom_multi.restype = _i
+_lib.gsr_backward_geom_multi.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp, C.POINTER(GsrViewGrad), _i,
+                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]
 _lib.gsr_accumulate_view_stats.restype = _i
 _lib.gsr_accumulate_view_stats.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
 _lib.gsr_sort_temp_bytes.restype = _sz
@@ -85,7 +95,7 @@ _lib.gsr_profile_collect.restype = _i
 _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
-                    "gsr_accumulate_view_stats",
+                    "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches",
@@ -280,6 +290,71 @@ def mark_visible(means3D, viewmatrix, projmatrix):
             _check(_lib.gsr_mark_visible(_stream(dev), P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix),
                                          present.data_ptr()), "mark_visible")
     return present
+
+
+def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBuffer, P, flags=None):
+    """K7 only (gsr_backward_blend): returns the packed per-Gaussian accumulator (uint8 scratch tensor)
+    that backward_geom_multi() consumes."""
+    flags = DEFAULT_FLAGS if flags is None else int(flags)
+    dev = dL_dout_color.device
+    H, W = dL_dout_color.shape[1], dL_dout_color.shape[2]
+    with torch.cuda.device(dev):
+        nscratch = int(_lib.gsr_backward_scratch_bytes(P))
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+        if P != 0:
+            background, dL_dout_color = _f32c(background, "background"), _f32c(dL_dout_color, "dL_dout_color")
+            _check(_lib.gsr_backward_blend(_stream(dev), P, _ptr(background), W, H, _ptr(geomBuffer), _ptr(binningBuffer),
+                                           _ptr(imageBuffer), _ptr(dL_dout_color), _ptr(scratch), nscratch, flags),
+                   "backward_blend")
+    return scratch
+
+
+def backward_geom_multi_supported(M: int) -> bool:
+    return M in (1, 4, 16)
+
+
+def backward_geom_multi(means3D, sh, scales, rotations, scale_modifier, degree, views, out, stats=None, flags=0,
+                        want_means2D=False):
+    """Batched K8+K9 over the views of one set of Gaussians (gsr_backward_geom_multi).
+    views: list of dicts with radii, geom, scratch, viewmatrix, projmatrix, campos, tanfovx, tanfovy, width, height.
+    out:   dict of preallocated dL_dmeans3D (P,3), dL_dsh (P,M,3), dL_dopacity (P,1), dL_dscales (P,3),
+           dL_drotations (P,4) -- written (or added to with FLAG_ACCUMULATE).
+    stats: optional (grad_norm_accum f32[P], visible_count i32[P], max_radii i32[P]).
+    Returns the list of per-view dL_dmeans2D (P,3) tensors if want_means2D else None."""
+    P, M = means3D.shape[0], sh.shape[1]
+    dev = means3D.device
+    keep = []   # contiguous copies must outlive the launch
+
+    def c(t, name):
+        t = _f32c(t, name)
+        keep.append(t)
+        return t
+    with torch.cuda.device(dev):
+        means3D, sh, scales, rotations = c(means3D, "means3D"), c(sh, "shs"), c(scales, "scales"), c(rotations, "rotations")
+        arr = (GsrViewGrad * len(views))()
+        m2d = []
+        for k, v in enumerate(views):
+            g = arr[k]
+            g.radii, g.geom_buffer, g.scratch = _ptr(v["radii"]), _ptr(v["geom"]), _ptr(v["scratch"])
+            g.viewmatrix, g.projmatrix, g.cam_pos = (_ptr(c(v["viewmatrix"], "viewmatrix")), _ptr(c(v["projmatrix"], "projmatrix")),
+                                                     _ptr(c(v["campos"], "campos")))
+            g.tan_fovx, g.tan_fovy, g.width, g.height = float(v["tanfovx"]), float(v["tanfovy"]), int(v["width"]), int(v["height"])
+            if want_means2D:
+                t = torch.empty(P, 3, dtype=torch.float32, device=dev)
+                m2d.append(t)
+                g.dL_dmean2D = t.data_ptr()
+            else:
+                g.dL_dmean2D = None
+        for name in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"):
+            t = out[name]
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), name
+        st = stats or (None, None, None)
+        if P != 0 and len(views) != 0:
+            _check(_lib.gsr_backward_geom_multi(
+                _stream(dev), P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(scales), float(scale_modifier), _ptr(rotations),
+                arr, len(views), _ptr(out["dL_dopacity"]), _ptr(out["dL_dmeans3D"]), _ptr(out["dL_dsh"]), _ptr(out["dL_dscales"]),
+                _ptr(out["dL_drotations"]), _ptr(st[0]), _ptr(st[1]), _ptr(st[2]), int(flags)), "backward_geom_multi")
+    return m2d if want_means2D else None
 
 
 def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_count=None, max_radii=None):

@@ -458,6 +458,81 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   return 0;
 }
 
+int gsr_backward_blend(void* stream, int P, const float* background, int width, int height,
+                       const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                       const float* dL_dpix, char* scratch, size_t scratch_bytes, uint32_t flags) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (P < 0 || width <= 0 || height <= 0) return fail(GSR_E_INVALID, "gsr_backward_blend: bad P/width/height");
+  if (P == 0) return 0;
+  if (!background || !geom_buffer || !binning_buffer || !image_buffer || !dL_dpix || !scratch)
+    return fail(GSR_E_INVALID, "gsr_backward_blend: null argument");
+  if (scratch_bytes < gsr_backward_scratch_bytes(P) || (reinterpret_cast<uintptr_t>(scratch) & 15))
+    return fail(GSR_E_INVALID, "gsr_backward_blend: scratch too small or misaligned");
+  const GeomLayout gl = geom_layout(P, flags);
+  const ImageLayout il = image_layout(width, height);
+  const BinningLayout bl = binning_layout(0, width, height, flags);  // point_list sits at offset 0 for any capacity
+  PROF(7);
+  GSR_CUDA(cudaMemsetAsync(scratch, 0, (size_t)P * 48, s), "memset accumulator");
+  PROF(8);
+  GSR_CUDA(launch_blend_backward(s, width, height, reinterpret_cast<const uint2*>(image_buffer + il.ranges),
+                                 reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list),
+                                 reinterpret_cast<const float4*>(geom_buffer + gl.rec), background,
+                                 reinterpret_cast<const float*>(image_buffer + il.final_T),
+                                 reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib), dL_dpix,
+                                 reinterpret_cast<float*>(scratch), (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
+  PROF(-1);
+  return 0;
+}
+
+int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* means3D, const float* shs,
+                            const float* scales, float scale_modifier, const float* rotations,
+                            const gsr_view_grad* views_host, int n_views, float* dL_dopacity,
+                            float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                            float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
+                            uint32_t flags) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (P < 0 || n_views < 0 || D < 0 || D > 3) return fail(GSR_E_INVALID, "gsr_backward_geom_multi: bad P/n_views/degree");
+  if (P == 0 || n_views == 0) return 0;
+  if (!geom_backward_multi_supported(M) || (D + 1) * (D + 1) > M)
+    return fail(GSR_E_INVALID, "gsr_backward_geom_multi: needs M in {1, 4, 16} and (D+1)^2 <= M");
+  if (!means3D || !shs || !scales || !rotations || !views_host || !dL_dopacity || !dL_dmean3D || !dL_dsh ||
+      !dL_dscale || !dL_drot)
+    return fail(GSR_E_INVALID, "gsr_backward_geom_multi: null argument (shs + scales/rotations inputs only)");
+  if ((reinterpret_cast<uintptr_t>(dL_drot) & 15) || (reinterpret_cast<uintptr_t>(rotations) & 15) ||
+      (reinterpret_cast<uintptr_t>(shs) & 15) || (reinterpret_cast<uintptr_t>(dL_dsh) & 15))
+    return fail(GSR_E_INVALID, "gsr_backward_geom_multi: dL_drot / dL_dsh / rotations / shs must be 16-byte aligned");
+  std::vector<ViewGrad> vs((size_t)n_views);
+  const GeomLayout gl = geom_layout(P, flags);
+  for (int v = 0; v < n_views; v++) {
+    const gsr_view_grad& in = views_host[v];
+    if (!in.radii || !in.geom_buffer || !in.scratch || !in.viewmatrix || !in.projmatrix || !in.cam_pos ||
+        in.width <= 0 || in.height <= 0 || (reinterpret_cast<uintptr_t>(in.scratch) & 15))
+      return fail(GSR_E_INVALID, "gsr_backward_geom_multi: bad view descriptor");
+    ViewGrad& o = vs[(size_t)v];
+    o.radii = in.radii;
+    o.clamped = reinterpret_cast<const uint8_t*>(in.geom_buffer + gl.clamped);
+    o.rec = reinterpret_cast<const float4*>(in.geom_buffer + gl.rec);
+    o.gacc = reinterpret_cast<const float*>(in.scratch);
+    o.view = in.viewmatrix;
+    o.proj = in.projmatrix;
+    o.campos = in.cam_pos;
+    o.dL_dmean2D = in.dL_dmean2D;
+    o.focal_x = in.width / (2.0f * in.tan_fovx);
+    o.focal_y = in.height / (2.0f * in.tan_fovy);
+    o.tan_fovx = in.tan_fovx;
+    o.tan_fovy = in.tan_fovy;
+    o.W = in.width;
+    o.H = in.height;
+  }
+  PROF(9);
+  GSR_CUDA(launch_geom_backward_multi(s, P, D, M, means3D, shs, scales, rotations, scale_modifier, vs.data(), n_views,
+                                      dL_dopacity, dL_dmean3D, dL_dsh, dL_dscale, dL_drot, grad_norm_accum,
+                                      visible_count, max_radii, (flags & GSR_FLAG_ACCUMULATE) != 0),
+           "multi-view per-Gaussian backward");
+  PROF(-1);
+  return 0;
+}
+
 int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii) {
   if (P < 0 || (P > 0 && (!radii || (grad_norm_accum && !dL_dmean2D))))

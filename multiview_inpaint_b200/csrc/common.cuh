@@ -185,6 +185,26 @@ cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const floa
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
                                  float* dL_dsh, float* dL_dscale, float* dL_drot, bool accumulate);
 
+// One view's inputs to the multi-view per-Gaussian backward (geom_backward_multi.cu)
+struct ViewGrad {
+  const int32_t* radii;
+  const uint8_t* clamped;
+  const float4* rec;
+  const float* gacc;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  float* dL_dmean2D;  // optional (P,3)
+  float focal_x, focal_y, tan_fovx, tan_fovy;
+  int W, H;
+};
+bool geom_backward_multi_supported(int M);
+cudaError_t launch_geom_backward_multi(cudaStream_t s, int P, int D, int M, const float* means3D, const float* shs,
+                                       const float* scales, const float* rotations, float scale_modifier,
+                                       const ViewGrad* views, int n_views, float* dL_dopacity,
+                                       float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                       float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
+                                       bool accumulate);
 cudaError_t launch_view_stats(cudaStream_t s, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii);
 

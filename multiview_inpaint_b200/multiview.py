@@ -190,6 +190,91 @@ def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.T
     return ViewResult(color, depth, radii, n)
 
 
+@dataclass
+class ViewState:
+    """What a view leaves behind between its forward + blend backward (K1..K7) and the batched
+    per-Gaussian backward (cuda_views_geom_backward)."""
+    color: torch.Tensor
+    depth: torch.Tensor
+    radii: torch.Tensor
+    num_rendered: int
+    geom: torch.Tensor
+    scratch: torch.Tensor
+    settings: object
+
+
+def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor], flags: int = 0,
+                        capacity: int | None = None, async_result: torch.Tensor | None = None,
+                        pipeline: ViewPipeline | None = None) -> ViewState:
+    """Forward (K1..K6), loss gradient, blend backward (K7) of one view; the per-Gaussian chain rule is
+    left to cuda_views_geom_backward(), which runs it ONCE for all views of the step.  With `pipeline`
+    the view runs on the pipeline's next stream; views need no mutual ordering here."""
+    import contextlib
+    from . import _C
+    with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
+        rs = settings() if callable(settings) else settings
+        e = torch.empty(0, device=gaussians["means3D"].device)
+        n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
+            rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
+            rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+            rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags,
+            capacity=capacity, async_result=async_result)
+        dL = dL_dcolor_fn(color)
+        scratch = _C.backward_blend(rs.bg, dL, geom, binning, img, gaussians["means3D"].shape[0], flags=flags)
+    return ViewState(color, depth, radii, n, geom, scratch, rs)
+
+
+def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena: GradArena, accumulate: bool = False,
+                             flags: int = 0, want_means2D: bool = False):
+    """Batched K8+K9 over `states` (one launch per four views): parameter gradients and densification
+    statistics are WRITTEN into `arena` (added with `accumulate`), so the arena needs no zeroing."""
+    from . import _C
+    if not states:
+        return None
+    views = [dict(radii=s.radii, geom=s.geom, scratch=s.scratch, viewmatrix=s.settings.viewmatrix,
+                  projmatrix=s.settings.projmatrix, campos=s.settings.campos, tanfovx=s.settings.tanfovx,
+                  tanfovy=s.settings.tanfovy, width=s.settings.image_width, height=s.settings.image_height) for s in states]
+    rs = states[0].settings
+    cur = torch.cuda.current_stream(gaussians["means3D"].device)
+    for st in states:   # produced on the pipeline's streams, consumed here: keep the allocator from recycling them early
+        for t in (st.radii, st.geom, st.scratch):
+            t.record_stream(cur)
+    return _C.backward_geom_multi(gaussians["means3D"], gaussians["shs"], gaussians["scales"], gaussians["rotations"],
+                                  rs.scale_modifier, rs.sh_degree, views, arena.views,
+                                  stats=(arena.grad_norm_accum, arena.visible_count, arena.max_radii),
+                                  flags=flags | (_C.FLAG_ACCUMULATE if accumulate else 0), want_means2D=want_means2D)
+
+
+def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: Sequence[Callable], arena: GradArena,
+                       flags: int = 0, capacities: Sequence[int] | None = None, async_results: Sequence | None = None,
+                       pipeline: ViewPipeline | None = None, accumulate: bool = False) -> list[ViewState]:
+    """A rank's share of a multi-view step: every view's forward + blend backward (two views in flight
+    with `pipeline`), then ONE batched per-Gaussian backward that writes the arena.  Falls back to the
+    per-view accumulate path when the batched kernel does not cover the configuration (M not in 1/4/16)."""
+    import contextlib
+    from . import _C
+    M = gaussians["shs"].shape[1]
+    if not _C.backward_geom_multi_supported(M):
+        if not accumulate:
+            arena.zero_()
+        out = []
+        with (pipeline.step() if pipeline else contextlib.nullcontext()):
+            for k, rs in enumerate(settings_list):
+                r = cuda_view_fwd_bwd(gaussians, rs, dL_dcolor_fns[k], arena, flags=flags,
+                                      capacity=capacities[k] if capacities else None,
+                                      async_result=async_results[k] if async_results else None, pipeline=pipeline)
+                out.append(ViewState(r.color, r.depth, r.radii, r.num_rendered, None, None, rs))
+        return out
+    states = []
+    with (pipeline.step() if pipeline else contextlib.nullcontext()):
+        for k, rs in enumerate(settings_list):
+            states.append(cuda_view_fwd_blend(gaussians, rs, dL_dcolor_fns[k], flags=flags,
+                                              capacity=capacities[k] if capacities else None,
+                                              async_result=async_results[k] if async_results else None, pipeline=pipeline))
+    cuda_views_geom_backward(gaussians, states, arena, accumulate=accumulate, flags=flags)
+    return states
+
+
 class AsyncViews:
     """Host-side bookkeeping for fully asynchronous view steps: one pinned (N, status) slot and one
     capacity per view.  Usage per step:  for v: cuda_view_fwd_bwd(..., capacity=a.capacity(v),

@@ -288,3 +288,63 @@ def test_view_pipeline_matches_single_stream(oracle):
     assert (a0.flat - a1.flat).abs().max() <= 2e-3 * a0.flat.abs().max()
     assert torch.equal(a0.visible_count, a1.visible_count) and torch.equal(a0.max_radii, a1.max_radii)
     assert (a0.grad_norm_accum - a1.grad_norm_accum).abs().max() <= 2e-3 * a0.grad_norm_accum.max()
+
+
+@pytest.mark.parametrize("deg,n_views", [(3, 4), (3, 6), (1, 3), (0, 2), (2, 1)])
+def test_batched_multiview_backward_matches_per_view_sum(oracle, deg, n_views):
+    """gsr_backward_blend + gsr_backward_geom_multi (parameters read once, gradients summed over the
+    views on chip, written once) == the per-view gsr_backward calls accumulated into the arena,
+    including the densification statistics and the per-view dL/dmean2D.  deg 2 (M = 9) exercises the
+    fallback inside cuda_views_fwd_bwd."""
+    from multiview_inpaint_b200 import _C, multiview as mv
+    from multiview_inpaint_b200.rasterizer import GaussianRasterizationSettings
+    W, H = 176, 112
+    sc = small_scene(15000, W, H, deg, 71 + deg, 6.0)
+    dev = torch.device("cuda")
+    gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    cams = [c.to(dev) for c in S.orbit_cameras(n_views, W, H, max_deg=10.0)]
+    bg = torch.tensor([0.2, 0.1, 0.3], device=dev)
+    wts = [S.loss_weights(W, H, 100 + v).to(dev) for v in range(n_views)]
+    rss = [GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                                         scale_modifier=1.0, viewmatrix=c.world_view_transform,
+                                         projmatrix=c.full_proj_transform, sh_degree=sc["sh_degree"],
+                                         campos=c.camera_center, prefiltered=False) for c in cams]
+    # reference: one accumulate call per view
+    a0 = mv.GradArena(sc["P"], sc["M"], dev)
+    m2d_ref = []
+    for v in range(n_views):
+        e = torch.empty(0, device=dev)
+        rs = rss[v]
+        n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
+            rs.bg, gauss["means3D"], e, gauss["opacities"], gauss["scales"], gauss["rotations"], 1.0, e, rs.viewmatrix,
+            rs.projmatrix, rs.tanfovx, rs.tanfovy, H, W, gauss["shs"], rs.sh_degree, rs.campos, False)
+        g = _C.rasterize_gaussians_backward(rs.bg, gauss["means3D"], radii, e, gauss["scales"], gauss["rotations"], 1.0, e,
+                                            rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, wts[v], gauss["shs"],
+                                            rs.sh_degree, rs.campos, geom, n, binning, img,
+                                            flags=_C.FLAG_ACCUMULATE, out=a0.views)
+        a0.add_view_stats(g[0], radii)
+        m2d_ref.append(g[0])
+    # batched, with garbage in the arena beforehand (it must be overwritten, not added to)
+    a1 = mv.GradArena(sc["P"], sc["M"], dev)
+    a1.flat.fill_(7.0)
+    a1.grad_norm_accum.fill_(3.0)
+    a1.visible_count.fill_(5)
+    a1.max_radii.fill_(9)
+    pipe = mv.ViewPipeline(dev, depth=2)
+    states = mv.cuda_views_fwd_bwd(gauss, rss, [lambda c, v=v: wts[v] for v in range(n_views)], a1, pipeline=pipe)
+    torch.cuda.synchronize()
+    scale = a0.flat.abs().max()
+    assert (a0.flat - a1.flat).abs().max() <= 2e-3 * scale
+    for name in a0.views:
+        d = (a0.views[name] - a1.views[name]).abs().max()
+        assert d <= 2e-3 * a0.views[name].abs().max() + 1e-12, (name, float(d))
+    assert torch.equal(a0.visible_count, a1.visible_count) and torch.equal(a0.max_radii, a1.max_radii)
+    assert (a0.grad_norm_accum - a1.grad_norm_accum).abs().max() <= 2e-3 * a0.grad_norm_accum.max()
+    if _C.backward_geom_multi_supported(sc["M"]):
+        # per-view dL/dmean2D on request, and accumulate mode doubles the arena
+        m2d = mv.cuda_views_geom_backward(gauss, states, a1, accumulate=True, want_means2D=True)
+        torch.cuda.synchronize()
+        for x, y in zip(m2d_ref, m2d):
+            assert (x - y).abs().max() <= 2e-3 * x.abs().max() + 1e-12
+        assert (2 * a0.flat - a1.flat).abs().max() <= 4e-3 * scale
+        assert torch.equal(2 * a0.visible_count, a1.visible_count)
