@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
     ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
     ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (ViewPipeline depth; 1 = one stream)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "nvls"],
+                    help="arena collective: NCCL, the in-switch multimem kernel, or whichever is faster here")
     ap.add_argument("--per-view-backward", action="store_true", help="K8+K9 per view (accumulate) instead of one batched launch per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
@@ -226,7 +228,14 @@ def run_ours(args):
         c = cams_cpu[v]
         buf = torch.cat([c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center.reshape(-1)]).pin_memory()
         cam_pinned[v] = buf
-    arena = mv.GradArena(P, M, dev)
+    arena = mv.GradArena(P, M, dev, symmetric=(args.allreduce != "nccl"))
+    comm = {"method": "none"}
+    if world > 1:
+        if args.allreduce == "auto":
+            comm = arena.calibrate()
+        else:
+            arena.method = args.allreduce if arena._mc else "nccl"
+            comm = {"method": arena.method}
     stats = {}
     av = mv.AsyncViews(n_views)
 
@@ -388,7 +397,7 @@ def run_ours(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_geom_backward": not args.per_view_backward, "P": P, "V": V, "N": N,
-                   "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce",
+                   "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce", "allreduce": comm,
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

@@ -139,6 +139,20 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
                             float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
                             uint32_t flags);
 
+/* In-switch all-reduce (NVLink SHARP / NVLS) of one symmetric buffer that every rank has mapped through the
+ * same MULTICAST address `multicast_ptr` (torch.distributed._symmetric_memory: handle.multicast_ptr).
+ * Three segments, given as byte offsets into the buffer: float32 SUM (n_f32 a multiple of 4, 16-byte
+ * aligned offset), int32 SUM, int32 MAX.  Rank `rank` of `world` reduces and re-broadcasts slice `rank` of
+ * every segment with multimem.ld_reduce / multimem.st.  The caller must order the launch between two
+ * cross-rank barriers on `stream`.  blocks <= 0 picks a default grid.
+ * Row sparsity (optional, sparse_rows = 0 disables it): floats [sparse_first_f32, sparse_first_f32 +
+ * sparse_rows * sparse_row_f32) of the float segment form a row-major matrix whose row g is known to be zero
+ * on every rank whenever the SUM over ranks of element g of the int32 SUM segment is zero (the (P,M,3) SH
+ * gradient vs the visibility count): those rows are skipped.  Needs sparse_row_f32 % 4 == 0. */
+int gsr_nvls_all_reduce(void* stream, void* multicast_ptr, size_t off_f32, size_t n_f32, size_t off_add_s32,
+                        size_t n_add_s32, size_t off_max_s32, size_t n_max_s32, int rank, int world, int blocks,
+                        size_t sparse_first_f32, size_t sparse_rows, int sparse_row_f32);
+
 /* Densification statistics of one view, fused (the reference does this in torch after backward():
  * gs-simp/scene/gaussian_model.py:482-484 `xyz_gradient_accum[vis] += norm(viewspace.grad[vis, :2])`,
  * `denom[vis] += 1`, and gs-simp/train.py:115 `max_radii2D[vis] = max(max_radii2D[vis], radii[vis])`,

@@ -74,6 +74,8 @@ _lib.gsr_backward_blend.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _v
 _lib.gsr_backward_geom_multi.restype = _i
 _lib.gsr_backward_geom_multi.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp, C.POINTER(GsrViewGrad), _i,
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]
+_lib.gsr_nvls_all_reduce.restype = _i
+_lib.gsr_nvls_all_reduce.argtypes = [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _i, _i, _i, _sz, _sz, _i]
 _lib.gsr_accumulate_view_stats.restype = _i
 _lib.gsr_accumulate_view_stats.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
 _lib.gsr_sort_temp_bytes.restype = _sz
@@ -95,7 +97,7 @@ _lib.gsr_profile_collect.restype = _i
 _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
-                    "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi",
+                    "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_nvls_all_reduce",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches",
@@ -355,6 +357,16 @@ def backward_geom_multi(means3D, sh, scales, rotations, scale_modifier, degree, 
                 arr, len(views), _ptr(out["dL_dopacity"]), _ptr(out["dL_dmeans3D"]), _ptr(out["dL_dsh"]), _ptr(out["dL_dscales"]),
                 _ptr(out["dL_drotations"]), _ptr(st[0]), _ptr(st[1]), _ptr(st[2]), int(flags)), "backward_geom_multi")
     return m2d if want_means2D else None
+
+
+def nvls_all_reduce(multicast_ptr: int, device, off_f32: int, n_f32: int, off_add_s32: int, n_add_s32: int,
+                    off_max_s32: int, n_max_s32: int, rank: int, world: int, blocks: int = 0,
+                    sparse_first_f32: int = 0, sparse_rows: int = 0, sparse_row_f32: int = 0):
+    """gsr_nvls_all_reduce on the current stream of `device` (see include/gsrast_b200.h)."""
+    with torch.cuda.device(device):
+        _check(_lib.gsr_nvls_all_reduce(_stream(device), multicast_ptr, off_f32, n_f32, off_add_s32, n_add_s32,
+                                        off_max_s32, n_max_s32, rank, world, blocks, sparse_first_f32, sparse_rows,
+                                        sparse_row_f32), "nvls_all_reduce")
 
 
 def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_count=None, max_radii=None):

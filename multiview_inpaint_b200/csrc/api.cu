@@ -533,6 +533,19 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
   return 0;
 }
 
+int gsr_nvls_all_reduce(void* stream, void* multicast_ptr, size_t off_f32, size_t n_f32, size_t off_add_s32,
+                        size_t n_add_s32, size_t off_max_s32, size_t n_max_s32, int rank, int world, int blocks,
+                        size_t sparse_first_f32, size_t sparse_rows, int sparse_row_f32) {
+  if (!multicast_ptr || world < 1 || rank < 0 || rank >= world || (n_f32 & 3) || (off_f32 & 15) || (off_add_s32 & 3) ||
+      (off_max_s32 & 3) || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15))
+    return fail(GSR_E_INVALID, "gsr_nvls_all_reduce: bad argument (alignment / rank / multicast pointer)");
+  GSR_CUDA(launch_nvls_allreduce(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<char*>(multicast_ptr), off_f32,
+                                 n_f32, off_add_s32, n_add_s32, off_max_s32, n_max_s32, rank, world, blocks,
+                                 sparse_first_f32, sparse_rows, sparse_row_f32),
+           "nvls all-reduce");
+  return 0;
+}
+
 int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii) {
   if (P < 0 || (P > 0 && (!radii || (grad_norm_accum && !dL_dmean2D))))

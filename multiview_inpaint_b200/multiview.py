@@ -27,32 +27,92 @@ def shard_views(n_views: int, rank: int, world: int) -> list[int]:
 
 class GradArena:
     """Flat fp32 buffer [dL_dmeans3D | dL_dsh | dL_dopacity | dL_dscales | dL_drotations] =
-    3 + 3M + 1 + 3 + 4 floats per Gaussian (14 / 23 / 59 at M = 1 / 4 / 16), plus typed views."""
+    3 + 3M + 1 + 3 + 4 floats per Gaussian (14 / 23 / 59 at M = 1 / 4 / 16), plus typed views, plus the
+    densification statistics.  Everything lives in ONE allocation
+        [ flat | grad_norm_accum f32[P] | visible_count i32[P] | max_radii i32[P] ]
+    so that one collective covers it.  With `symmetric=True` (CUDA, world > 1) the allocation is
+    symmetric memory with an NVSwitch multicast mapping and all_reduce() runs the in-switch kernel
+    gsr_nvls_all_reduce (multimem.ld_reduce / multimem.st) between two cross-rank barriers; without
+    multicast support (or on CPU / gloo) it falls back to torch.distributed all-reduces."""
 
-    def __init__(self, P: int, M: int, device):
+    def __init__(self, P: int, M: int, device, symmetric: bool = False, group=None):
         self.P, self.M = P, M
+        device = torch.device(device)
         sizes = [("dL_dmeans3D", (P, 3)), ("dL_dsh", (P, M, 3)), ("dL_dopacity", (P, 1)),
                  ("dL_dscales", (P, 3)), ("dL_drotations", (P, 4))]
         # each slice starts on a 16-byte boundary (float4 stores in the kernels)
         offs, off = [], 0
         for _, shp in sizes:
             offs.append(off)
-            n = 1
-            for s in shp:
-                n *= s
-            off += (n + 3) // 4 * 4
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+            off += (_numel(shp) + 3) // 4 * 4
+        n_flat, Pp = off, (P + 3) // 4 * 4
+        total = n_flat + 3 * Pp
+        self._handle, self._mc = None, 0
+        self.group = group
+        storage = None
+        if symmetric and device.type == "cuda" and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size(group) > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                storage = symm_mem.empty(max(total, 4), dtype=torch.float32, device=device)
+                self._handle = symm_mem.rendezvous(storage, group if group is not None else dist.group.WORLD)
+                self._mc = int(getattr(self._handle, "multicast_ptr", 0) or 0)
+            except Exception as ex:   # no symmetric memory on this system / build: plain allocation + NCCL
+                self._handle, self._mc, storage = None, 0, None
+                self.symmetric_error = repr(ex)
+        if storage is None:
+            storage = torch.empty(max(total, 4), dtype=torch.float32, device=device)
+        storage.zero_()
+        self.storage = storage
+        self._n_f32 = n_flat + Pp                     # float SUM segment: flat + grad_norm_accum
+        self._sh_first = offs[1]                      # first float of the (P, M, 3) SH gradient inside it
+        self.sparse = True                            # skip SH rows of Gaussians no rank saw (visible_count == 0)
+        self._off_cnt, self._off_max = 4 * (n_flat + Pp), 4 * (n_flat + 2 * Pp)   # byte offsets of the int segments
+        self.flat = storage[:n_flat]
         self.views = {name: self.flat[o:o + _numel(shp)].view(*shp) for (name, shp), o in zip(sizes, offs)}
-        # densification statistics (kept out of the float arena: different reductions)
-        self.grad_norm_accum = torch.zeros(P, dtype=torch.float32, device=device)
-        self.visible_count = torch.zeros(P, dtype=torch.int32, device=device)
-        self.max_radii = torch.zeros(P, dtype=torch.int32, device=device)
+        # densification statistics (different reductions: SUM / SUM / MAX)
+        self.grad_norm_accum = storage[n_flat:n_flat + P]
+        self.visible_count = storage[n_flat + Pp:n_flat + Pp + P].view(torch.int32)
+        self.max_radii = storage[n_flat + 2 * Pp:n_flat + 2 * Pp + P].view(torch.int32)
+
+    @property
+    def uses_nvls(self) -> bool:
+        return self._mc != 0 and self.method == "nvls"
+
+    method = "nvls"   # preferred collective when a multicast mapping exists; see calibrate()
+
+    def calibrate(self, iters: int = 3) -> dict:
+        """Times the in-switch kernel against the NCCL all-reduce on this arena (contents are summed
+        repeatedly: call it before the arena holds anything of value) and keeps the faster one.  All ranks
+        agree because the decision uses the max over ranks.  At 2 GPUs NCCL's direct peer copies win; from
+        4 GPUs on the switch reduction does."""
+        if not self._mc:
+            self.method = "nccl"
+            return {"method": "nccl", "reason": "no multicast mapping"}
+        res = {}
+        dev = self.storage.device
+        self.visible_count.fill_(1)   # worst case for the row-sparse kernel: every Gaussian seen by somebody
+        for m in ("nccl", "nvls"):
+            self.method = m
+            self.all_reduce()
+            torch.cuda.synchronize(dev)
+            dist.barrier(self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                self.all_reduce()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            res[m + "_ms"] = float(t.item())
+        self.method = "nvls" if res["nvls_ms"] < res["nccl_ms"] else "nccl"
+        res["method"] = self.method
+        self.zero_()
+        return res
 
     def zero_(self):
-        self.flat.zero_()
-        self.grad_norm_accum.zero_()
-        self.visible_count.zero_()
-        self.max_radii.zero_()
+        self.storage.zero_()
 
     def add_view_stats(self, dL_dmeans2D: torch.Tensor, radii: torch.Tensor):
         if radii.is_cuda:  # one fused kernel instead of six torch launches
@@ -65,11 +125,21 @@ class GradArena:
         torch.maximum(self.max_radii, radii, out=self.max_radii)                # train.py:115
 
     def all_reduce(self, group=None):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self.grad_norm_accum, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self.visible_count, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
+        group = group if group is not None else self.group
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        if self._mc and self.method == "nvls":
+            from . import _C
+            h = self._handle
+            h.barrier()      # every replica is complete (stream-ordered after this rank's kernels)
+            rows = self.P if (self.sparse and (3 * self.M) % 4 == 0) else 0
+            _C.nvls_all_reduce(self._mc, self.storage.device, 0, self._n_f32, self._off_cnt, self.P, self._off_max, self.P,
+                               h.rank, h.world_size, 0, self._sh_first, rows, 3 * self.M)
+            h.barrier()      # every slice has been written back everywhere
+            return
+        dist.all_reduce(self.storage[:self._n_f32], op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.visible_count, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
 
     @property
     def bytes(self) -> int:

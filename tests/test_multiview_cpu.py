@@ -42,8 +42,8 @@ def _run_rank(rank, world, port, out_dir):
     arena = mv.GradArena(P, sc["M"], "cpu")
     mine = mv.sharded_step(lambda v: _oracle_view(sc, cams[v], S.loss_weights(W, H, v), arena), N_VIEWS, arena)
     assert mine == list(range(rank, N_VIEWS, world))
-    torch.save({"flat": arena.flat, "norm": arena.grad_norm_accum, "vis": arena.visible_count,
-                "maxr": arena.max_radii, "mine": mine}, os.path.join(out_dir, f"rank{rank}.pt"))
+    torch.save({"flat": arena.flat.clone(), "norm": arena.grad_norm_accum.clone(), "vis": arena.visible_count.clone(),
+                "maxr": arena.max_radii.clone(), "mine": mine}, os.path.join(out_dir, f"rank{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 

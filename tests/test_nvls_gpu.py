@@ -1,0 +1,57 @@
+"""World-2 check of the in-switch arena all-reduce (gsr_nvls_all_reduce over symmetric memory with an
+NVSwitch multicast mapping) against NCCL.  Needs two GPUs: skipped on the single-GPU test box."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from multiview_inpaint_b200 import multiview as mv
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    for M in (16, 4, 1):
+        P = 70001
+        a = mv.GradArena(P, M, dev, symmetric=True)
+        b = mv.GradArena(P, M, dev, symmetric=False)
+        g = torch.Generator(device=dev)
+        g.manual_seed(5 + rank)
+        for x in (a, b):
+            g.manual_seed(5 + rank)
+            x.flat.copy_(torch.randn(x.flat.shape, device=dev, generator=g))
+            x.grad_norm_accum.copy_(torch.rand(P, device=dev, generator=g))
+            x.visible_count.copy_(torch.randint(0, 3, (P,), device=dev, generator=g, dtype=torch.int32))
+            x.max_radii.copy_(torch.randint(0, 900, (P,), device=dev, generator=g, dtype=torch.int32))
+            x.views["dL_dsh"][x.visible_count == 0] = 0     # unseen Gaussians have zero rows (what the kernels write)
+        a.method = "nvls"
+        a.all_reduce()
+        b.all_reduce()
+        torch.cuda.synchronize()
+        res[M] = dict(nvls=a.uses_nvls, err=float((a.flat - b.flat).abs().max()), scale=float(b.flat.abs().max()),
+                      norm=float((a.grad_norm_accum - b.grad_norm_accum).abs().max()),
+                      ints=bool(torch.equal(a.visible_count, b.visible_count) and torch.equal(a.max_radii, b.max_radii)))
+    torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nvls_arena_all_reduce_matches_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, 29541, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        for M, d in res.items():
+            if not d["nvls"]:
+                pytest.skip("no multicast mapping on this system")
+            assert d["err"] <= 1e-5 * d["scale"] and d["norm"] <= 1e-5 and d["ints"], (M, d)
