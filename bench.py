@@ -45,6 +45,7 @@ def parse():
                     help="arena collective: NCCL, the in-switch multimem kernel, or whichever is faster here")
     ap.add_argument("--per-view-backward", action="store_true", help="K8+K9 per view (accumulate) instead of one batched launch per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")
     ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     return ap.parse_args()
 
@@ -250,6 +251,7 @@ def run_ours(args):
         arena.all_reduce()
 
     pipe = mv.ViewPipeline(dev, depth=args.streams) if args.streams > 1 else None
+    throttle = mv.StepThrottle(2)   # host at most two steps ahead of the GPU (bounded scratch; see StepThrottle)
     import contextlib
 
     def step_resident(pipe=pipe):
@@ -267,6 +269,7 @@ def run_ours(args):
                                   arena, flags=args.flags, capacities=[av.capacity(v) for v in mine],
                                   async_results=[av.slot(v) for v in mine], pipeline=pipe)
         arena.all_reduce()
+        throttle.tick(dev)
 
     n_slots = max(args.streams, 1)
     cam_stage = {v: torch.empty(35, device=dev) for v in mine}   # per view: the batched K8+K9 reads every view's camera at the end
@@ -342,8 +345,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _C.kernel_launches()
+    a0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms_total = timed(step_resident, args.steps)
     launches = _C.kernel_launches() - l0
+    device_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - a0   # cudaMalloc calls inside the timed region (want 0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     assert not av.check(mine), "capacity overflow inside the timed region"
@@ -362,6 +367,25 @@ def run_ours(args):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- ablation baseline on the same device and data (N = 1 only): kernels with the STRUCTURE of the public
+    #      rasterizer the reference depends on (GSR_FLAG_REFERENCE: host round trip for N, one 64-bit cub sort,
+    #      thread-per-pixel blend, 9 atomics per pair), one view at a time on one stream, arena zeroed per step.
+    #      A stand-in: the reference's own extension is not in its tree and cannot be built offline. ----
+    ref_struct = None
+    if world == 1 and not args.no_reference_structure:
+        def step_refstruct():
+            arena.zero_()
+            for v in mine:
+                wt = wts_dev[v]
+                mv.cuda_view_fwd_bwd(gauss, settings(cams_dev[v]), lambda c, wt=wt: wt, arena, flags=_C.FLAG_REFERENCE, capacity=0)
+        for _ in range(2):
+            step_refstruct()
+        rs_steps = max(2, min(args.steps, 5))
+        ms_rs = timed(step_refstruct, rs_steps)
+        ref_struct = {"value": n_views * rs_steps / (ms_rs / 1000.0), "unit": UNIT, "ms_per_view": ms_rs / (n_views * rs_steps),
+                      "steps": rs_steps, "flags": _C.FLAG_REFERENCE,
+                      "note": "reference-STRUCTURE stand-in kernels of this repo (csrc/refstruct.cu), not the reference's binary"}
 
     views_total = n_views * args.steps
     value = views_total / (ms_total / 1000.0)
@@ -401,6 +425,7 @@ def run_ours(args):
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "alloc": {"cudaMalloc_in_timed_region": int(device_allocs), "reserved_gb": round(torch.cuda.memory_reserved(dev) / 2**30, 2)},
         "clocks": sampler.summary(),
         "profiled_ms_per_step": ms_prof / args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -410,6 +435,8 @@ def run_ours(args):
                               "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
         "stages": stages,
     }
+    if ref_struct is not None:
+        line["reference_structure"] = ref_struct
 
     # ---- cpu_baseline: rank 0, N = 1 only ----
     if world == 1 and not args.no_cpu_baseline:

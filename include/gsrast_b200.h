@@ -43,6 +43,12 @@ extern "C" {
                                      Both produce bit-identical point lists and tile ranges.          */
 #define GSR_FLAG_PRECISE       2u /* blend with the oracle's exact op order, expf and IEEE division
                                      (parity build); default is ex2.approx / rcp.approx, ~2e-7 in colour */
+#define GSR_FLAG_REFERENCE     4u /* ablation baseline, NOT the product path: kernels with the STRUCTURE of the
+                                     public rasterizer the reference depends on (its source is absent from
+                                     the reference tree): host round trip for N, one 64-bit key sort by
+                                     cub::DeviceRadixSort, one thread per pixel with no culling, nine global
+                                     atomicAdd per contributing (pixel, Gaussian) pair.  Same results as
+                                     GSR_FLAG_PRECISE (forward bit-identical).  Implies BINNING_KEY64.     */
 /* flag for gsr_backward: ADD the per-Gaussian parameter gradients (dL_dmean3D, dL_dsh, dL_dcolor,
  * dL_dopacity, dL_dcov3D, dL_dscale, dL_drot) into the output buffers instead of overwriting them, and
  * leave culled Gaussians untouched.  Used by the view-sharded multi-view step, where the outputs are

@@ -25,6 +25,7 @@ LIB_PATH = os.path.join(_HERE, "libgsrast_b200.so")
 
 FLAG_BINNING_KEY64 = 1
 FLAG_PRECISE = 2
+FLAG_REFERENCE = 4     # reference-structure ablation baseline (cub sort, thread-per-pixel blend, 9 atomics/pair)
 FLAG_ACCUMULATE = 8
 FLAG_ASYNC = 16
 NUM_STAGES = 10

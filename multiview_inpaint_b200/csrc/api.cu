@@ -8,6 +8,7 @@
 //   forward : K1 preprocess -> [depth sort] -> K2 scan -> (N to host) -> K3 duplicate -> K4 sort
 //             -> K5 ranges -> K6 blend
 //   backward: K7 blend backward -> K8+K9 per-Gaussian backward
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -60,7 +61,8 @@ static int fail(int code, const char* msg) {
     if (_e != cudaSuccess) return fail_cuda(_e, where); \
   } while (0)
 
-static bool key64(uint32_t flags) { return (flags & GSR_FLAG_BINNING_KEY64) != 0; }
+static bool refstruct(uint32_t flags) { return (flags & GSR_FLAG_REFERENCE) != 0; }
+static bool key64(uint32_t flags) { return (flags & (GSR_FLAG_BINNING_KEY64 | GSR_FLAG_REFERENCE)) != 0; }
 
 GeomLayout geom_layout(int P, uint32_t flags) {
   GeomLayout L{};
@@ -129,6 +131,7 @@ BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags) {
   L.keys_a = take(n * kb);
   L.keys_b = take(n * kb);
   L.temp_bytes = sort_temp_bytes(N, (int)kb, end_bit);
+  if (refstruct(flags)) L.temp_bytes = std::max(L.temp_bytes, ref_sort_temp_bytes(N, end_bit));
   L.temp = take(L.temp_bytes);
   L.big_items = k64 ? (size_t)-1 : take((size_t)bin_big_capacity(N) * 16);
   L.bytes = off;
@@ -276,6 +279,11 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   int64_t N = 0;
   const uint32_t* order = nullptr;
   const bool async = (flags & GSR_FLAG_ASYNC) != 0;
+  const bool ref = refstruct(flags);
+  if (ref) {  // the reference learns N on the host mid-pipeline and sizes everything exactly
+    if (async) return fail(GSR_E_INVALID, "gsr_forward: GSR_FLAG_REFERENCE excludes GSR_FLAG_ASYNC");
+    capacity_hint = 0;
+  }
   int64_t* result = async ? num_rendered_host : pin.result;  // [0] = N, [1] = status bits
   if (async && capacity_hint <= 0) return fail(GSR_E_INVALID, "gsr_forward: GSR_FLAG_ASYNC needs a capacity_hint");
   if (P > 0) {
@@ -321,7 +329,16 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       // one in "b" -- pick a so that the result is always point_list (offset 0)
       uint32_t* va = (passes & 1) ? vals_alt : point_list;
       uint32_t* valt = (passes & 1) ? va : vals_alt;
-      if (k64) {
+      if (ref) {  // reference structure: duplicateWithKeys -> cub SortPairs (unsorted -> sorted arrays) -> identifyTileRanges
+        uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
+        uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
+        PROF(3);
+        GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, vals_alt, cap, status), "duplicateWithKeys");
+        PROF(4);
+        GSR_CUDA(launch_ref_sort_pairs(s, cap, ka, vals_alt, kb, point_list, end_bit, bin + bl.temp, bl.temp_bytes), "cub sort");
+        PROF(5);
+        GSR_CUDA(launch_tile_ranges_u64(s, cap, n_dev, kb, G, ranges), "identifyTileRanges");
+      } else if (k64) {
         uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
         uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
         PROF(3);
@@ -351,8 +368,12 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
       GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
     }
     PROF(6);
-    GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
-                                  out_depth, final_T, n_contrib, (flags & GSR_FLAG_PRECISE) != 0), "blend forward");
+    if (ref)
+      GSR_CUDA(launch_ref_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
+                                        out_depth, final_T, n_contrib), "blend forward (reference structure)");
+    else
+      GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
+                                    out_depth, final_T, n_contrib, (flags & GSR_FLAG_PRECISE) != 0), "blend forward");
     PROF(-1);
     return 0;
   };
@@ -447,7 +468,11 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   PROF(8);
   // always launched: the tile ranges, not num_rendered, bound the work (num_rendered may be unknown
   // to the host after an asynchronous forward)
-  GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
+  if (refstruct(flags))
+    GSR_CUDA(launch_ref_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
+                                       dL_dpix, gacc), "blend backward (reference structure)");
+  else
+    GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
                                    dL_dpix, gacc, (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
   PROF(9);
   GSR_CUDA(launch_geom_backward(s, P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp,
@@ -474,12 +499,20 @@ int gsr_backward_blend(void* stream, int P, const float* background, int width, 
   PROF(7);
   GSR_CUDA(cudaMemsetAsync(scratch, 0, (size_t)P * 48, s), "memset accumulator");
   PROF(8);
-  GSR_CUDA(launch_blend_backward(s, width, height, reinterpret_cast<const uint2*>(image_buffer + il.ranges),
-                                 reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list),
-                                 reinterpret_cast<const float4*>(geom_buffer + gl.rec), background,
-                                 reinterpret_cast<const float*>(image_buffer + il.final_T),
-                                 reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib), dL_dpix,
-                                 reinterpret_cast<float*>(scratch), (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
+  if (refstruct(flags))
+    GSR_CUDA(launch_ref_blend_backward(s, width, height, reinterpret_cast<const uint2*>(image_buffer + il.ranges),
+                                       reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list),
+                                       reinterpret_cast<const float4*>(geom_buffer + gl.rec), background,
+                                       reinterpret_cast<const float*>(image_buffer + il.final_T),
+                                       reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib), dL_dpix,
+                                       reinterpret_cast<float*>(scratch)), "blend backward (reference structure)");
+  else
+    GSR_CUDA(launch_blend_backward(s, width, height, reinterpret_cast<const uint2*>(image_buffer + il.ranges),
+                                   reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list),
+                                   reinterpret_cast<const float4*>(geom_buffer + gl.rec), background,
+                                   reinterpret_cast<const float*>(image_buffer + il.final_T),
+                                   reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib), dL_dpix,
+                                   reinterpret_cast<float*>(scratch), (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
   PROF(-1);
   return 0;
 }

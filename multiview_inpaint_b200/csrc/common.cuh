@@ -185,6 +185,17 @@ cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const floa
                                  float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
                                  float* dL_dsh, float* dL_dscale, float* dL_drot, bool accumulate);
 
+// Reference-structure stand-in (refstruct.cu, GSR_FLAG_REFERENCE): cub sort + thread-per-pixel blend
+size_t ref_sort_temp_bytes(int64_t n, int end_bit);
+cudaError_t launch_ref_sort_pairs(cudaStream_t s, int64_t n, const uint64_t* keys_in, const uint32_t* vals_in,
+                                  uint64_t* keys_out, uint32_t* vals_out, int end_bit, char* temp, size_t temp_bytes);
+cudaError_t launch_ref_blend_forward(cudaStream_t s, int W, int H, const uint2* ranges, const uint32_t* point_list,
+                                     const float4* rec, const float* depths, const float* bg, float* out_color,
+                                     float* out_depth, float* final_T, uint32_t* n_contrib);
+cudaError_t launch_ref_blend_backward(cudaStream_t s, int W, int H, const uint2* ranges, const uint32_t* point_list,
+                                      const float4* rec, const float* bg, const float* final_T,
+                                      const uint32_t* n_contrib, const float* dL_dpix, float* gacc);
+
 // One view's inputs to the multi-view per-Gaussian backward (geom_backward_multi.cu)
 struct ViewGrad {
   const int32_t* radii;

@@ -345,6 +345,26 @@ def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: 
     return states
 
 
+class StepThrottle:
+    """Bounds how far the host may run ahead of the GPU when steps never block (GSR_FLAG_ASYNC): at most
+    `max_inflight` steps queued.  Every queued step pins ~1 GB of per-view scratch (geometry, binning and
+    image buffers) until it has run, so an unbounded run-ahead makes the caching allocator fall back to
+    cudaMalloc -- a device synchronisation -- in the middle of the loop.  Waiting on the event of the step
+    before the previous one keeps the GPU fed (a whole step is still queued behind the running one)."""
+
+    def __init__(self, max_inflight: int = 2):
+        self.max_inflight = max(1, max_inflight)
+        self._events: list = []
+
+    def tick(self, device=None):
+        """Call once per step, after queueing it."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._events.append(ev)
+        if len(self._events) > self.max_inflight:
+            self._events.pop(0).synchronize()
+
+
 class AsyncViews:
     """Host-side bookkeeping for fully asynchronous view steps: one pinned (N, status) slot and one
     capacity per view.  Usage per step:  for v: cuda_view_fwd_bwd(..., capacity=a.capacity(v),
@@ -362,7 +382,11 @@ class AsyncViews:
         return self.slots[v]
 
     def capacity(self, v: int) -> int:
-        return self.cap[v]
+        """One capacity for all views (the largest seen, rounded up to 2^20 instances): every view's binning
+        buffer then has the same size, so the caching allocator recycles blocks between views instead of
+        growing a pool per size."""
+        c = max(self.cap)
+        return (c + (1 << 20) - 1) >> 20 << 20 if c > 0 else 0
 
     def learn(self, v: int, n: int):
         self.cap[v] = max(self.cap[v], int(n * self.margin) + 65536)
@@ -374,7 +398,7 @@ class AsyncViews:
             n, status = int(self.slots[v, 0]), int(self.slots[v, 1])
             if status & 0xffffffff:
                 raise RuntimeError("rasterize_gaussians: point filtered by culling but 'prefiltered' was set")
-            if n > self.cap[v] or (status >> 32):
+            if n > self.capacity(v) or (status >> 32):
                 bad.append(v)
             self.learn(v, n)
         return bad

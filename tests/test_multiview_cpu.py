@@ -101,10 +101,10 @@ def test_world2_gloo_sharded_step_equals_single_rank_loop(tmp_path, oracle):
 def test_async_views_bookkeeping():
     a = mv.AsyncViews(3)
     a.learn(0, 1000)
-    assert a.capacity(0) == int(1000 * 1.25) + 65536 and a.capacity(1) == 0
+    # one capacity for every view (largest seen, rounded up to 2^20): buffers are interchangeable between views
+    assert a.capacity(0) == 1 << 20 == a.capacity(1) and mv.AsyncViews(2).capacity(0) == 0
     a.slots[0, 0], a.slots[0, 1] = 900, 0
     a.slots[1, 0], a.slots[1, 1] = 5_000_000, 1 << 32          # overflow bit set by the kernels
-    a.cap[1] = 100
     assert a.check([0, 1]) == [1]
     assert a.capacity(1) >= 5_000_000
     a.slots[2, 1] = 1                                           # prefiltered trap

@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 
 KEY64 = 1     # reference-structure binning: one 64-bit (tile|depth) sort
 PRECISE = 2   # blend in the oracle's exact op order with expf / IEEE division
+REFERENCE = 4 # reference-structure ablation baseline: cub sort, thread-per-pixel blend, 9 atomics per pair
 
 
 def _state(out, sc, cam, flags):
@@ -41,7 +42,7 @@ def _check_forward(oracle, sc, flags, cam=None, bg=None, **kw):
     np.testing.assert_array_equal(radii.cpu().numpy(), f.radii)
     np.testing.assert_array_equal(st["tiles_touched"].view(np.uint32), f.tiles_touched)
     assert n == f.num_rendered
-    if flags & KEY64:
+    if flags & (KEY64 | REFERENCE):
         np.testing.assert_array_equal(st["point_offsets"].view(np.uint32), f.point_offsets)
     else:
         dkeys = np.where(vis, f.depths.view(np.uint32), np.uint32(0xFFFFFFFF))
@@ -97,7 +98,7 @@ def _check_backward(oracle, f, out, d, camd, bgd, sc, flags, seed, **kw):
     return res
 
 
-@pytest.mark.parametrize("flags", [0, KEY64, PRECISE, KEY64 | PRECISE])
+@pytest.mark.parametrize("flags", [0, KEY64, PRECISE, KEY64 | PRECISE, REFERENCE])
 def test_config1_plumbing_every_intermediate(oracle, flags):
     """BASELINE.json configs[0]: 10k Gaussians, 256x256, SH degree 0, fwd+bwd, every intermediate."""
     sc = S.make_config_scene("plumbing")
@@ -106,7 +107,7 @@ def test_config1_plumbing_every_intermediate(oracle, flags):
     _check_backward(oracle, f, out, d, camd, bgd, sc, flags, seed=1)
 
 
-@pytest.mark.parametrize("flags", [0, KEY64, PRECISE])
+@pytest.mark.parametrize("flags", [0, KEY64, PRECISE, REFERENCE])
 @pytest.mark.parametrize("P,W,H,deg,seed,rad", [
     (3000, 96, 80, 3, 11, 6.0),      # deg 3, several tiles
     (500, 64, 64, 1, 12, 20.0),      # big splats: long lists per tile
@@ -130,6 +131,26 @@ def test_dense_opaque_scene_long_lists_and_saturation(oracle):
     lens = f.ranges[:, 1] - f.ranges[:, 0]
     assert lens.max() > 1024 and f.n_contrib.max() < lens.max()
     _check_backward(oracle, f, out, d, camd, bgd, sc, 0, 31)
+
+
+def test_reference_structure_baseline_is_bit_identical_to_precise_forward(oracle):
+    """The ablation baseline (GSR_FLAG_REFERENCE: cub sort, one thread per pixel, no culling) and the
+    product kernels in PRECISE mode are two independent implementations of the same recurrence in the
+    same op order: every forward output must agree bit for bit, the gradients within the atomic-order bar."""
+    sc = S.make_scene(60_000, 200, 120, 2, 37, mu_s=S.default_mu_s(200, 9.0))
+    outp, d, camd, bgd = cuda_forward(sc, flags=PRECISE)
+    outr, *_ = cuda_forward(sc, flags=REFERENCE)
+    assert outp[0] == outr[0]
+    for a, b in ((outp[1], outr[1]), (outp[2], outr[2]), (outp[6], outr[6])):
+        assert torch.equal(a, b)
+    sp, sr = _state(outp, sc, camd, PRECISE), _state(outr, sc, camd, REFERENCE)
+    for k in ("point_list", "ranges", "final_T", "n_contrib"):
+        np.testing.assert_array_equal(sp[k].view(np.uint32), sr[k].view(np.uint32), err_msg=k)
+    wt = S.loss_weights(200, 120, 5)
+    gp = cuda_backward(outp, d, camd, bgd, sc, wt, flags=PRECISE)
+    gr = cuda_backward(outr, d, camd, bgd, sc, wt, flags=REFERENCE)
+    for k in gp:
+        assert rel_err(gr[k].cpu().numpy(), gp[k].cpu().numpy()) < 1e-3, k
 
 
 def test_orbit_camera_rotated_view(oracle):
