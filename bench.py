@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (ViewPipeline depth; 1 = one stream)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "nvls"],
                     help="arena collective: NCCL, the in-switch multimem kernel, or whichever is faster here")
+    ap.add_argument("--ar-chunks", type=int, default=4, help="Gaussian-range chunks of the pipelined per-Gaussian backward + in-switch all-reduce (1 = sequential)")
     ap.add_argument("--per-view-backward", action="store_true", help="K8+K9 per view (accumulate) instead of one batched launch per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")
@@ -201,6 +202,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = dict(S.CONFIGS[args.workload])
@@ -251,6 +254,7 @@ def run_ours(args):
         arena.all_reduce()
 
     pipe = mv.ViewPipeline(dev, depth=args.streams) if args.streams > 1 else None
+    workspaces = [_C.Workspace(dev) for _ in mine]   # per-view scratch + outputs, reused every step (no allocator traffic)
     throttle = mv.StepThrottle(2)   # host at most two steps ahead of the GPU (bounded scratch; see StepThrottle)
     import contextlib
 
@@ -267,8 +271,10 @@ def run_ours(args):
         else:
             mv.cuda_views_fwd_bwd(gauss, [settings(cams_dev[v]) for v in mine], [lambda c, wt=wts_dev[v]: wt for v in mine],
                                   arena, flags=args.flags, capacities=[av.capacity(v) for v in mine],
-                                  async_results=[av.slot(v) for v in mine], pipeline=pipe)
-        arena.all_reduce()
+                                  async_results=[av.slot(v) for v in mine], pipeline=pipe, all_reduce=True, chunks=args.ar_chunks,
+                                  workspaces=workspaces)
+        if args.per_view_backward:
+            arena.all_reduce()
         throttle.tick(dev)
 
     n_slots = max(args.streams, 1)
@@ -306,8 +312,10 @@ def run_ours(args):
                                          capacity=av.capacity(v), async_result=av.slot(v), pipeline=pipe)
         else:
             mv.cuda_views_fwd_bwd(gauss, stages, grads, arena, flags=args.flags, capacities=[av.capacity(v) for v in mine],
-                                  async_results=[av.slot(v) for v in mine], pipeline=pipe)
-        arena.all_reduce()
+                                  async_results=[av.slot(v) for v in mine], pipeline=pipe, all_reduce=True, chunks=args.ar_chunks,
+                                  workspaces=workspaces)
+        if args.per_view_backward:
+            arena.all_reduce()
         out = float(torch.stack(loss_parts).sum().item())                  # D2H: the step's result (syncs)
         assert not av.check(mine), "capacity overflow inside the timed region"
         return out
@@ -420,7 +428,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_geom_backward": not args.per_view_backward, "P": P, "V": V, "N": N,
+        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_geom_backward": not args.per_view_backward, "ar_chunks": args.ar_chunks, "P": P, "V": V, "N": N,
                    "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce", "allreduce": comm,
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

@@ -144,6 +144,14 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
                             float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                             float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
                             uint32_t flags);
+/* The same for Gaussians [g_begin, g_end) only (g_begin a multiple of 4); all pointers are those of the FULL
+ * arrays.  Lets the caller pipeline chunks of the backward with chunks of the gradient all-reduce. */
+int gsr_backward_geom_multi_range(void* stream, int P, int D, int M, const float* means3D, const float* shs,
+                                  const float* scales, float scale_modifier, const float* rotations,
+                                  const gsr_view_grad* views_host, int n_views, float* dL_dopacity,
+                                  float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                  float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
+                                  uint32_t flags, int g_begin, int g_end);
 
 /* In-switch all-reduce (NVLink SHARP / NVLS) of one symmetric buffer that every rank has mapped through the
  * same MULTICAST address `multicast_ptr` (torch.distributed._symmetric_memory: handle.multicast_ptr).
@@ -158,6 +166,25 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
 int gsr_nvls_all_reduce(void* stream, void* multicast_ptr, size_t off_f32, size_t n_f32, size_t off_add_s32,
                         size_t n_add_s32, size_t off_max_s32, size_t n_max_s32, int rank, int world, int blocks,
                         size_t sparse_first_f32, size_t sparse_rows, int sparse_row_f32);
+
+/* The same collective for an arbitrary set of ranges of the symmetric buffer -- used to all-reduce the arena in
+ * Gaussian-range chunks so that the reduction of chunk c overlaps the per-Gaussian backward of chunk c + 1.
+ * All offsets are bytes from the multicast base, 16-byte aligned for float data; dense lengths are multiples of
+ * 4 floats.  `rows` rows of `row_f32` floats starting at rows_off are reduced row-sparsely against the int32
+ * counts starting at rows_count_off (row g is skipped when the SUM over ranks of count g is zero; that count
+ * must lie inside the add_s32 range so that it is itself reduced); row widths other than 12 / 48 floats are
+ * reduced densely. */
+typedef struct {
+  size_t dense_off[6];
+  size_t dense_n_f32[6];
+  int n_dense;
+  size_t rows_off, rows;
+  int row_f32;
+  size_t rows_count_off;
+  size_t add_s32_off, n_add_s32;
+  size_t max_s32_off, n_max_s32;
+} gsr_nvls_plan;
+int gsr_nvls_all_reduce_plan(void* stream, void* multicast_ptr, const gsr_nvls_plan* plan, int rank, int world, int blocks);
 
 /* Densification statistics of one view, fused (the reference does this in torch after backward():
  * gs-simp/scene/gaussian_model.py:482-484 `xyz_gradient_accum[vis] += norm(viewspace.grad[vis, :2])`,

@@ -28,6 +28,7 @@ FLAG_PRECISE = 2
 FLAG_REFERENCE = 4     # reference-structure ablation baseline (cub sort, thread-per-pixel blend, 9 atomics/pair)
 FLAG_ACCUMULATE = 8
 FLAG_ASYNC = 16
+GM_MAX_VIEWS = 4        # views per launch of the batched per-Gaussian backward (csrc/geom_backward_multi.cu)
 NUM_STAGES = 10
 STAGE_NAMES = ("preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward",
                "accum_clear", "blend_backward", "geom_backward")
@@ -75,6 +76,18 @@ _lib.gsr_backward_blend.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _v
 _lib.gsr_backward_geom_multi.restype = _i
 _lib.gsr_backward_geom_multi.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp, C.POINTER(GsrViewGrad), _i,
                                          _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32]
+_lib.gsr_backward_geom_multi_range.restype = _i
+_lib.gsr_backward_geom_multi_range.argtypes = _lib.gsr_backward_geom_multi.argtypes + [_i, _i]
+
+
+class GsrNvlsPlan(C.Structure):
+    _fields_ = [("dense_off", _sz * 6), ("dense_n_f32", _sz * 6), ("n_dense", _i), ("rows_off", _sz), ("rows", _sz),
+                ("row_f32", _i), ("rows_count_off", _sz), ("add_s32_off", _sz), ("n_add_s32", _sz),
+                ("max_s32_off", _sz), ("n_max_s32", _sz)]
+
+
+_lib.gsr_nvls_all_reduce_plan.restype = _i
+_lib.gsr_nvls_all_reduce_plan.argtypes = [_vp, _vp, C.POINTER(GsrNvlsPlan), _i, _i, _i]
 _lib.gsr_nvls_all_reduce.restype = _i
 _lib.gsr_nvls_all_reduce.argtypes = [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _i, _i, _i, _sz, _sz, _i]
 _lib.gsr_accumulate_view_stats.restype = _i
@@ -98,7 +111,7 @@ _lib.gsr_profile_collect.restype = _i
 _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
-                    "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_nvls_all_reduce",
+                    "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches",
@@ -136,6 +149,37 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class Workspace:
+    """Caller-owned scratch of ONE view slot: the geometry / binning / image buffers, the blend-backward
+    accumulator and the colour / depth / radii outputs live in tensors that are kept between calls and only
+    ever grow, so a steady-state multi-view loop never reaches the caching allocator (with several steps in
+    flight on several streams its cross-stream reuse rules otherwise end in cudaMalloc -- a device
+    synchronisation -- inside the loop).  Contract: a workspace may be handed to the next call only when the
+    work that used it last is stream-ordered before that call (ViewPipeline guarantees this for one workspace
+    per view of a step); tensors returned from a call with a workspace are views into it and are overwritten
+    by the next call."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.bufs: dict = {}
+
+    def bytes(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self.bufs.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.bufs[name] = t
+        return t[:nbytes]
+
+    def tensor(self, name: str, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        return self.bytes(name, n * torch.empty(0, dtype=dtype).element_size()).view(dtype).view(*shape)
+
+    def reserved_bytes(self) -> int:
+        return sum(t.numel() for t in self.bufs.values())
+
+
 class _Grower:
     """The reference's resizeFunctional(): a callback that (re)allocates a uint8 tensor.
 
@@ -144,20 +188,24 @@ class _Grower:
     force the caching allocator into a fresh cudaMalloc.  `take()` breaks the cycle as soon as the
     native call has returned, so the buffers are freed by reference counting."""
 
-    def __init__(self, device):
+    def __init__(self, device, workspace=None, name=None):
         self.device = device
+        self.workspace, self.name = workspace, name
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
         self.cb = _ALLOC_FN(self._alloc)
 
     def _alloc(self, _user, nbytes):
         try:
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            if self.workspace is not None:
+                self.tensor = self.workspace.bytes(self.name, int(nbytes))
+            else:
+                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
             return self.tensor.data_ptr()
         except Exception:  # surfaces as GSR_E_ALLOC
             return 0
 
     def take(self) -> torch.Tensor:
-        t, self.tensor, self.cb = self.tensor, None, None
+        t, self.tensor, self.cb, self.workspace = self.tensor, None, None, None
         return t
 
 
@@ -180,8 +228,9 @@ def _note_rendered(device, n: int):
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
                         image_width, sh, degree, campos, prefiltered, debug=False, flags=None,
-                        capacity=None, async_result=None):
-    """`capacity` / `async_result` (extensions): with `async_result` (a pinned int64[2] tensor) the
+                        capacity=None, async_result=None, workspace=None):
+    """`workspace` (extension): a Workspace that provides every buffer and output of this call (see there).
+    `capacity` / `async_result` (extensions): with `async_result` (a pinned int64[2] tensor) the
     call never blocks the host -- GSR_FLAG_ASYNC -- and returns num_rendered = -1; the caller reads
     async_result after a stream sync ([0] = N must be <= capacity, [1] must be 0)."""
     if means3D.ndim != 2 or means3D.shape[1] != 3:
@@ -207,10 +256,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
         scales, rotations = _f32c(scales, "scales"), _f32c(rotations, "rotations")
         cov3D_precomp, sh = _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(sh, "shs")
         viewmatrix, projmatrix, campos = _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix"), _f32c(campos, "campos")
-        out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
-        out_depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
-        radii = torch.empty(P, dtype=torch.int32, device=dev)
-        geom, binning, img = _Grower(dev), _Grower(dev), _Grower(dev)
+        if workspace is not None:
+            out_color = workspace.tensor("color", (3, H, W), torch.float32)
+            out_depth = workspace.tensor("depth", (1, H, W), torch.float32)
+            radii = workspace.tensor("radii", (P,), torch.int32)
+        else:
+            out_color = torch.empty(3, H, W, dtype=torch.float32, device=dev)
+            out_depth = torch.empty(1, H, W, dtype=torch.float32, device=dev)
+            radii = torch.empty(P, dtype=torch.int32, device=dev)
+        geom, binning, img = _Grower(dev, workspace, "geom"), _Grower(dev, workspace, "binning"), _Grower(dev, workspace, "image")
         n = _i64(0)
         if async_result is not None:
             assert async_result.is_pinned() and async_result.dtype == torch.int64 and async_result.numel() >= 2
@@ -295,7 +349,7 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     return present
 
 
-def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBuffer, P, flags=None):
+def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBuffer, P, flags=None, workspace=None):
     """K7 only (gsr_backward_blend): returns the packed per-Gaussian accumulator (uint8 scratch tensor)
     that backward_geom_multi() consumes."""
     flags = DEFAULT_FLAGS if flags is None else int(flags)
@@ -303,7 +357,7 @@ def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBu
     H, W = dL_dout_color.shape[1], dL_dout_color.shape[2]
     with torch.cuda.device(dev):
         nscratch = int(_lib.gsr_backward_scratch_bytes(P))
-        scratch = torch.empty(nscratch, dtype=torch.uint8, device=dev)
+        scratch = workspace.bytes("scratch", nscratch) if workspace is not None else torch.empty(nscratch, dtype=torch.uint8, device=dev)
         if P != 0:
             background, dL_dout_color = _f32c(background, "background"), _f32c(dL_dout_color, "dL_dout_color")
             _check(_lib.gsr_backward_blend(_stream(dev), P, _ptr(background), W, H, _ptr(geomBuffer), _ptr(binningBuffer),
@@ -317,14 +371,16 @@ def backward_geom_multi_supported(M: int) -> bool:
 
 
 def backward_geom_multi(means3D, sh, scales, rotations, scale_modifier, degree, views, out, stats=None, flags=0,
-                        want_means2D=False):
+                        want_means2D=False, g_range=None):
     """Batched K8+K9 over the views of one set of Gaussians (gsr_backward_geom_multi).
     views: list of dicts with radii, geom, scratch, viewmatrix, projmatrix, campos, tanfovx, tanfovy, width, height.
     out:   dict of preallocated dL_dmeans3D (P,3), dL_dsh (P,M,3), dL_dopacity (P,1), dL_dscales (P,3),
            dL_drotations (P,4) -- written (or added to with FLAG_ACCUMULATE).
     stats: optional (grad_norm_accum f32[P], visible_count i32[P], max_radii i32[P]).
+    g_range: optional (g_begin, g_end), g_begin % 4 == 0: only those Gaussians (gsr_backward_geom_multi_range).
     Returns the list of per-view dL_dmeans2D (P,3) tensors if want_means2D else None."""
     P, M = means3D.shape[0], sh.shape[1]
+    g0, g1 = (0, P) if g_range is None else (int(g_range[0]), int(g_range[1]))
     dev = means3D.device
     keep = []   # contiguous copies must outlive the launch
 
@@ -353,10 +409,10 @@ def backward_geom_multi(means3D, sh, scales, rotations, scale_modifier, degree, 
             assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), name
         st = stats or (None, None, None)
         if P != 0 and len(views) != 0:
-            _check(_lib.gsr_backward_geom_multi(
+            _check(_lib.gsr_backward_geom_multi_range(
                 _stream(dev), P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(scales), float(scale_modifier), _ptr(rotations),
                 arr, len(views), _ptr(out["dL_dopacity"]), _ptr(out["dL_dmeans3D"]), _ptr(out["dL_dsh"]), _ptr(out["dL_dscales"]),
-                _ptr(out["dL_drotations"]), _ptr(st[0]), _ptr(st[1]), _ptr(st[2]), int(flags)), "backward_geom_multi")
+                _ptr(out["dL_drotations"]), _ptr(st[0]), _ptr(st[1]), _ptr(st[2]), int(flags), g0, g1), "backward_geom_multi")
     return m2d if want_means2D else None
 
 
@@ -368,6 +424,22 @@ def nvls_all_reduce(multicast_ptr: int, device, off_f32: int, n_f32: int, off_ad
         _check(_lib.gsr_nvls_all_reduce(_stream(device), multicast_ptr, off_f32, n_f32, off_add_s32, n_add_s32,
                                         off_max_s32, n_max_s32, rank, world, blocks, sparse_first_f32, sparse_rows,
                                         sparse_row_f32), "nvls_all_reduce")
+
+
+def nvls_all_reduce_plan(multicast_ptr: int, device, rank: int, world: int, dense=(), rows=None, add_s32=(0, 0),
+                         max_s32=(0, 0), blocks: int = 0):
+    """gsr_nvls_all_reduce_plan on the current stream.  dense: [(byte offset, n floats)], rows: (byte offset, n rows,
+    floats per row, byte offset of row 0's int32 count) or None, add_s32 / max_s32: (byte offset, n)."""
+    pl = GsrNvlsPlan()
+    pl.n_dense = len(dense)
+    for k, (off, n) in enumerate(dense):
+        pl.dense_off[k], pl.dense_n_f32[k] = int(off), int(n)
+    if rows is not None:
+        pl.rows_off, pl.rows, pl.row_f32, pl.rows_count_off = int(rows[0]), int(rows[1]), int(rows[2]), int(rows[3])
+    pl.add_s32_off, pl.n_add_s32 = int(add_s32[0]), int(add_s32[1])
+    pl.max_s32_off, pl.n_max_s32 = int(max_s32[0]), int(max_s32[1])
+    with torch.cuda.device(device):
+        _check(_lib.gsr_nvls_all_reduce_plan(_stream(device), multicast_ptr, C.byref(pl), rank, world, blocks), "nvls_all_reduce_plan")
 
 
 def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_count=None, max_radii=None):

@@ -523,9 +523,22 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
                             float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
                             float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
                             uint32_t flags) {
+  return gsr_backward_geom_multi_range(stream, P, D, M, means3D, shs, scales, scale_modifier, rotations, views_host,
+                                       n_views, dL_dopacity, dL_dmean3D, dL_dsh, dL_dscale, dL_drot, grad_norm_accum,
+                                       visible_count, max_radii, flags, 0, P);
+}
+
+int gsr_backward_geom_multi_range(void* stream, int P, int D, int M, const float* means3D, const float* shs,
+                                  const float* scales, float scale_modifier, const float* rotations,
+                                  const gsr_view_grad* views_host, int n_views, float* dL_dopacity,
+                                  float* dL_dmean3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                  float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii,
+                                  uint32_t flags, int g_begin, int g_end) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (P < 0 || n_views < 0 || D < 0 || D > 3) return fail(GSR_E_INVALID, "gsr_backward_geom_multi: bad P/n_views/degree");
-  if (P == 0 || n_views == 0) return 0;
+  if (g_begin < 0 || g_end > P || g_begin > g_end || (g_begin & 3))
+    return fail(GSR_E_INVALID, "gsr_backward_geom_multi_range: need 0 <= g_begin <= g_end <= P and g_begin % 4 == 0");
+  if (P == 0 || n_views == 0 || g_begin == g_end) return 0;
   if (!geom_backward_multi_supported(M) || (D + 1) * (D + 1) > M)
     return fail(GSR_E_INVALID, "gsr_backward_geom_multi: needs M in {1, 4, 16} and (D+1)^2 <= M");
   if (!means3D || !shs || !scales || !rotations || !views_host || !dL_dopacity || !dL_dmean3D || !dL_dsh ||
@@ -536,20 +549,21 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
     return fail(GSR_E_INVALID, "gsr_backward_geom_multi: dL_drot / dL_dsh / rotations / shs must be 16-byte aligned");
   std::vector<ViewGrad> vs((size_t)n_views);
   const GeomLayout gl = geom_layout(P, flags);
+  const size_t g0 = (size_t)g_begin;
   for (int v = 0; v < n_views; v++) {
     const gsr_view_grad& in = views_host[v];
     if (!in.radii || !in.geom_buffer || !in.scratch || !in.viewmatrix || !in.projmatrix || !in.cam_pos ||
         in.width <= 0 || in.height <= 0 || (reinterpret_cast<uintptr_t>(in.scratch) & 15))
       return fail(GSR_E_INVALID, "gsr_backward_geom_multi: bad view descriptor");
     ViewGrad& o = vs[(size_t)v];
-    o.radii = in.radii;
-    o.clamped = reinterpret_cast<const uint8_t*>(in.geom_buffer + gl.clamped);
-    o.rec = reinterpret_cast<const float4*>(in.geom_buffer + gl.rec);
-    o.gacc = reinterpret_cast<const float*>(in.scratch);
+    o.radii = in.radii + g0;
+    o.clamped = reinterpret_cast<const uint8_t*>(in.geom_buffer + gl.clamped) + g0;
+    o.rec = reinterpret_cast<const float4*>(in.geom_buffer + gl.rec) + 3 * g0;
+    o.gacc = reinterpret_cast<const float*>(in.scratch) + 12 * g0;
     o.view = in.viewmatrix;
     o.proj = in.projmatrix;
     o.campos = in.cam_pos;
-    o.dL_dmean2D = in.dL_dmean2D;
+    o.dL_dmean2D = in.dL_dmean2D ? in.dL_dmean2D + 3 * g0 : nullptr;
     o.focal_x = in.width / (2.0f * in.tan_fovx);
     o.focal_y = in.height / (2.0f * in.tan_fovy);
     o.tan_fovx = in.tan_fovx;
@@ -558,9 +572,12 @@ int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* mean
     o.H = in.height;
   }
   PROF(9);
-  GSR_CUDA(launch_geom_backward_multi(s, P, D, M, means3D, shs, scales, rotations, scale_modifier, vs.data(), n_views,
-                                      dL_dopacity, dL_dmean3D, dL_dsh, dL_dscale, dL_drot, grad_norm_accum,
-                                      visible_count, max_radii, (flags & GSR_FLAG_ACCUMULATE) != 0),
+  GSR_CUDA(launch_geom_backward_multi(s, g_end - g_begin, D, M, means3D + 3 * g0, shs + (size_t)M * 3 * g0, scales + 3 * g0,
+                                      rotations + 4 * g0, scale_modifier, vs.data(), n_views, dL_dopacity + g0,
+                                      dL_dmean3D + 3 * g0, dL_dsh + (size_t)M * 3 * g0, dL_dscale + 3 * g0, dL_drot + 4 * g0,
+                                      grad_norm_accum ? grad_norm_accum + g0 : nullptr,
+                                      visible_count ? visible_count + g0 : nullptr, max_radii ? max_radii + g0 : nullptr,
+                                      (flags & GSR_FLAG_ACCUMULATE) != 0),
            "multi-view per-Gaussian backward");
   PROF(-1);
   return 0;
@@ -576,6 +593,19 @@ int gsr_nvls_all_reduce(void* stream, void* multicast_ptr, size_t off_f32, size_
                                  n_f32, off_add_s32, n_add_s32, off_max_s32, n_max_s32, rank, world, blocks,
                                  sparse_first_f32, sparse_rows, sparse_row_f32),
            "nvls all-reduce");
+  return 0;
+}
+
+int gsr_nvls_all_reduce_plan(void* stream, void* multicast_ptr, const gsr_nvls_plan* plan, int rank, int world, int blocks) {
+  if (!multicast_ptr || !plan || world < 1 || rank < 0 || rank >= world || (reinterpret_cast<uintptr_t>(multicast_ptr) & 15) ||
+      plan->n_dense < 0 || plan->n_dense > 6 || (plan->rows_off & 15) || (plan->rows_count_off & 3) ||
+      (plan->add_s32_off & 3) || (plan->max_s32_off & 3) || plan->row_f32 < 0)
+    return fail(GSR_E_INVALID, "gsr_nvls_all_reduce_plan: bad argument (alignment / rank / multicast pointer)");
+  for (int d = 0; d < plan->n_dense; d++)
+    if ((plan->dense_off[d] & 15) || (plan->dense_n_f32[d] & 3))
+      return fail(GSR_E_INVALID, "gsr_nvls_all_reduce_plan: dense segments must be 16-byte aligned multiples of 4 floats");
+  GSR_CUDA(launch_nvls_allreduce_plan(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<char*>(multicast_ptr), *plan,
+                                      rank, world, blocks), "nvls all-reduce (plan)");
   return 0;
 }
 

@@ -56,30 +56,36 @@ __device__ __forceinline__ void reduce_dense_f32(float4* base, size_t lo4, size_
   }
 }
 
-// Float4 indices [row_lo4, row_hi4) of the float segment form a (rows x row_f4) matrix -- the (P, M, 3) SH
-// gradient, 81 % of the arena at M = 16 -- whose row g is all-zero on every rank exactly when the Gaussian
-// was visible in no view of any rank, i.e. when the SUM over ranks of element g of the add_s32 segment (the
-// visibility count) is zero.  Such rows are skipped.  A warp takes a group of 96 / row_f4 rows (96 float4,
-// three per lane, lane-contiguous so every access is a coalesced 512-byte run); its first lanes fetch the
-// group's counts with one 4-byte in-switch reduction each and broadcast them by shuffle.  (The count segment
-// is concurrently being replaced by its own sum, which can only turn a positive value into a larger one, so
-// the `!= 0` test is race free.)
+// Plan of one launch (by value): up to six dense float4 ranges, one row-sparse matrix, two int ranges; all
+// positions are relative to the multicast base.
+struct NvlsPlan {
+  unsigned long long dense_lo4[6], dense_hi4[6];
+  int n_dense;
+  unsigned long long row_lo4, rows;   // float4 index of row 0, number of rows
+  unsigned row_f4;                    // float4 per row (0: no sparse matrix)
+  unsigned long long cnt_off;         // byte offset of the int32 count that belongs to row 0
+  unsigned long long add_off, n_add, max_off, n_max;
+};
+
+// The sparse matrix is a (rows x row_f4) block of float4 -- the (P, M, 3) SH gradient, 81 % of the arena at
+// M = 16 -- whose row g is all-zero on every rank exactly when the Gaussian was visible in no view of any
+// rank, i.e. when the SUM over ranks of its visibility count is zero.  Such rows are skipped.  A warp takes a
+// group of 96 / row_f4 rows (96 float4, three per lane, lane-contiguous so every access is a coalesced
+// 512-byte run); its first lanes fetch the group's counts with one 4-byte in-switch reduction each and
+// broadcast them by shuffle.  (The count segment is concurrently being replaced by its own sum, which can
+// only turn a positive value into a larger one, so the `!= 0` test is race free.)
 __global__ void __launch_bounds__(512)
-nvls_allreduce_kernel(char* __restrict__ mc, size_t off_f32, size_t n_f32x4, size_t off_add_s32, size_t n_add_s32,
-                      size_t off_max_s32, size_t n_max_s32, int rank, int world, size_t row_lo4, size_t row_hi4,
-                      unsigned row_f4) {
+nvls_allreduce_kernel(char* __restrict__ mc, const NvlsPlan pl, int rank, int world) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-  float4* base = reinterpret_cast<float4*>(mc + off_f32);
-  if (row_f4 == 0) {
-    reduce_dense_f32(base, 0, n_f32x4, rank, world, tid, nthreads);
-  } else {
-    reduce_dense_f32(base, 0, row_lo4, rank, world, tid, nthreads);
-    reduce_dense_f32(base, row_hi4, n_f32x4, rank, world, tid, nthreads);
-    const int* cnt = reinterpret_cast<const int*>(mc + off_add_s32);
+  float4* base = reinterpret_cast<float4*>(mc);
+  for (int d = 0; d < pl.n_dense; d++) reduce_dense_f32(base, pl.dense_lo4[d], pl.dense_hi4[d], rank, world, tid, nthreads);
+  if (pl.row_f4 != 0) {
+    const unsigned row_f4 = pl.row_f4;
+    const int* cnt = reinterpret_cast<const int*>(mc + pl.cnt_off);
     const unsigned lane = threadIdx.x & 31;
     const unsigned G = 96 / row_f4;                               // rows per group (8 at M = 16, 32 at M = 4)
-    const size_t rows = (row_hi4 - row_lo4) / row_f4;
+    const size_t rows = pl.rows;
     const size_t groups = (rows + G - 1) / G;
     const size_t per = (groups + world - 1) / world;
     const size_t g_lo = min(groups, per * rank), g_hi = min(groups, g_lo + per);
@@ -88,7 +94,7 @@ nvls_allreduce_kernel(char* __restrict__ mc, size_t off_f32, size_t n_f32x4, siz
       const size_t row0 = g * G;
       int c = 0;
       if (lane < G && row0 + lane < rows) c = mm_ld_reduce_add_s32(cnt + row0 + lane);
-      float4* p = base + row_lo4 + row0 * row_f4;
+      float4* p = base + pl.row_lo4 + row0 * row_f4;
       float4 v[3];
       bool live[3];
 #pragma unroll
@@ -107,35 +113,67 @@ nvls_allreduce_kernel(char* __restrict__ mc, size_t off_f32, size_t n_f32x4, siz
     }
   }
   {
-    const size_t per = (n_add_s32 + world - 1) / world;
-    const size_t lo = min(n_add_s32, per * rank), hi = min(n_add_s32, lo + per);
-    int* base = reinterpret_cast<int*>(mc + off_add_s32);
-    for (size_t i = lo + tid; i < hi; i += nthreads) mm_st_s32(base + i, mm_ld_reduce_add_s32(base + i));
+    const size_t per = (pl.n_add + world - 1) / world;
+    const size_t lo = min((size_t)pl.n_add, per * rank), hi = min((size_t)pl.n_add, lo + per);
+    int* b = reinterpret_cast<int*>(mc + pl.add_off);
+    for (size_t i = lo + tid; i < hi; i += nthreads) mm_st_s32(b + i, mm_ld_reduce_add_s32(b + i));
   }
   {
-    const size_t per = (n_max_s32 + world - 1) / world;
-    const size_t lo = min(n_max_s32, per * rank), hi = min(n_max_s32, lo + per);
-    int* base = reinterpret_cast<int*>(mc + off_max_s32);
-    for (size_t i = lo + tid; i < hi; i += nthreads) mm_st_s32(base + i, mm_ld_reduce_max_s32(base + i));
+    const size_t per = (pl.n_max + world - 1) / world;
+    const size_t lo = min((size_t)pl.n_max, per * rank), hi = min((size_t)pl.n_max, lo + per);
+    int* b = reinterpret_cast<int*>(mc + pl.max_off);
+    for (size_t i = lo + tid; i < hi; i += nthreads) mm_st_s32(b + i, mm_ld_reduce_max_s32(b + i));
   }
+}
+
+cudaError_t launch_nvls_allreduce_plan(cudaStream_t s, char* mc, const gsr_nvls_plan& in, int rank, int world, int blocks) {
+  if (blocks <= 0) blocks = 148 * 2;
+  NvlsPlan pl{};
+  for (int d = 0; d < in.n_dense && d < 6; d++) {
+    pl.dense_lo4[pl.n_dense] = in.dense_off[d] / 16;
+    pl.dense_hi4[pl.n_dense] = in.dense_off[d] / 16 + in.dense_n_f32[d] / 4;
+    pl.n_dense++;
+  }
+  if (in.rows > 0 && (in.row_f32 == 12 || in.row_f32 == 48)) {
+    pl.row_f4 = (unsigned)in.row_f32 / 4;
+    pl.row_lo4 = in.rows_off / 16;
+    pl.rows = in.rows;
+    pl.cnt_off = in.rows_count_off;
+  } else if (in.rows > 0) {   // row width the sparse walk does not cover: reduce the matrix densely
+    if (pl.n_dense >= 6) return cudaErrorInvalidValue;
+    pl.dense_lo4[pl.n_dense] = in.rows_off / 16;
+    pl.dense_hi4[pl.n_dense] = in.rows_off / 16 + (in.rows * (size_t)in.row_f32 + 3) / 4;
+    pl.n_dense++;
+  }
+  pl.add_off = in.add_s32_off; pl.n_add = in.n_add_s32;
+  pl.max_off = in.max_s32_off; pl.n_max = in.n_max_s32;
+  nvls_allreduce_kernel<<<blocks, 512, 0, s>>>(mc, pl, rank, world);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_nvls_allreduce(cudaStream_t s, char* mc, size_t off_f32, size_t n_f32, size_t off_add_s32,
                                   size_t n_add_s32, size_t off_max_s32, size_t n_max_s32, int rank, int world,
                                   int blocks, size_t sparse_first_f32, size_t sparse_rows, int sparse_row_f32) {
-  if (blocks <= 0) blocks = 148 * 2;
-  size_t row_lo4 = 0, row_hi4 = 0;
-  unsigned row_f4 = 0;
+  gsr_nvls_plan in{};
   if (sparse_rows > 0 && (sparse_row_f32 == 12 || sparse_row_f32 == 48) && (sparse_first_f32 & 3) == 0 &&
       sparse_rows <= n_add_s32) {
-    row_f4 = (unsigned)sparse_row_f32 / 4;
-    row_lo4 = sparse_first_f32 / 4;
-    row_hi4 = row_lo4 + sparse_rows * row_f4;
+    const size_t mat = sparse_rows * (size_t)sparse_row_f32;
+    in.n_dense = 2;
+    in.dense_off[0] = off_f32;                                  in.dense_n_f32[0] = sparse_first_f32;
+    in.dense_off[1] = off_f32 + 4 * (sparse_first_f32 + mat);   in.dense_n_f32[1] = n_f32 - sparse_first_f32 - mat;
+    in.rows_off = off_f32 + 4 * sparse_first_f32;
+    in.rows = sparse_rows;
+    in.row_f32 = sparse_row_f32;
+    in.rows_count_off = off_add_s32;
+  } else {
+    in.n_dense = 1;
+    in.dense_off[0] = off_f32;
+    in.dense_n_f32[0] = n_f32;
   }
-  nvls_allreduce_kernel<<<blocks, 512, 0, s>>>(mc, off_f32, n_f32 / 4, off_add_s32, n_add_s32, off_max_s32, n_max_s32,
-                                               rank, world, row_lo4, row_hi4, row_f4);
-  count_launch();
-  return cudaGetLastError();
+  in.add_s32_off = off_add_s32; in.n_add_s32 = n_add_s32;
+  in.max_s32_off = off_max_s32; in.n_max_s32 = n_max_s32;
+  return launch_nvls_allreduce_plan(s, mc, in, rank, world, blocks);
 }
 
 }  // namespace gsr

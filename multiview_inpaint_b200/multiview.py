@@ -68,6 +68,10 @@ class GradArena:
         self._sh_first = offs[1]                      # first float of the (P, M, 3) SH gradient inside it
         self.sparse = True                            # skip SH rows of Gaussians no rank saw (visible_count == 0)
         self._off_cnt, self._off_max = 4 * (n_flat + Pp), 4 * (n_flat + 2 * Pp)   # byte offsets of the int segments
+        self._offs = {name: o for (name, _), o in zip(sizes, offs)}          # first float of each slice
+        self._row_w = {name: _numel(shp) // max(P, 1) for name, shp in sizes}  # floats per Gaussian
+        self._n_flat, self._Pp = n_flat, Pp
+        self._comm_stream = None
         self.flat = storage[:n_flat]
         self.views = {name: self.flat[o:o + _numel(shp)].view(*shp) for (name, shp), o in zip(sizes, offs)}
         # densification statistics (different reductions: SUM / SUM / MAX)
@@ -140,6 +144,31 @@ class GradArena:
         dist.all_reduce(self.storage[:self._n_f32], op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.visible_count, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
+
+    def all_reduce_range(self, g0: int, g1: int):
+        """In-switch all-reduce of the arena rows (and statistics) of Gaussians [g0, g1) only, on the current
+        stream; g0 must be a multiple of 4.  NVLS only (see cuda_views_geom_backward_allreduce)."""
+        assert self.uses_nvls and g0 % 4 == 0 and 0 <= g0 <= g1 <= self.P
+        from . import _C
+        h = self._handle
+        r4 = lambda n: (n + 3) // 4 * 4     # slices are padded to 4 floats: rounding a tail up stays inside the slice
+        dense, rows = [], None
+        for name in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"):
+            w, first = self._row_w[name], self._offs[name]
+            if name == "dL_dsh" and self.sparse and w in (12, 48):
+                rows = (4 * (first + g0 * w), g1 - g0, w, self._off_cnt + 4 * g0)
+            else:
+                dense.append((4 * (first + g0 * w), r4((g1 - g0) * w)))
+        dense.append((4 * (self._n_flat + g0), r4(g1 - g0)))                      # grad_norm_accum
+        h.barrier()
+        _C.nvls_all_reduce_plan(self._mc, self.storage.device, h.rank, h.world_size, dense=dense, rows=rows,
+                                add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0))
+        h.barrier()
+
+    def comm_stream(self):
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.storage.device)
+        return self._comm_stream
 
     @property
     def bytes(self) -> int:
@@ -275,7 +304,7 @@ class ViewState:
 
 def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor], flags: int = 0,
                         capacity: int | None = None, async_result: torch.Tensor | None = None,
-                        pipeline: ViewPipeline | None = None) -> ViewState:
+                        pipeline: ViewPipeline | None = None, workspace=None) -> ViewState:
     """Forward (K1..K6), loss gradient, blend backward (K7) of one view; the per-Gaussian chain rule is
     left to cuda_views_geom_backward(), which runs it ONCE for all views of the step.  With `pipeline`
     the view runs on the pipeline's next stream; views need no mutual ordering here."""
@@ -288,9 +317,10 @@ def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch
             rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
             rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
             rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags,
-            capacity=capacity, async_result=async_result)
+            capacity=capacity, async_result=async_result, workspace=workspace)
         dL = dL_dcolor_fn(color)
-        scratch = _C.backward_blend(rs.bg, dL, geom, binning, img, gaussians["means3D"].shape[0], flags=flags)
+        scratch = _C.backward_blend(rs.bg, dL, geom, binning, img, gaussians["means3D"].shape[0], flags=flags,
+                                    workspace=workspace)
     return ViewState(color, depth, radii, n, geom, scratch, rs)
 
 
@@ -315,12 +345,53 @@ def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena
                                   flags=flags | (_C.FLAG_ACCUMULATE if accumulate else 0), want_means2D=want_means2D)
 
 
+def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewState], arena: GradArena, flags: int = 0,
+                                       chunks: int = 4):
+    """Batched K8+K9 + gradient all-reduce of a multi-rank step, pipelined over Gaussian-range chunks: while the
+    switch reduces the arena rows of chunk c (comm stream: barrier, gsr_nvls_all_reduce_plan, barrier), the
+    per-Gaussian backward of chunk c + 1 runs on the caller's stream.  The backward is HBM-bound, the reduction
+    NVLink-bound, so the backward disappears behind the collective.  Without a multicast mapping (or with NCCL
+    selected) it is the plain sequence: backward, then arena.all_reduce()."""
+    from . import _C
+    P = arena.P
+    if not (arena.uses_nvls and dist.is_initialized() and dist.get_world_size(arena.group) > 1) or chunks <= 1 \
+            or P < 4096:
+        cuda_views_geom_backward(gaussians, states, arena, flags=flags)
+        arena.all_reduce()
+        return
+    views = [dict(radii=s.radii, geom=s.geom, scratch=s.scratch, viewmatrix=s.settings.viewmatrix,
+                  projmatrix=s.settings.projmatrix, campos=s.settings.campos, tanfovx=s.settings.tanfovx,
+                  tanfovy=s.settings.tanfovy, width=s.settings.image_width, height=s.settings.image_height) for s in states]
+    rs = states[0].settings
+    dev = gaussians["means3D"].device
+    main, comm = torch.cuda.current_stream(dev), arena.comm_stream()
+    for st in states:
+        for t in (st.radii, st.geom, st.scratch):
+            t.record_stream(main)
+    step = ((P + chunks - 1) // chunks + 31) // 32 * 32
+    for g0 in range(0, P, step):
+        g1 = min(P, g0 + step)
+        _C.backward_geom_multi(gaussians["means3D"], gaussians["shs"], gaussians["scales"], gaussians["rotations"],
+                               rs.scale_modifier, rs.sh_degree, views, arena.views,
+                               stats=(arena.grad_norm_accum, arena.visible_count, arena.max_radii), flags=flags, g_range=(g0, g1))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            arena.all_reduce_range(g0, g1)
+    main.wait_stream(comm)
+
+
 def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: Sequence[Callable], arena: GradArena,
                        flags: int = 0, capacities: Sequence[int] | None = None, async_results: Sequence | None = None,
-                       pipeline: ViewPipeline | None = None, accumulate: bool = False) -> list[ViewState]:
+                       pipeline: ViewPipeline | None = None, accumulate: bool = False, all_reduce: bool = False,
+                       chunks: int = 4, workspaces: Sequence | None = None) -> list[ViewState]:
     """A rank's share of a multi-view step: every view's forward + blend backward (two views in flight
     with `pipeline`), then ONE batched per-Gaussian backward that writes the arena.  Falls back to the
-    per-view accumulate path when the batched kernel does not cover the configuration (M not in 1/4/16)."""
+    per-view accumulate path when the batched kernel does not cover the configuration (M not in 1/4/16).
+    With `all_reduce` the arena is also summed over ranks, pipelined with the per-Gaussian backward
+    (cuda_views_geom_backward_allreduce).  `workspaces`: one _C.Workspace per view (kept by the caller across
+    steps) -- the steady-state loop then never touches the caching allocator."""
     import contextlib
     from . import _C
     M = gaussians["shs"].shape[1]
@@ -334,14 +405,22 @@ def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: 
                                       capacity=capacities[k] if capacities else None,
                                       async_result=async_results[k] if async_results else None, pipeline=pipeline)
                 out.append(ViewState(r.color, r.depth, r.radii, r.num_rendered, None, None, rs))
+        if all_reduce:
+            arena.all_reduce()
         return out
     states = []
     with (pipeline.step() if pipeline else contextlib.nullcontext()):
         for k, rs in enumerate(settings_list):
             states.append(cuda_view_fwd_blend(gaussians, rs, dL_dcolor_fns[k], flags=flags,
                                               capacity=capacities[k] if capacities else None,
-                                              async_result=async_results[k] if async_results else None, pipeline=pipeline))
-    cuda_views_geom_backward(gaussians, states, arena, accumulate=accumulate, flags=flags)
+                                              async_result=async_results[k] if async_results else None, pipeline=pipeline,
+                                              workspace=workspaces[k] if workspaces else None))
+    if all_reduce and not accumulate:
+        cuda_views_geom_backward_allreduce(gaussians, states, arena, flags=flags, chunks=chunks)
+    else:
+        cuda_views_geom_backward(gaussians, states, arena, accumulate=accumulate, flags=flags)
+        if all_reduce:
+            arena.all_reduce()
     return states
 
 

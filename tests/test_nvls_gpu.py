@@ -36,7 +36,23 @@ def _worker(rank, world, port, out_dir):
         a.all_reduce()
         b.all_reduce()
         torch.cuda.synchronize()
-        res[M] = dict(nvls=a.uses_nvls, err=float((a.flat - b.flat).abs().max()), scale=float(b.flat.abs().max()),
+        # the same reduction in Gaussian-range chunks (gsr_nvls_all_reduce_plan), as the pipelined backward issues it
+        c = mv.GradArena(P, M, dev, symmetric=True)
+        g.manual_seed(5 + rank)
+        c.flat.copy_(torch.randn(c.flat.shape, device=dev, generator=g))
+        c.grad_norm_accum.copy_(torch.rand(P, device=dev, generator=g))
+        c.visible_count.copy_(torch.randint(0, 3, (P,), device=dev, generator=g, dtype=torch.int32))
+        c.max_radii.copy_(torch.randint(0, 900, (P,), device=dev, generator=g, dtype=torch.int32))
+        c.views["dL_dsh"][c.visible_count == 0] = 0
+        chunk_ok = True
+        if c.uses_nvls:
+            for g0 in range(0, P, 23456):
+                c.all_reduce_range(g0, min(P, g0 + 23456))
+            torch.cuda.synchronize()
+            chunk_ok = bool((c.flat - b.flat).abs().max() <= 1e-5 * b.flat.abs().max()
+                            and (c.grad_norm_accum - b.grad_norm_accum).abs().max() <= 1e-5
+                            and torch.equal(c.visible_count, b.visible_count) and torch.equal(c.max_radii, b.max_radii))
+        res[M] = dict(nvls=a.uses_nvls, chunks=chunk_ok, err=float((a.flat - b.flat).abs().max()), scale=float(b.flat.abs().max()),
                       norm=float((a.grad_norm_accum - b.grad_norm_accum).abs().max()),
                       ints=bool(torch.equal(a.visible_count, b.visible_count) and torch.equal(a.max_radii, b.max_radii)))
     torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
@@ -54,4 +70,4 @@ def test_nvls_arena_all_reduce_matches_nccl(tmp_path):
         for M, d in res.items():
             if not d["nvls"]:
                 pytest.skip("no multicast mapping on this system")
-            assert d["err"] <= 1e-5 * d["scale"] and d["norm"] <= 1e-5 and d["ints"], (M, d)
+            assert d["err"] <= 1e-5 * d["scale"] and d["norm"] <= 1e-5 and d["ints"] and d["chunks"], (M, d)

@@ -311,6 +311,41 @@ def test_view_pipeline_matches_single_stream(oracle):
     assert (a0.grad_norm_accum - a1.grad_norm_accum).abs().max() <= 2e-3 * a0.grad_norm_accum.max()
 
 
+def test_workspace_steps_are_identical_and_never_reach_the_allocator(oracle):
+    """_C.Workspace: caller-owned scratch and outputs.  The multi-view step gives the same arena with and
+    without it, and from the second step on the caching allocator sees no new device allocation."""
+    from multiview_inpaint_b200 import _C, multiview as mv
+    from multiview_inpaint_b200.rasterizer import GaussianRasterizationSettings
+    W, H, n_views = 160, 96, 4
+    sc = small_scene(12000, W, H, 3, 91, 6.0)
+    dev = torch.device("cuda")
+    gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    cams = [c.to(dev) for c in S.orbit_cameras(n_views, W, H, max_deg=8.0)]
+    bg = torch.zeros(3, device=dev)
+    wts = [S.loss_weights(W, H, 300 + v).to(dev) for v in range(n_views)]
+    rss = [GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                                         scale_modifier=1.0, viewmatrix=c.world_view_transform,
+                                         projmatrix=c.full_proj_transform, sh_degree=3, campos=c.camera_center,
+                                         prefiltered=False) for c in cams]
+    fns = [lambda c, v=v: wts[v] for v in range(n_views)]
+    a0, a1 = mv.GradArena(sc["P"], sc["M"], dev), mv.GradArena(sc["P"], sc["M"], dev)
+    pipe = mv.ViewPipeline(dev, depth=2)
+    st0 = mv.cuda_views_fwd_bwd(gauss, rss, fns, a0, pipeline=pipe)
+    colors0 = [s.color.clone() for s in st0]
+    wss = [_C.Workspace(dev) for _ in range(n_views)]
+    allocs = []
+    for step in range(4):
+        st1 = mv.cuda_views_fwd_bwd(gauss, rss, fns, a1, pipeline=pipe, workspaces=wss)
+        torch.cuda.synchronize()
+        allocs.append(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
+    for x, s in zip(colors0, st1):
+        assert torch.equal(x, s.color)
+    assert (a0.flat - a1.flat).abs().max() <= 2e-3 * a0.flat.abs().max()
+    assert torch.equal(a0.visible_count, a1.visible_count)
+    assert allocs[-1] == allocs[1], allocs
+    assert all(w.reserved_bytes() > 0 for w in wss)
+
+
 @pytest.mark.parametrize("deg,n_views", [(3, 4), (3, 6), (1, 3), (0, 2), (2, 1)])
 def test_batched_multiview_backward_matches_per_view_sum(oracle, deg, n_views):
     """gsr_backward_blend + gsr_backward_geom_multi (parameters read once, gradients summed over the
@@ -369,3 +404,21 @@ def test_batched_multiview_backward_matches_per_view_sum(oracle, deg, n_views):
             assert (x - y).abs().max() <= 2e-3 * x.abs().max() + 1e-12
         assert (2 * a0.flat - a1.flat).abs().max() <= 4e-3 * scale
         assert torch.equal(2 * a0.visible_count, a1.visible_count)
+        # Gaussian-range launches (gsr_backward_geom_multi_range, what the pipelined all-reduce issues) tile the
+        # full launch exactly: same arithmetic per Gaussian, so the arena must be bit-identical
+        a2 = mv.GradArena(sc["P"], sc["M"], dev)
+        a3 = mv.GradArena(sc["P"], sc["M"], dev)
+        a3.flat.fill_(-1.0)
+        mv.cuda_views_geom_backward(gauss, states, a2)
+        views = [dict(radii=s.radii, geom=s.geom, scratch=s.scratch, viewmatrix=s.settings.viewmatrix,
+                      projmatrix=s.settings.projmatrix, campos=s.settings.campos, tanfovx=s.settings.tanfovx,
+                      tanfovy=s.settings.tanfovy, width=W, height=H) for s in states]
+        for g0 in range(0, sc["P"], 4100):
+            _C.backward_geom_multi(gauss["means3D"], gauss["shs"], gauss["scales"], gauss["rotations"], 1.0, sc["sh_degree"],
+                                   views, a3.views, stats=(a3.grad_norm_accum, a3.visible_count, a3.max_radii),
+                                   g_range=(g0, min(sc["P"], g0 + 4100)))
+        torch.cuda.synchronize()
+        assert torch.equal(a2.storage, a3.storage)
+        with pytest.raises(RuntimeError):
+            _C.backward_geom_multi(gauss["means3D"], gauss["shs"], gauss["scales"], gauss["rotations"], 1.0, sc["sh_degree"],
+                                   views, a3.views, g_range=(3, 100))
