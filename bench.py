@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (ViewPipeline depth; 1 = one stream)")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "nvls"],
                     help="arena collective: NCCL, the in-switch multimem kernel, or whichever is faster here")
-    ap.add_argument("--ar-chunks", type=int, default=4, help="Gaussian-range chunks of the pipelined per-Gaussian backward + in-switch all-reduce (1 = sequential)")
+    ap.add_argument("--ar-chunks", type=int, default=8, help="Gaussian-range chunks of the pipelined per-Gaussian backward + in-switch all-reduce (1 = sequential)")
     ap.add_argument("--per-view-backward", action="store_true", help="K8+K9 per view (accumulate) instead of one batched launch per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")

@@ -145,9 +145,12 @@ class GradArena:
         dist.all_reduce(self.visible_count, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
 
-    def all_reduce_range(self, g0: int, g1: int):
+    def all_reduce_range(self, g0: int, g1: int, post_barrier: bool = True):
         """In-switch all-reduce of the arena rows (and statistics) of Gaussians [g0, g1) only, on the current
-        stream; g0 must be a multiple of 4.  NVLS only (see cuda_views_geom_backward_allreduce)."""
+        stream; g0 must be a multiple of 4.  NVLS only (see cuda_views_geom_backward_allreduce).  The barrier
+        AFTER the kernel (every rank's slice written back everywhere) is only needed before somebody reads the
+        result or overwrites the rows again: a caller reducing several ranges back to back passes
+        post_barrier=False and ends with one `arena.barrier()`."""
         assert self.uses_nvls and g0 % 4 == 0 and 0 <= g0 <= g1 <= self.P
         from . import _C
         h = self._handle
@@ -163,11 +166,18 @@ class GradArena:
         h.barrier()
         _C.nvls_all_reduce_plan(self._mc, self.storage.device, h.rank, h.world_size, dense=dense, rows=rows,
                                 add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0))
-        h.barrier()
+        if post_barrier:
+            h.barrier()
+
+    def barrier(self):
+        """Cross-rank barrier on the current stream (symmetric-memory signal pads)."""
+        self._handle.barrier()
 
     def comm_stream(self):
         if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(self.storage.device)
+            # high priority: the reduction's CTAs must get SM slots while the (grid-filling) backward of the next
+            # chunk is running, otherwise the two kernels simply run one after the other
+            self._comm_stream = torch.cuda.Stream(self.storage.device, priority=-1)
         return self._comm_stream
 
     @property
@@ -378,7 +388,9 @@ def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewSta
         ev.record(main)
         comm.wait_event(ev)
         with torch.cuda.stream(comm):
-            arena.all_reduce_range(g0, g1)
+            arena.all_reduce_range(g0, g1, post_barrier=False)
+    with torch.cuda.stream(comm):
+        arena.barrier()
     main.wait_stream(comm)
 
 
