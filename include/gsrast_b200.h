@@ -242,6 +242,10 @@ void gsr_profile_enable(int on);
 int gsr_profile_collect(double* ms_host, int64_t* counts_host);
 /* Number of CUDA kernels this library has launched in this process (monotonic). */
 uint64_t gsr_kernel_launches(void);
+/* Diagnostics for the parity tests: evaluates on the device, for each x[i], the approximate units the
+ * default (non-PRECISE) blend uses: out[2i] = rcp.approx.ftz(x[i]), out[2i+1] = ex2.approx.ftz(x[i]).
+ * The branch-free blend backward relies on rcp.approx(1) == 1 and ex2.approx(0) == 1 being exact. */
+int gsr_debug_approx_units(const float* x_dev, int n, float* out_dev, void* stream);
 
 const char* gsr_last_error(void);
 int gsr_version(void);

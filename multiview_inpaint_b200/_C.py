@@ -114,7 +114,7 @@ EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes",
                     "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
-                    "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches",
+                    "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches", "gsr_debug_approx_units",
                     "gsr_last_error", "gsr_version")
 
 
@@ -462,6 +462,16 @@ def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_coun
 
 def kernel_launches() -> int:
     return int(_lib.gsr_kernel_launches())
+
+
+def debug_approx_units(x: torch.Tensor) -> torch.Tensor:
+    """(n,) float32 CUDA -> (n, 2): [rcp.approx.ftz(x), ex2.approx.ftz(x)] as the default blend evaluates them."""
+    x = x.contiguous().float()
+    out = torch.empty(x.numel(), 2, dtype=torch.float32, device=x.device)
+    _lib.gsr_debug_approx_units.restype = _i
+    _lib.gsr_debug_approx_units.argtypes = [C.c_void_p, _i, C.c_void_p, C.c_void_p]
+    _check(_lib.gsr_debug_approx_units(_ptr(x), x.numel(), _ptr(out), _stream(x.device)), "gsr_debug_approx_units")
+    return out
 
 
 def profile_enable(on: bool):

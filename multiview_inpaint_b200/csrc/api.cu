@@ -202,6 +202,13 @@ int gsr_profile_collect(double* ms_host, int64_t* counts_host) {
 }
 int gsr_version(void) { return GSR_VERSION; }
 
+int gsr_debug_approx_units(const float* x_dev, int n, float* out_dev, void* stream) {
+  if (n <= 0) return 0;
+  if (!x_dev || !out_dev) return fail(GSR_E_INVALID, "gsr_debug_approx_units: null pointer");
+  const cudaError_t e = launch_debug_approx_units((cudaStream_t)stream, x_dev, n, out_dev);
+  return e == cudaSuccess ? 0 : fail_cuda(e, "gsr_debug_approx_units");
+}
+
 size_t gsr_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * 48); }
 size_t gsr_sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
   // internal temp + alternate key/value buffers (inputs are preserved by the public entry points)

@@ -10,8 +10,8 @@
 //   * the walk starts at the CTA's max n_contrib, not at the end of the tile list (entries past
 //     every pixel's last contributor are never even staged);
 //   * per (warp, Gaussian) the nine partial sums are reduced across the 32 lanes with a
-//     transposing butterfly (9 shuffles for 8 values + 5 for the ninth) and ONE lane per value
-//     issues a RED.ADD.F32 -- <= 9 L2 reductions per (warp, Gaussian) instead of 9 x 32;
+//     transposing butterfly (12 shuffles for the nine values) and ONE lane per value issues a
+//     RED.ADD.F32 (one predicated instruction) -- 9 L2 reductions per (warp, Gaussian), not 9 x 32;
 //   * reductions land in a packed 48-byte accumulator per Gaussian (2 sectors):
 //       [0..2] dL/dcolor   [3] A = sum dL_dG*G*dx   [4] B = sum dL_dG*G*dy
 //       [5..7] dL/dconic (xx, xy, yy)               [8] dL/dopacity
@@ -23,15 +23,14 @@
 
 namespace gsr {
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// Reduces v0..v7 over the warp; on return lane l holds the total of value index (l >> 2).
-__device__ __forceinline__ float warp_transpose_reduce8(float v0, float v1, float v2, float v3,
-                                                        float v4, float v5, float v6, float v7, int lane) {
+// Reduces nine per-lane values over the warp with a transposing butterfly: 5 + 3 + 2 + 1 + 1 = 12
+// shuffles (every stage halves the number of live values; the ninth rides along and is paired
+// with the survivor of the other eight at the xor-2 stage).  On return lane l holds
+//   (l & 2) == 0 : the total of value index (l >> 2)        (v0..v7)
+//   (l & 2) != 0 : the total of v8
+__device__ __forceinline__ float warp_transpose_reduce9(float v0, float v1, float v2, float v3,
+                                                        float v4, float v5, float v6, float v7,
+                                                        float v8, int lane) {
   const bool h16 = lane & 16;
   float a0 = h16 ? v4 : v0, a1 = h16 ? v5 : v1, a2 = h16 ? v6 : v2, a3 = h16 ? v7 : v3;
   const float b0 = h16 ? v0 : v4, b1 = h16 ? v1 : v5, b2 = h16 ? v2 : v6, b3 = h16 ? v3 : v7;
@@ -39,18 +38,24 @@ __device__ __forceinline__ float warp_transpose_reduce8(float v0, float v1, floa
   a1 += __shfl_xor_sync(0xffffffffu, b1, 16);
   a2 += __shfl_xor_sync(0xffffffffu, b2, 16);
   a3 += __shfl_xor_sync(0xffffffffu, b3, 16);
+  v8 += __shfl_xor_sync(0xffffffffu, v8, 16);
   const bool h8 = lane & 8;
   float c0 = h8 ? a2 : a0, c1 = h8 ? a3 : a1;
   const float d0 = h8 ? a0 : a2, d1 = h8 ? a1 : a3;
   c0 += __shfl_xor_sync(0xffffffffu, d0, 8);
   c1 += __shfl_xor_sync(0xffffffffu, d1, 8);
+  v8 += __shfl_xor_sync(0xffffffffu, v8, 8);
   const bool h4 = lane & 4;
   float e0 = h4 ? c1 : c0;
   const float f0 = h4 ? c0 : c1;
   e0 += __shfl_xor_sync(0xffffffffu, f0, 4);
-  e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
-  e0 += __shfl_xor_sync(0xffffffffu, e0, 1);
-  return e0;
+  v8 += __shfl_xor_sync(0xffffffffu, v8, 4);
+  const bool h2 = lane & 2;
+  float k = h2 ? v8 : e0;
+  const float snd = h2 ? e0 : v8;
+  k += __shfl_xor_sync(0xffffffffu, snd, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  return k;
 }
 
 template <bool PRECISE>
@@ -92,6 +97,9 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;   // accum_rec
   float lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;      // last_color
   float last_alpha = 0.0f;
+  const uint32_t one = (uint32_t)(px >= 0);  // == 1, per-lane and opaque to ptxas (see K6)
+  const bool red_lane = (lane & 3) == 0 || lane == 2;
+  const uint32_t red_off = lane == 2 ? 8u : (uint32_t)(lane >> 2);
 
   const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
   if (lane == 0) s_wmax[warp] = warp_last;
@@ -120,7 +128,7 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
         const uint32_t ebase = s_ent + ws * 32 * ENTRY_BYTES;
         while (m) {
           const int j = bfind(m);
-          m &= ~(1u << j);
+          m &= ~(one << j);
           const uint32_t ea = ebase + j * ENTRY_BYTES;
           const uint32_t epos = gbase + j;  // 0-based list position == contributor index
           const float4 e0 = lds128(ea);
@@ -137,41 +145,51 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
           if (!__any_sync(0xffffffffu, contrib)) continue;
 
           const float4 e2 = lds128(ea + 32);
-          // per-lane partials; lanes that do not contribute add exact zeros
-          const float one_m_alpha = SUB(1.0f, alpha);
-          float Tn, dchT;  // new T, and -T_final/(1-alpha)*bg_dot
+          float dch, dL_dalpha;
           if (PRECISE) {
-            Tn = DIV(T, one_m_alpha);
-            dchT = MUL(DIV(-T_final, one_m_alpha), bg_dot);
+            // the oracle's op order; lanes that do not contribute add exact zeros
+            const float one_m_alpha = SUB(1.0f, alpha);
+            const float Tn = DIV(T, one_m_alpha);
+            const float dchT = MUL(DIV(-T_final, one_m_alpha), bg_dot);  // -T_final/(1-alpha)*<bg, dL_dpixel>
+            dch = contrib ? MUL(alpha, Tn) : 0.0f;
+            const float na0 = FMA(last_alpha, lc0, MUL(SUB(1.0f, last_alpha), acc0));
+            const float na1 = FMA(last_alpha, lc1, MUL(SUB(1.0f, last_alpha), acc1));
+            const float na2 = FMA(last_alpha, lc2, MUL(SUB(1.0f, last_alpha), acc2));
+            dL_dalpha = MUL(SUB(e2.x, na0), dLp0);
+            dL_dalpha = FMA(SUB(e2.y, na1), dLp1, dL_dalpha);
+            dL_dalpha = FMA(SUB(e2.z, na2), dLp2, dL_dalpha);
+            dL_dalpha = FMA(dL_dalpha, Tn, dchT);
+            if (contrib) {
+              T = Tn;
+              acc0 = na0; acc1 = na1; acc2 = na2;
+              lc0 = e2.x; lc1 = e2.y; lc2 = e2.z;
+              last_alpha = alpha;
+            } else {
+              dL_dalpha = 0.0f;
+            }
           } else {
-            const float inv = rcp_approx(one_m_alpha);
-            Tn = T * inv;
-            dchT = neg_Tf_bg * inv;
-          }
-          const float dch = contrib ? MUL(alpha, Tn) : 0.0f;
-          const float na0 = FMA(last_alpha, lc0, MUL(SUB(1.0f, last_alpha), acc0));
-          const float na1 = FMA(last_alpha, lc1, MUL(SUB(1.0f, last_alpha), acc1));
-          const float na2 = FMA(last_alpha, lc2, MUL(SUB(1.0f, last_alpha), acc2));
-          float dL_dalpha = MUL(SUB(e2.x, na0), dLp0);
-          dL_dalpha = FMA(SUB(e2.y, na1), dLp1, dL_dalpha);
-          dL_dalpha = FMA(SUB(e2.z, na2), dLp2, dL_dalpha);
-          dL_dalpha = FMA(dL_dalpha, Tn, dchT);
-          if (contrib) {
-            T = Tn;
-            acc0 = na0; acc1 = na1; acc2 = na2;
-            lc0 = e2.x; lc1 = e2.y; lc2 = e2.z;
-            last_alpha = alpha;
-          } else {
-            dL_dalpha = 0.0f;
+            // Branch-free: a lane that does not contribute runs the same arithmetic with alpha = G = 0,
+            // which leaves its state untouched (rcp.approx(1) == 1 exactly, R + 0 * d == R) and makes
+            // every partial below an exact zero -- no predicated state moves.  The colour behind the
+            // current Gaussian is carried as ONE value per channel, R = last_alpha * last_color +
+            // (1 - last_alpha) * accum_rec, updated as R += alpha * (c - R) (same recurrence as A.6).
+            if (!contrib) { alpha = 0.0f; G = 0.0f; }
+            const float inv = rcp_approx(1.0f - alpha);
+            const float d0 = e2.x - acc0, d1 = e2.y - acc1, d2 = e2.z - acc2;
+            T *= inv;
+            dL_dalpha = fmaf(fmaf(d2, dLp2, fmaf(d1, dLp1, d0 * dLp0)), T, neg_Tf_bg * inv);
+            acc0 = fmaf(alpha, d0, acc0);
+            acc1 = fmaf(alpha, d1, acc1);
+            acc2 = fmaf(alpha, d2, acc2);
+            dch = alpha * T;
           }
           const float w = MUL(MUL(e1.y, dL_dalpha), G);  // dL_dG * G
           const float wx = MUL(w, dx), wy = MUL(w, dy);
-          const float r8 = warp_transpose_reduce8(MUL(dch, dLp0), MUL(dch, dLp1), MUL(dch, dLp2), wx, wy,
-                                                  MUL(-0.5f * dx, wx), MUL(-0.5f * dy, wx), MUL(-0.5f * dy, wy), lane);
-          const float r1 = warp_sum(MUL(G, dL_dalpha));
-          float* dst = gacc + (size_t)__float_as_uint(e1.w) * 12;
-          if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), r8);
-          if (lane == 1) atomicAdd(dst + 8, r1);
+          const float r9 = warp_transpose_reduce9(MUL(dch, dLp0), MUL(dch, dLp1), MUL(dch, dLp2), wx, wy,
+                                                  MUL(-0.5f * dx, wx), MUL(-0.5f * dy, wx), MUL(-0.5f * dy, wy),
+                                                  MUL(G, dL_dalpha), lane);
+          // ONE predicated RED per (warp, Gaussian): lanes 0,4,..,28 carry values 0..7, lane 2 carries value 8
+          if (red_lane) atomicAdd(gacc + (size_t)__float_as_uint(e1.w) * 12 + red_off, r9);
         }
       }
     }
@@ -190,6 +208,19 @@ cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ran
   else
     blend_backward_kernel<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
                                                          n_contrib, dL_dpix, gacc);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// diagnostics (gsr_debug_approx_units): the exact identities the branch-free fast path relies on
+__global__ void debug_approx_units_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[2 * i] = rcp_approx(x[i]);
+  out[2 * i + 1] = ex2_approx(x[i]);
+}
+cudaError_t launch_debug_approx_units(cudaStream_t s, const float* x, int n, float* out) {
+  debug_approx_units_kernel<<<cdiv(n, 128), 128, 0, s>>>(x, n, out);
   count_launch();
   return cudaGetLastError();
 }

@@ -70,6 +70,9 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
     if (!__all_sync(0xffffffffu, done)) {
 #pragma unroll 1
       for (int ws = 0; ws < 8; ws++) {
+        // every pixel of the sub-tile saturated inside this batch: the rest of it can only be skipped
+        // pair by pair (NaN coordinate), so stop walking at the next group of 32 entries
+        if (ws && __all_sync(0xffffffffu, done)) break;
         unsigned m = lds32(s_mask + (warp * 8 + ws) * 4);  // bit 31 - j <=> entry j of this group
         const uint32_t etop = s_ent + (ws * 32 + 31) * ENTRY_BYTES;          // entry 31 of the group
         const uint32_t last_top = (uint32_t)(b * BLEND_BATCH + ws * 32 + 32);  // its 1-based list position

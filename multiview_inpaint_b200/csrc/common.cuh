@@ -176,6 +176,7 @@ cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ran
                                   const uint32_t* point_list, const float4* rec, const float* bg,
                                   const float* final_T, const uint32_t* n_contrib,
                                   const float* dL_dpix, float* gacc /*[P][12]*/, bool precise);
+cudaError_t launch_debug_approx_units(cudaStream_t s, const float* x, int n, float* out /*[n][2]*/);
 cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const float* means3D,
                                  const int32_t* radii, const float* shs, const uint8_t* clamped,
                                  const float* scales, const float* rotations,

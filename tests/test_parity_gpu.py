@@ -422,3 +422,18 @@ def test_batched_multiview_backward_matches_per_view_sum(oracle, deg, n_views):
         with pytest.raises(RuntimeError):
             _C.backward_geom_multi(gauss["means3D"], gauss["shs"], gauss["scales"], gauss["rotations"], 1.0, sc["sh_degree"],
                                    views, a3.views, g_range=(3, 100))
+
+
+def test_approx_units_identities_the_branch_free_backward_relies_on():
+    """The default blend backward runs non-contributing lanes with alpha = G = 0 instead of predicating
+    their state updates: T *= rcp.approx(1 - 0) must leave T untouched, so rcp.approx(1) must be exactly 1
+    (and ex2.approx(0) exactly 1, the peak of a Gaussian).  Also bounds the two units' relative error."""
+    from multiview_inpaint_b200 import _C
+    x = torch.tensor([1.0, 0.0, 0.5, 2.0, 0.01, 0.25, 1.0 - 0.99, 0.7311, -3.25, -17.5], device="cuda")
+    out = _C.debug_approx_units(x).cpu().double()
+    assert out[0, 0].item() == 1.0          # rcp(1) == 1 exactly
+    assert out[1, 1].item() == 1.0          # ex2(0) == 1 exactly
+    xs = x.cpu().double()
+    nz = xs != 0
+    assert ((out[nz, 0] * xs[nz] - 1).abs() < 2e-7 * 4).all()            # rcp.approx: ~1 ulp
+    assert ((out[:, 1] / torch.exp2(xs) - 1).abs() < 5e-7).all()         # ex2.approx: 2^-22
