@@ -194,6 +194,17 @@ int gsr_nvls_all_reduce_plan(void* stream, void* multicast_ptr, const gsr_nvls_p
 int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii);
 
+/* ---- neighbour distances --------------------------------------------------------
+ * Replaces `simple_knn._C.distCUDA2(points) -> Tensor[P]` (third-party simple-knn extension, source not in the
+ * reference tree), imported at gs-simp/scene/gaussian_model.py:20 and called at :134, :546, :623:
+ * mean_dist2[i] = (d1 + d2 + d3) / 3, the mean SQUARED distance from point i to its three nearest OTHER
+ * points (coincident points count, with distance 0; fewer than four points leave FLT_MAX terms, as upstream).
+ * points (P,3) float32, mean_dist2 (P,), temp >= gsr_knn_temp_bytes(P) bytes, all device memory.
+ * Exact (not approximate) nearest neighbours: bit-identical to a brute-force scan with
+ * d = fma(dz,dz, fma(dy,dy, dx*dx)). */
+size_t gsr_knn_temp_bytes(int P);
+int gsr_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, char* temp, size_t temp_bytes);
+
 /* ---- building blocks, exported so that parity tests can drive each stage through the C ABI ---- */
 
 /* Stable LSD onesweep radix sort of (key,value) pairs on key bits [0,end_bit), 8-bit digits.

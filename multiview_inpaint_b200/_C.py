@@ -92,6 +92,10 @@ _lib.gsr_nvls_all_reduce.restype = _i
 _lib.gsr_nvls_all_reduce.argtypes = [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _i, _i, _i, _sz, _sz, _i]
 _lib.gsr_accumulate_view_stats.restype = _i
 _lib.gsr_accumulate_view_stats.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
+_lib.gsr_knn_temp_bytes.restype = _sz
+_lib.gsr_knn_temp_bytes.argtypes = [_i]
+_lib.gsr_knn3_mean_dist2.restype = _i
+_lib.gsr_knn3_mean_dist2.argtypes = [_vp, _i, _vp, _vp, _vp, _sz]
 _lib.gsr_sort_temp_bytes.restype = _sz
 _lib.gsr_sort_temp_bytes.argtypes = [_i64, _i, _i]
 _lib.gsr_sort_pairs_u64.restype = _i
@@ -111,7 +115,7 @@ _lib.gsr_profile_collect.restype = _i
 _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
-                    "gsr_accumulate_view_stats", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
+                    "gsr_accumulate_view_stats", "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches", "gsr_debug_approx_units",
@@ -347,6 +351,23 @@ def mark_visible(means3D, viewmatrix, projmatrix):
             _check(_lib.gsr_mark_visible(_stream(dev), P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix),
                                          present.data_ptr()), "mark_visible")
     return present
+
+
+def dist_cuda2(points):
+    """`simple_knn._C.distCUDA2(points) -> float32[P]`: mean squared distance of every point to its three
+    nearest other points (reference call sites gs-simp/scene/gaussian_model.py:134,546,623)."""
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("points must have dimensions (num_points, 3)")
+    P = points.shape[0]
+    dev = points.device
+    points = _f32c(points, "points")
+    out = torch.empty(P, dtype=torch.float32, device=dev)
+    if P != 0:
+        with torch.cuda.device(dev):
+            nb = int(_lib.gsr_knn_temp_bytes(P))
+            temp = torch.empty(nb, dtype=torch.uint8, device=dev)
+            _check(_lib.gsr_knn3_mean_dist2(_stream(dev), P, _ptr(points), _ptr(out), _ptr(temp), nb), "knn3_mean_dist2")
+    return out
 
 
 def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBuffer, P, flags=None, workspace=None):

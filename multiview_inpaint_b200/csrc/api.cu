@@ -209,6 +209,17 @@ int gsr_debug_approx_units(const float* x_dev, int n, float* out_dev, void* stre
   return e == cudaSuccess ? 0 : fail_cuda(e, "gsr_debug_approx_units");
 }
 
+size_t gsr_knn_temp_bytes(int P) { return knn_temp_bytes(P); }
+int gsr_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, char* temp, size_t temp_bytes) {
+  if (P < 0) return fail(GSR_E_INVALID, "gsr_knn3_mean_dist2: P < 0");
+  if (P == 0) return 0;
+  if (P >= (1 << 30)) return fail(GSR_E_OVERFLOW, "gsr_knn3_mean_dist2: P >= 2^30");
+  if (!points || !mean_dist2 || !temp || temp_bytes < knn_temp_bytes(P))
+    return fail(GSR_E_INVALID, "gsr_knn3_mean_dist2: null argument or temp too small");
+  GSR_CUDA(launch_knn3_mean_dist2(reinterpret_cast<cudaStream_t>(stream), P, points, mean_dist2, temp), "knn3_mean_dist2");
+  return 0;
+}
+
 size_t gsr_backward_scratch_bytes(int P) { return align_up((size_t)(P > 0 ? P : 1) * 48); }
 size_t gsr_sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
   // internal temp + alternate key/value buffers (inputs are preserved by the public entry points)

@@ -10,6 +10,7 @@
  */
 #include "gsplat_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -756,5 +757,32 @@ void gso_mark_visible(int P, const float* means3D, const float* viewmatrix, uint
     float pv[3];
     xform4x3(means3D + 3 * (size_t)i, viewmatrix, pv);
     present[i] = pv[2] > 0.2f;
+  }
+}
+
+/* ---- simple_knn.distCUDA2 -------------------------------------------------
+ * Restates what the reference gets from `simple_knn._C.distCUDA2` (import gs-simp/scene/gaussian_model.py:20,
+ * call sites :134, :546, :623).  The extension's source is not in the reference tree (third-party
+ * simple-knn, unpinned, environment.yml:17): PARITY UNPINNED.  Published algorithm: for every point keep
+ * the three smallest squared distances to the OTHER points (strict '<' insertion into a sorted triple that
+ * starts at FLT_MAX) and return their mean; upstream only prunes the scan with conservative box tests, so
+ * the value equals this brute-force scan.  Distance op order = what nvcc's default contraction makes of
+ * d.x*d.x + d.y*d.y + d.z*d.z: fma(dz,dz, fma(dy,dy, dx*dx)).
+ * queries == NULL: all P points (out has P entries); otherwise out[k] is for point queries[k]. */
+void gso_knn3_mean_dist2(int P, const float* pts, const int32_t* queries, int nq, float* out) {
+  const int n = queries ? nq : P;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int k = 0; k < n; k++) {
+    const int i = queries ? queries[k] : k;
+    const float qx = pts[3 * (size_t)i], qy = pts[3 * (size_t)i + 1], qz = pts[3 * (size_t)i + 2];
+    float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    for (int j = 0; j < P; j++) {
+      if (j == i) continue;
+      const float dx = qx - pts[3 * (size_t)j], dy = qy - pts[3 * (size_t)j + 1], dz = qz - pts[3 * (size_t)j + 2];
+      float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      for (int t = 0; t < 3; t++)
+        if (best[t] > d) { const float tmp = best[t]; best[t] = d; d = tmp; }
+    }
+    out[k] = ((best[0] + best[1]) + best[2]) / 3.0f;
   }
 }

@@ -116,6 +116,10 @@ void gso_preprocess_backward(int P, int D, int M,
 /* markVisible (K10): view-space z > 0.2. */
 void gso_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present);
 
+/* simple_knn.distCUDA2: mean squared distance to the three nearest other points (brute force, exact).
+ * PARITY UNPINNED (third-party source absent).  queries may be NULL (= all points). */
+void gso_knn3_mean_dist2(int P, const float* pts, const int32_t* queries, int nq, float* out);
+
 int gso_num_threads(void);
 
 #ifdef __cplusplus

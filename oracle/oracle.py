@@ -205,3 +205,18 @@ def mark_visible(means3D, viewmatrix) -> np.ndarray:
     out = np.zeros(means3D.shape[0], np.uint8)
     lib().gso_mark_visible(C.c_int(means3D.shape[0]), _p(means3D), _p(viewmatrix), _p(out))
     return out.astype(bool)
+
+
+def knn3_mean_dist2(points, queries=None) -> np.ndarray:
+    """simple_knn.distCUDA2 restated by brute force (gaussian_model.py:134,546,623); `queries` = optional
+    subset of point indices (for sampled checks at sizes where P*P is too much)."""
+    pts = _f32(points).reshape(-1, 3)
+    P = pts.shape[0]
+    if queries is None:
+        out = np.zeros(P, np.float32)
+        lib().gso_knn3_mean_dist2(C.c_int(P), _p(pts), _p(None), C.c_int(0), _p(out))
+        return out
+    q = np.ascontiguousarray(np.asarray(queries, dtype=np.int32))
+    out = np.zeros(q.shape[0], np.float32)
+    lib().gso_knn3_mean_dist2(C.c_int(P), _p(pts), _p(q), C.c_int(q.shape[0]), _p(out))
+    return out
