@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: fwd+bwd views/s (the BASELINE metric, default); infer: forward-only colour+depth views/s "
+                         "(BASELINE config 4, render.py / render_depth.py), no collective")
     ap.add_argument("--views-per-rank", type=int, default=4)
     ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
     ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
@@ -472,9 +475,167 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# -------------------------------------------------------------------------------------------------
+# inference mode (BASELINE config 4: render.py + render_depth.py loops): forward only, views sharded, no collective
+# -------------------------------------------------------------------------------------------------
+def run_infer(args):
+    import torch
+    import torch.distributed as dist
+    from multiview_inpaint_b200 import _C, multiview as mv, scenes as S
+    from multiview_inpaint_b200.rasterizer import GaussianRasterizationSettings
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(S.CONFIGS[args.workload])
+    sc = S.make_config_scene(args.workload)
+    P, W, H, M, D = sc["P"], sc["W"], sc["H"], sc["M"], sc["sh_degree"]
+    G = ((W + 15) // 16) * ((H + 15) // 16)
+    gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    vpr = args.views_per_rank
+    n_views = vpr * world
+    cams_cpu = S.orbit_cameras(n_views, W, H, max_deg=args.orbit_deg)
+    mine = mv.shard_views(n_views, rank, world)
+    bg = torch.zeros(3, device=dev)
+    cams_dev = {v: cams_cpu[v].to(dev) for v in mine}
+
+    def settings(cam):
+        return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                             bg=bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform,
+                                             projmatrix=cam.full_proj_transform, sh_degree=D, campos=cam.camera_center,
+                                             prefiltered=False)
+    av = mv.AsyncViews(n_views)
+    stats = {}
+    for v in mine:   # exact-size pass: learns each view's num_rendered for the capacity hints
+        r = mv.cuda_views_render(gauss, [settings(cams_dev[v])], flags=args.flags)[0]
+        av.learn(v, r.num_rendered)
+        stats["N"], stats["radii"] = r.num_rendered, r.radii
+    pipe = mv.ViewPipeline(dev, depth=args.streams) if args.streams > 1 else None
+    workspaces = [_C.Workspace(dev) for _ in mine]
+    throttle = mv.StepThrottle(2)
+
+    def step_resident(pipe=pipe):
+        mv.cuda_views_render(gauss, [settings(cams_dev[v]) for v in mine], flags=args.flags,
+                             capacities=[av.capacity(v) for v in mine], async_results=[av.slot(v) for v in mine],
+                             pipeline=pipe, workspaces=workspaces)
+        throttle.tick(dev)
+
+    # e2e: camera from pinned host memory in, colour + depth to pinned host memory out (what the PNG / NPY writer reads)
+    cam_pinned = {v: torch.cat([cams_cpu[v].world_view_transform.reshape(-1), cams_cpu[v].full_proj_transform.reshape(-1),
+                                cams_cpu[v].camera_center.reshape(-1)]).pin_memory() for v in mine}
+    cam_stage = {v: torch.empty(35, device=dev) for v in mine}
+    host_color = [torch.empty(3, H, W).pin_memory() for _ in mine]
+    host_depth = [torch.empty(1, H, W).pin_memory() for _ in mine]
+
+    def step_e2e():
+        def stage(v):
+            def f():
+                cam_stage[v].copy_(cam_pinned[v], non_blocking=True)
+                c = cams_cpu[v]
+                return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                                                     scale_modifier=1.0, viewmatrix=cam_stage[v][:16].view(4, 4),
+                                                     projmatrix=cam_stage[v][16:32].view(4, 4), sh_degree=D,
+                                                     campos=cam_stage[v][32:35], prefiltered=False)
+            return f
+
+        def sink(k, color, depth, radii):
+            host_color[k].copy_(color, non_blocking=True)
+            host_depth[k].copy_(depth, non_blocking=True)
+        mv.cuda_views_render(gauss, [stage(v) for v in mine], flags=args.flags, capacities=[av.capacity(v) for v in mine],
+                             async_results=[av.slot(v) for v in mine], pipeline=pipe, workspaces=workspaces, sink=sink)
+        torch.cuda.current_stream(dev).synchronize()     # the step's result is on the host
+        assert not av.check(mine), "capacity overflow inside the timed region"
+    h2d = len(mine) * 35 * 4
+    d2h = len(mine) * (4 * H * W * 4 + 8)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    assert not av.check(mine)
+    V, N = int((stats["radii"] > 0).sum().item()), int(stats["N"])
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _C.kernel_launches()
+    ms_total = timed(step_resident, args.steps)
+    launches = _C.kernel_launches() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert not av.check(mine), "capacity overflow inside the timed region"
+    step_resident(None)
+    torch.cuda.synchronize()
+    _C.profile_enable(True)
+    _C.profile_collect()
+    ms_prof = timed(lambda: step_resident(None), args.steps)
+    _C.profile_enable(False)
+    stage_ms, stage_cnt = _C.profile_collect()
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    views_total = n_views * args.steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = peaks()
+    alg = algorithmic_bytes(P, V, N, G, W, H, M)
+    fwd_stages = ("preprocess", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward")
+    per_launch = {k: stage_ms[k] / max(stage_cnt[k], 1) for k in stage_ms if stage_cnt[k] > 0}
+    dom = max((k for k in per_launch if k in fwd_stages), key=lambda k: stage_ms[k])
+    ach = alg[dom] / (per_launch[dom] / 1000.0) / 1e9
+    b_view = sum(alg[k] for k in fwd_stages)
+    ms_view = ms_total / views_total * world
+    line = {
+        "metric": "fwd views/s (colour + depth)", "value": views_total / (ms_total / 1000.0), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "mode": "infer", **cfg, "views_per_rank": vpr, "views_per_step": n_views,
+                   "orbit_deg": args.orbit_deg, "streams": args.streams, "P": P, "V": V, "N": N, "G": G, "M": M, "flags": args.flags,
+                   "parallelism": f"views sharded over {world} rank(s), no collective",
+                   "l2": "inputs larger than the 126 MB L2; no flush needed"},
+        "e2e": {"value": views_total / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": sampler.summary(), "profiled_ms_per_step": ms_prof / args.steps,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": alg[dom],
+                     "ms_per_launch": per_launch[dom],
+                     "view": {"alg_bytes": b_view, "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
+                              "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
+        "stages": {k: {"ms_per_launch": round(per_launch[k], 4), "alg_bytes_per_view": alg.get(k)} for k in per_launch},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "infer":
+        run_infer(a)
     else:
         run_ours(a)

@@ -11,7 +11,7 @@
 //
 // B200 design (not the upstream structure, which walks every 1024-point box for every point through an
 // index indirection):
-//   * bounds by ordered-uint atomics, 30-bit Morton keys, the repo's own onesweep sort (scan_sort.cu),
+//   * bounds by ordered-uint atomics, 63-bit Morton keys, the repo's own onesweep sort (scan_sort.cu),
 //     points GATHERED into Morton order as float4 so that every later read is a coalesced 512-byte line;
 //   * a 32-ary bounding-box tree over the sorted order, built bottom-up one warp per node;
 //   * search: ONE WARP per leaf of 32 queries.  The warp seeds its 32 running top-3 lists from its own leaf,
@@ -78,27 +78,31 @@ __global__ void __launch_bounds__(256) knn_bounds_kernel(const float* __restrict
   }
 }
 
-__device__ __forceinline__ uint32_t spread10(uint32_t x) {  // 10 bits -> every third bit
-  x &= 0x3ffu;
-  x = (x | (x << 16)) & 0x030000ffu;
-  x = (x | (x << 8)) & 0x0300f00fu;
-  x = (x | (x << 4)) & 0x030c30c3u;
-  x = (x | (x << 2)) & 0x09249249u;
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {  // 21 bits -> every third bit
+  uint64_t x = v & 0x1fffffu;
+  x = (x | (x << 32)) & 0x001f00000000ffffull;
+  x = (x | (x << 16)) & 0x001f0000ff0000ffull;
+  x = (x | (x << 8)) & 0x100f00f00f00f00full;
+  x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
   return x;
 }
 
+// 63-bit Morton keys (21 bits per axis).  Upstream uses 10 bits per axis; a dense cluster that falls into one
+// 1/1024 cell then keeps its input order, its leaves become spatially random and no box can be pruned inside
+// it (measured: 137 ms instead of a few ms at 3 M clustered points).  The order only affects speed, never values.
 __global__ void __launch_bounds__(256) knn_morton_kernel(const float* __restrict__ pts, int P, const uint32_t* __restrict__ bounds,
-                                                         uint32_t* __restrict__ keys) {
+                                                         uint64_t* __restrict__ keys) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  uint32_t code = 0;
+  uint64_t code = 0;
 #pragma unroll
   for (int c = 0; c < 3; c++) {
     const float lo = ord2f(__ldg(bounds + c)), hi = ord2f(__ldg(bounds + 4 + c));
     const float ext = hi - lo;
     const float t = ext > 0.f ? (__ldg(pts + 3 * (size_t)i + c) - lo) / ext : 0.f;
-    const int q = min(1023, max(0, (int)(t * 1023.f)));   // NaN -> 0
-    code |= spread10((uint32_t)q) << c;
+    const int q = min(2097151, max(0, (int)(t * 2097151.f)));   // NaN -> 0
+    code |= spread21((uint32_t)q) << c;
   }
   keys[i] = code;
 }
@@ -267,12 +271,12 @@ KnnLayout knn_layout(int P) {
   auto take = [&](size_t bytes) { const size_t r = o; o += align_up(bytes); return r; };
   const int P32 = (P + 31) / 32 * 32;
   L.bounds = take(32);
-  L.keys = take((size_t)P * 4);
-  L.keys_sorted = take((size_t)P * 4);
+  L.keys = take((size_t)P * 8);
+  L.keys_sorted = take((size_t)P * 8);
   L.order = take((size_t)P * 4);
-  L.keys_alt = take((size_t)P * 4);
+  L.keys_alt = take((size_t)P * 8);
   L.vals_alt = take((size_t)P * 4);
-  L.sort_temp = take(sort_temp_bytes(P, 4, 30));
+  L.sort_temp = take(sort_temp_bytes(P, 8, 63));
   L.sorted = take((size_t)P32 * sizeof(float4));
   int n = P32 / 32, lv = 0;
   L.boxes = o;
@@ -298,8 +302,8 @@ cudaError_t launch_knn3_mean_dist2(cudaStream_t s, int P, const float* points, f
   if (L.count[L.levels - 1] > 32) return cudaErrorInvalidValue;   // cannot happen below 2^30 points
   const int P32 = (P + 31) / 32 * 32;
   uint32_t* bounds = reinterpret_cast<uint32_t*>(temp + L.bounds);
-  uint32_t* keys = reinterpret_cast<uint32_t*>(temp + L.keys);
-  uint32_t* keys_sorted = reinterpret_cast<uint32_t*>(temp + L.keys_sorted);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(temp + L.keys);
+  uint64_t* keys_sorted = reinterpret_cast<uint64_t*>(temp + L.keys_sorted);
   uint32_t* order = reinterpret_cast<uint32_t*>(temp + L.order);
   float4* sorted = reinterpret_cast<float4*>(temp + L.sorted);
   cudaError_t e;
@@ -310,8 +314,8 @@ cudaError_t launch_knn3_mean_dist2(cudaStream_t s, int P, const float* points, f
   knn_bounds_kernel<<<blocks, 256, 0, s>>>(points, P, bounds);
   knn_morton_kernel<<<cdiv(P, 256), 256, 0, s>>>(points, P, bounds, keys);
   count_launch(2);
-  e = launch_sort_pairs_u32(s, P, nullptr, keys, nullptr, keys_sorted, order, reinterpret_cast<uint32_t*>(temp + L.keys_alt),
-                            reinterpret_cast<uint32_t*>(temp + L.vals_alt), 30, temp + L.sort_temp);
+  e = launch_sort_pairs_u64(s, P, nullptr, keys, nullptr, keys_sorted, order, reinterpret_cast<uint64_t*>(temp + L.keys_alt),
+                            reinterpret_cast<uint32_t*>(temp + L.vals_alt), 63, temp + L.sort_temp);
   if (e != cudaSuccess) return e;
   knn_gather_kernel<<<cdiv(P32, 256), 256, 0, s>>>(points, order, P, P32, sorted);
   KnnTree tree{};

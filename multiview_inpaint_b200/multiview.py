@@ -510,6 +510,38 @@ def sharded_step(view_fwd_bwd: Callable[[int], None], n_views: int, arena: GradA
     return mine
 
 
+def cuda_views_render(gaussians: dict, settings_list: Sequence, flags: int = 0, capacities: Sequence[int] | None = None,
+                      async_results: Sequence | None = None, pipeline: ViewPipeline | None = None,
+                      workspaces: Sequence | None = None,
+                      sink: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None] | None = None) -> list[ViewResult]:
+    """Batched inference: the forward of every view of `settings_list` -- the loops of
+    render.py:32-39, render_depth.py:31-39 and gen_seq.py:36-58, which call render() once per camera under
+    no_grad and then block on an image write.  Views alternate over the pipeline's streams (front end of view
+    v+1 under the blend of view v), each with its own caller-owned Workspace, and with `capacities` +
+    `async_results` nothing blocks the host.  `sink(k, color, depth, radii)` runs on view k's stream right after
+    its forward -- the place for the device-to-host copy into pinned memory that an asynchronous PNG / NPY
+    writer drains; with workspaces the three tensors are views that the next call on that workspace overwrites."""
+    import contextlib
+    from . import _C
+    out = []
+    with torch.no_grad(), (pipeline.step() if pipeline else contextlib.nullcontext()):
+        for k, settings in enumerate(settings_list):
+            with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
+                rs = settings() if callable(settings) else settings
+                e = torch.empty(0, device=gaussians["means3D"].device)
+                n, color, radii, _geom, _binning, _img, depth = _C.rasterize_gaussians(
+                    rs.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
+                    rs.scale_modifier, e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                    rs.image_width, gaussians["shs"], rs.sh_degree, rs.campos, rs.prefiltered, flags=flags,
+                    capacity=capacities[k] if capacities else None,
+                    async_result=async_results[k] if async_results else None,
+                    workspace=workspaces[k] if workspaces else None)
+                if sink is not None:
+                    sink(k, color, depth, radii)
+                out.append(ViewResult(color, depth, radii, n))
+    return out
+
+
 def render_views_sharded(render_one: Callable[[int], Sequence[torch.Tensor]], n_views: int,
                          rank: int = 0, world: int = 1) -> dict[int, Sequence[torch.Tensor]]:
     """Inference (render.py / render_depth.py loops): no collective, rank r renders views r, r+R, ..."""
