@@ -194,6 +194,53 @@ int gsr_nvls_all_reduce_plan(void* stream, void* multicast_ptr, const gsr_nvls_p
 int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii);
 
+/* ---- the training step either side of the rasterizer ---------------------
+ * Fused photometric loss, replaces the torch expression of gs-simp/train.py:91-92 (also sds_train.py:117-118,
+ * inpaint_rec.py:118-123):
+ *     Ll1 = l1_loss(image, gt)                                   utils/loss_utils.py:17-18
+ *     loss = (1 - lambda_dssim) * Ll1 + lambda_dssim * (1 - ssim(image, gt))    utils/loss_utils.py:33-62
+ * image, gt (C,H,W) float32.  Forward writes out_loss3 = {Ll1, ssim, loss} (device, 3 floats) and keeps three
+ * (C,H,W) derivative maps in `temp` (>= gsr_loss_temp_bytes bytes), which the backward consumes:
+ * dL_dimage (C,H,W) = dL_dloss * d loss / d image; dL_dloss is a DEVICE scalar (NULL = 1.0, what loss.backward()
+ * seeds).  dL_dimage is what gsr_backward takes as dL_dpix. */
+size_t gsr_loss_temp_bytes(int C, int H, int W);
+int gsr_loss_l1_ssim_forward(void* stream, int C, int H, int W, const float* image, const float* gt,
+                             float lambda_dssim, float* out_loss3, char* temp, size_t temp_bytes);
+int gsr_loss_l1_ssim_backward(void* stream, int C, int H, int W, const float* image, const float* gt,
+                              float lambda_dssim, const float* dL_dloss, const char* temp, size_t temp_bytes,
+                              float* dL_dimage);
+
+/* Parameter activations of GaussianModel's getters (gs-simp/scene/gaussian_model.py:33-41,95-115), one kernel:
+ * scales = exp(raw_scales) (P,3), rotations = normalize(raw_rotations) (P,4; v / max(|v|, 1e-12)),
+ * opacities = sigmoid(raw_opacities) (P,).  Any of the three raw pointers may be NULL (that group is skipped).
+ * Backward runs IN PLACE: g_* hold dL/d(activated) on entry (e.g. slices of the gradient arena after
+ * gsr_backward_geom_multi) and dL/d(raw) on exit -- what autograd would hand to Adam for _scaling, _rotation,
+ * _opacity.  rotations / g_rotations must be 16-byte aligned. */
+int gsr_activate_forward(void* stream, int P, const float* raw_scales, const float* raw_rotations,
+                         const float* raw_opacities, float* scales, float* rotations, float* opacities);
+int gsr_activate_backward(void* stream, int P, const float* raw_scales, const float* raw_rotations,
+                          const float* raw_opacities, float* g_scales, float* g_rotations, float* g_opacities);
+
+/* Adam over up to 8 parameter segments in ONE launch; replaces `gaussians.optimizer.step()` (train.py:127) for the
+ * optimizer of gaussian_model.py:154-165 = torch.optim.Adam(groups, lr=0.0, eps=1e-15): betas (0.9, 0.999), no
+ * weight decay, no amsgrad, dense (every parameter moves every step, as in the reference).  `step` is the
+ * 1-based step count after the increment (torch's state['step']).  A row-structured segment (row_len > 0) uses
+ * `lr` for floats [0,row_split) of every row and `lr_rest` for [row_split,row_len): the (P,M,3) SH tensor holds
+ * f_dc (lr = feature_lr) and f_rest (lr = feature_lr / 20) side by side, row_len = 3M, row_split = 3. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  uint64_t n;        /* floats in the segment */
+  float lr;
+  float lr_rest;
+  int row_len;       /* 0 = flat segment */
+  int row_split;
+} gsr_adam_segment;
+int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, float beta1,
+                  float beta2, float eps);
+
 /* ---- neighbour distances --------------------------------------------------------
  * Replaces `simple_knn._C.distCUDA2(points) -> Tensor[P]` (third-party simple-knn extension, source not in the
  * reference tree), imported at gs-simp/scene/gaussian_model.py:20 and called at :134, :546, :623:

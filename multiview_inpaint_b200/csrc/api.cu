@@ -209,6 +209,68 @@ int gsr_debug_approx_units(const float* x_dev, int n, float* out_dev, void* stre
   return e == cudaSuccess ? 0 : fail_cuda(e, "gsr_debug_approx_units");
 }
 
+size_t gsr_loss_temp_bytes(int C, int H, int W) {
+  if (C <= 0 || H <= 0 || W <= 0) return 0;
+  return loss_temp_bytes(C, H, W);
+}
+int gsr_loss_l1_ssim_forward(void* stream, int C, int H, int W, const float* image, const float* gt,
+                             float lambda_dssim, float* out_loss3, char* temp, size_t temp_bytes) {
+  if (C <= 0 || H <= 0 || W <= 0 || C > 65535) return fail(GSR_E_INVALID, "gsr_loss_l1_ssim_forward: bad shape");
+  if (!image || !gt || !out_loss3 || !temp || temp_bytes < loss_temp_bytes(C, H, W))
+    return fail(GSR_E_INVALID, "gsr_loss_l1_ssim_forward: null argument or temp too small");
+  if ((reinterpret_cast<uintptr_t>(temp) & 15) != 0) return fail(GSR_E_INVALID, "gsr_loss_l1_ssim_forward: temp not 16-byte aligned");
+  GSR_CUDA(launch_loss_forward(reinterpret_cast<cudaStream_t>(stream), C, H, W, image, gt, lambda_dssim, out_loss3, temp),
+           "loss forward");
+  return 0;
+}
+int gsr_loss_l1_ssim_backward(void* stream, int C, int H, int W, const float* image, const float* gt,
+                              float lambda_dssim, const float* dL_dloss, const char* temp, size_t temp_bytes,
+                              float* dL_dimage) {
+  if (C <= 0 || H <= 0 || W <= 0 || C > 65535) return fail(GSR_E_INVALID, "gsr_loss_l1_ssim_backward: bad shape");
+  if (!image || !gt || !dL_dimage || !temp || temp_bytes < loss_temp_bytes(C, H, W))
+    return fail(GSR_E_INVALID, "gsr_loss_l1_ssim_backward: null argument or temp too small");
+  GSR_CUDA(launch_loss_backward(reinterpret_cast<cudaStream_t>(stream), C, H, W, image, gt, lambda_dssim, dL_dloss, temp,
+                                dL_dimage), "loss backward");
+  return 0;
+}
+
+int gsr_activate_forward(void* stream, int P, const float* raw_scales, const float* raw_rotations,
+                         const float* raw_opacities, float* scales, float* rotations, float* opacities) {
+  if (P < 0 || (P > 0 && ((raw_scales && !scales) || (raw_rotations && !rotations) || (raw_opacities && !opacities))))
+    return fail(GSR_E_INVALID, "gsr_activate_forward: bad argument");
+  if (((reinterpret_cast<uintptr_t>(raw_rotations) | reinterpret_cast<uintptr_t>(rotations)) & 15) != 0)
+    return fail(GSR_E_INVALID, "gsr_activate_forward: rotations not 16-byte aligned");
+  GSR_CUDA(launch_activate_forward(reinterpret_cast<cudaStream_t>(stream), P, raw_scales, raw_rotations, raw_opacities,
+                                   scales, rotations, opacities), "activate forward");
+  return 0;
+}
+int gsr_activate_backward(void* stream, int P, const float* raw_scales, const float* raw_rotations,
+                          const float* raw_opacities, float* g_scales, float* g_rotations, float* g_opacities) {
+  if (P < 0 || (P > 0 && ((raw_scales && !g_scales) || (raw_rotations && !g_rotations) || (raw_opacities && !g_opacities))))
+    return fail(GSR_E_INVALID, "gsr_activate_backward: bad argument");
+  if (((reinterpret_cast<uintptr_t>(raw_rotations) | reinterpret_cast<uintptr_t>(g_rotations)) & 15) != 0)
+    return fail(GSR_E_INVALID, "gsr_activate_backward: rotations not 16-byte aligned");
+  GSR_CUDA(launch_activate_backward(reinterpret_cast<cudaStream_t>(stream), P, raw_scales, raw_rotations, raw_opacities,
+                                    g_scales, g_rotations, g_opacities), "activate backward");
+  return 0;
+}
+
+int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, float beta1,
+                  float beta2, float eps) {
+  if (n_segs < 0 || n_segs > 8 || (n_segs > 0 && !segs_host) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
+      !(beta2 >= 0.f && beta2 < 1.f))
+    return fail(GSR_E_INVALID, "gsr_adam_step: bad argument (1..8 segments, step >= 1, betas in [0,1))");
+  for (int k = 0; k < n_segs; k++) {
+    const gsr_adam_segment& g = segs_host[k];
+    if (g.n == 0) continue;
+    if (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq) return fail(GSR_E_INVALID, "gsr_adam_step: null pointer in a segment");
+    if (g.row_len < 0 || (g.row_len > 0 && (g.row_split < 0 || g.row_split > g.row_len)))
+      return fail(GSR_E_INVALID, "gsr_adam_step: bad row structure");
+  }
+  GSR_CUDA(launch_adam(reinterpret_cast<cudaStream_t>(stream), segs_host, n_segs, step, beta1, beta2, eps), "adam");
+  return 0;
+}
+
 size_t gsr_knn_temp_bytes(int P) { return knn_temp_bytes(P); }
 int gsr_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, char* temp, size_t temp_bytes) {
   if (P < 0) return fail(GSR_E_INVALID, "gsr_knn3_mean_dist2: P < 0");

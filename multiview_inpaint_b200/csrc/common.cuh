@@ -226,4 +226,16 @@ cudaError_t launch_knn3_mean_dist2(cudaStream_t s, int P, const float* points, f
 cudaError_t launch_view_stats(cudaStream_t s, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii);
 
+size_t loss_temp_bytes(int C, int H, int W);
+cudaError_t launch_loss_forward(cudaStream_t s, int C, int H, int W, const float* img, const float* gt, float lambda,
+                                float* out3, char* temp);
+cudaError_t launch_loss_backward(cudaStream_t s, int C, int H, int W, const float* img, const float* gt, float lambda,
+                                 const float* dL_dloss, const char* temp, float* dL_dimg);
+cudaError_t launch_activate_forward(cudaStream_t s, int P, const float* raw_scale, const float* raw_rot,
+                                    const float* raw_opacity, float* scale, float* rot, float* opacity);
+cudaError_t launch_activate_backward(cudaStream_t s, int P, const float* raw_scale, const float* raw_rot,
+                                     const float* raw_opacity, float* g_scale, float* g_rot, float* g_opacity);
+cudaError_t launch_adam(cudaStream_t s, const gsr_adam_segment* segs, int n_segs, int64_t step, float beta1,
+                        float beta2, float eps);
+
 }  // namespace gsr

@@ -1,0 +1,115 @@
+"""Pins oracle/trainstep_oracle.py against tests/golden/trainstep.npz -- outputs of the REFERENCE's own
+utils/loss_utils.py (l1_loss, ssim, autograd), torch's activation callables that gaussian_model.py:33-41 installs,
+and torch.optim.Adam over the reference's six parameter groups (tests/golden/make_trainstep_golden.py).
+This oracle is therefore parity-PINNED (the rasterizer's oracle is not: its source is outside the tree)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import trainstep_oracle as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "trainstep.npz"))
+
+
+def test_window_matches_reference_create_window(gold):
+    w = T.gaussian_window()
+    assert w.dtype == np.float32 and w.shape == (11,)
+    assert abs(float(w.sum()) - 1.0) < 1e-6 and np.all(w == w[::-1]) and w.argmax() == 5
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_loss_forward_against_reference(gold, case):
+    img, gt = gold[f"loss_{case}_img"], gold[f"loss_{case}_gt"]
+    lam = float(gold["loss_lambda"])
+    ref = gold[f"loss_{case}_out"]
+    l1, ss, loss = T.loss_forward(img, gt, lam)
+    # the reference computes in float32 (conv2d accumulation order unknown): 2e-6 absolute on O(0.1..1) scalars
+    assert abs(l1 - ref[0]) < 2e-6 and abs(ss - ref[1]) < 2e-6 and abs(loss - ref[2]) < 2e-6, (l1, ss, loss, ref)
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d"])
+def test_loss_backward_against_reference_autograd(gold, case):
+    img, gt = gold[f"loss_{case}_img"], gold[f"loss_{case}_gt"]
+    g = T.loss_backward(img, gt, float(gold["loss_lambda"]))
+    ref = gold[f"loss_{case}_grad"].astype(np.float64)
+    # exactly-equal pixels: |x - y| has subgradient sign(0) = 0 in torch
+    assert np.abs(g - ref).max() <= 2e-5 * np.abs(ref).max(), np.abs(g - ref).max() / np.abs(ref).max()
+
+
+def test_loss_backward_is_the_gradient_of_forward(gold):
+    """finite differences of the oracle's own forward, in float64"""
+    img, gt = gold["loss_c_img"].astype(np.float64), gold["loss_c_gt"].astype(np.float64)
+    g = T.loss_backward(img, gt, 0.35)
+    rng = np.random.default_rng(3)
+    for _ in range(12):
+        c, y, x = rng.integers(0, 3), rng.integers(0, 7), rng.integers(0, 9)
+        if img[c, y, x] == gt[c, y, x]:
+            continue
+        h = 1e-6
+        a, b = img.copy(), img.copy()
+        a[c, y, x] += h
+        b[c, y, x] -= h
+        fd = (T.loss_forward(a, gt, 0.35)[2] - T.loss_forward(b, gt, 0.35)[2]) / (2 * h)
+        assert abs(fd - g[c, y, x]) < 1e-6 * max(1.0, abs(fd)) + 1e-9, (fd, g[c, y, x])
+
+
+def test_activations_against_torch(gold):
+    s, q, o = T.activate_forward(gold["act_raw_s"], gold["act_raw_q"], gold["act_raw_o"])
+    np.testing.assert_allclose(s, gold["act_s"], rtol=3e-7)
+    np.testing.assert_allclose(q, gold["act_q"], rtol=3e-7, atol=1e-9)
+    np.testing.assert_allclose(o, gold["act_o"], rtol=3e-7)
+    assert np.all(q[3] == 0.0)      # zero quaternion stays zero (norm clamped at eps)
+
+
+def test_activation_backward_against_torch_autograd(gold):
+    ds, dq, do = T.activate_backward(gold["act_raw_s"], gold["act_raw_q"], gold["act_raw_o"], gold["act_gs"],
+                                     gold["act_gq"], gold["act_go"])
+    np.testing.assert_allclose(ds, gold["act_d_raw_s"], rtol=1e-6)
+    # the reference forms (1 - y) in fp32, which cancels for y -> 1 (|raw| up to ~8): relative 1e-4 there
+    np.testing.assert_allclose(do, gold["act_d_raw_o"], rtol=1e-4, atol=1e-9)
+    ref = gold["act_d_raw_q"].astype(np.float64)
+    ok = np.ones(len(ref), bool)
+    ok[3] = False                   # norm == 0 < eps: gradient is g / eps, huge; compared relatively below
+    np.testing.assert_allclose(dq[ok], ref[ok], rtol=1e-4, atol=2e-6 * np.abs(ref[ok]).max())
+    np.testing.assert_allclose(dq[3], ref[3], rtol=1e-6)
+
+
+GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+
+
+def test_adam_against_torch_optim(gold):
+    steps = int(gold["adam_steps"])
+    for k in GROUPS:
+        p, lr = gold[f"adam_p0_{k}"], float(gold[f"adam_lr_{k}"])
+        m, v = np.zeros_like(p), np.zeros_like(p)
+        for t in range(steps):
+            p, m, v = T.adam_step(p, gold[f"adam_g{t}_{k}"], m, v, t + 1, lr)
+            # fp32 rounding order only (lerp as fma or not; gradients jump decades between steps, so m cancels)
+            mr, vr = gold[f"adam_m{t + 1}_{k}"], gold[f"adam_v{t + 1}_{k}"]
+            np.testing.assert_allclose(m, mr, rtol=2e-6, atol=2e-7 * np.abs(mr).max())
+            np.testing.assert_allclose(v, vr, rtol=2e-6, atol=2e-7 * np.abs(vr).max())
+            # parameters are O(1) and move by ~lr per step: compare the position to 1 ulp-ish of fp32
+            np.testing.assert_allclose(p, gold[f"adam_p{t + 1}_{k}"], rtol=0, atol=3e-7)
+
+
+def test_adam_per_element_lr_equals_two_groups(gold):
+    """The fused kernel keeps f_dc and f_rest in ONE (P,M,3) tensor with a column-dependent learning rate; in the
+    oracle that is adam_step with an lr array, and it must equal the reference's two separate groups."""
+    M = int(gold["adam_M"])
+    dc, rest = gold["adam_p0_f_dc"], gold["adam_p0_f_rest"]
+    sh = np.concatenate([dc, rest], axis=1)
+    lr = np.empty_like(sh)
+    lr[:, :1], lr[:, 1:] = float(gold["adam_lr_f_dc"]), float(gold["adam_lr_f_rest"])
+    assert sh.shape[1] == M
+    m, v = np.zeros_like(sh), np.zeros_like(sh)
+    for t in range(int(gold["adam_steps"])):
+        g = np.concatenate([gold[f"adam_g{t}_f_dc"], gold[f"adam_g{t}_f_rest"]], axis=1)
+        sh, m, v = T.adam_step(sh, g, m, v, t + 1, lr)
+    np.testing.assert_allclose(sh[:, :1], gold["adam_p5_f_dc"], rtol=0, atol=3e-7)
+    np.testing.assert_allclose(sh[:, 1:], gold["adam_p5_f_rest"], rtol=0, atol=3e-7)
