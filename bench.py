@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -50,6 +51,7 @@ def parse():
     ap.add_argument("--per-view-backward", action="store_true", help="K8+K9 per view (accumulate) instead of one batched launch per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the fused-optimisation-step leg (SURVEY 8f rows 1, 4)")
     ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     return ap.parse_args()
 
@@ -192,6 +194,72 @@ def run_reference(args):
 # -------------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------------
+def bench_train_step(args, torch, _C, mv, S, sc, gauss, settings_list, dev, timed, av, mine, pipe, workspaces):
+    """iterations/s of one optimisation step over this rank's views, fused vs torch structure (see run_ours)."""
+    import torch.nn.functional as F
+    from multiview_inpaint_b200.rasterizer import GaussianRasterizer
+    from multiview_inpaint_b200.trainstep import GaussianParamArena, ViewLoss, fused_train_step
+    P, M, H, W = sc["P"], sc["M"], sc["H"], sc["W"]
+    lrs = dict(xyz=0.00016, f_dc=0.0025, f_rest=0.0025 / 20.0, opacity=0.05, scaling=0.005, rotation=0.001)   # arguments/__init__.py:79-86
+    raw = dict(xyz=gauss["means3D"], f_dc=gauss["shs"][:, :1].contiguous(), f_rest=gauss["shs"][:, 1:].contiguous(),
+               opacity=torch.logit(gauss["opacities"].clamp(1e-4, 1 - 1e-4)).reshape(P, 1), scaling=torch.log(gauss["scales"]),
+               rotation=gauss["rotations"].clone())
+    g = torch.Generator().manual_seed(77)
+    gts = [torch.rand(3, H, W, generator=g).to(dev) for _ in mine]     # synthetic targets (the metric is time, not quality)
+    steps = max(2, min(args.steps, 5))
+
+    # fused
+    pa = GaussianParamArena.from_tensors(raw["xyz"], raw["f_dc"], raw["f_rest"], raw["opacity"], raw["scaling"], raw["rotation"])
+    arena = mv.GradArena(P, M, dev)
+    losses = [ViewLoss(gt, 0.2, weight=1.0 / len(mine)) for gt in gts]
+    caps, slots = [av.capacity(v) for v in mine], [av.slot(v) for v in mine]
+
+    def step_fused():
+        fused_train_step(pa, settings_list, losses, arena, lrs, flags=args.flags, pipeline=pipe, capacities=caps,
+                         async_results=slots, workspaces=workspaces)
+    l0 = _C.kernel_launches()
+    for _ in range(2):
+        step_fused()
+    ms_f = timed(step_fused, steps)
+    launches = (_C.kernel_launches() - l0) // (steps + 2)
+    overflow = bool(av.check(mine))     # the parameters move: a view may outgrow its binning capacity (25 % margin)
+    loss_fused = float(sum(l.out3[2].item() for l in losses) / len(losses))
+    del pa, arena, losses
+
+    # torch structure around the same rasterizer (drop-in autograd Function, one view at a time)
+    leaves = {k: torch.nn.Parameter(v.clone()) for k, v in raw.items()}
+    opt = torch.optim.Adam([{"params": [leaves[k]], "lr": lrs[k], "name": k} for k in leaves], lr=0.0, eps=1e-15)
+    w1 = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], device=dev)
+    w1 = w1 / w1.sum()
+    w2 = torch.outer(w1, w1).expand(3, 1, 11, 11).contiguous()
+    blur = lambda t: F.conv2d(t[None], w2, padding=5, groups=3)[0]
+
+    def step_torch():
+        opt.zero_grad(set_to_none=True)
+        for rs, gt in zip(settings_list, gts):
+            shs = torch.cat((leaves["f_dc"], leaves["f_rest"]), dim=1)
+            means2D = torch.zeros_like(leaves["xyz"], requires_grad=True)
+            x, _radii, _depth = GaussianRasterizer(rs)(means3D=leaves["xyz"], means2D=means2D, opacities=torch.sigmoid(leaves["opacity"]),
+                                                       shs=shs, scales=torch.exp(leaves["scaling"]), rotations=F.normalize(leaves["rotation"]))
+            mx, my = blur(x), blur(gt)
+            vx, vy, cxy = blur(x * x) - mx * mx, blur(gt * gt) - my * my, blur(x * gt) - mx * my
+            ssim = (((2 * mx * my + 1e-4) * (2 * cxy + 9e-4)) / ((mx * mx + my * my + 1e-4) * (vx + vy + 9e-4))).mean()
+            loss = (0.8 * (x - gt).abs().mean() + 0.2 * (1.0 - ssim)) / len(gts)
+            loss.backward()
+        opt.step()
+    for _ in range(2):
+        step_torch()
+    ms_t = timed(step_torch, steps)
+    nv = len(mine)
+    return {"fused": {"iters_per_s": steps / (ms_f / 1000.0), "ms_per_step": ms_f / steps, "views_per_s": nv * steps / (ms_f / 1000.0),
+                      "gpu_launches_per_step": int(launches), "mean_loss_last_step": loss_fused, "capacity_overflow": overflow},
+            "torch_structure": {"iters_per_s": steps / (ms_t / 1000.0), "ms_per_step": ms_t / steps,
+                                "views_per_s": nv * steps / (ms_t / 1000.0),
+                                "note": "torch getters + cat, F.conv2d SSIM, autograd, torch.optim.Adam (six groups) around THIS repo's "
+                                        "rasterizer (drop-in autograd Function), one view at a time, one optimizer.step() per iteration"},
+            "views_per_step": nv, "steps": steps, "speedup": ms_t / ms_f}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -398,6 +466,19 @@ def run_ours(args):
                       "steps": rs_steps, "flags": _C.FLAG_REFERENCE,
                       "note": "reference-STRUCTURE stand-in kernels of this repo (csrc/refstruct.cu), not the reference's binary"}
 
+
+    # ---- the whole optimisation step (SURVEY 8f rows 1 + 4), N = 1: getters -> rasterizer -> L1+SSIM loss -> backward ->
+    #      Adam, fused (GaussianParamArena / ViewLoss / one Adam launch) against the torch structure the reference runs
+    #      around the same rasterizer (torch getters + cat, F.conv2d SSIM, autograd, torch.optim.Adam over six groups;
+    #      gs-simp/train.py:86-128).  Both do `views_per_rank` views and ONE optimizer step per iteration. ----
+    train_step = None
+    if world == 1 and not args.no_train_step:
+        try:
+            train_step = bench_train_step(args, torch, _C, mv, S, sc, gauss, [settings(cams_dev[v]) for v in mine], dev, timed,
+                                          av, mine, pipe, workspaces)
+        except Exception as ex:   # an extra leg: never a reason to lose the bench line
+            train_step = {"failed": repr(ex)}
+
     views_total = n_views * args.steps
     value = views_total / (ms_total / 1000.0)
     e2e_value = views_total / (ms_e2e / 1000.0)
@@ -448,6 +529,8 @@ def run_ours(args):
     }
     if ref_struct is not None:
         line["reference_structure"] = ref_struct
+    if train_step is not None:
+        line["train_step"] = train_step
 
     # ---- cpu_baseline: rank 0, N = 1 only ----
     if world == 1 and not args.no_cpu_baseline:

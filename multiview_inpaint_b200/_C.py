@@ -114,8 +114,29 @@ _lib.gsr_profile_enable.argtypes = [_i]
 _lib.gsr_profile_collect.restype = _i
 _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
+
+class GsrAdamSegment(C.Structure):
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_uint64),
+                ("lr", _f), ("lr_rest", _f), ("row_len", _i), ("row_split", _i)]
+
+
+_lib.gsr_loss_temp_bytes.restype = _sz
+_lib.gsr_loss_temp_bytes.argtypes = [_i, _i, _i]
+_lib.gsr_loss_l1_ssim_forward.restype = _i
+_lib.gsr_loss_l1_ssim_forward.argtypes = [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _sz]
+_lib.gsr_loss_l1_ssim_backward.restype = _i
+_lib.gsr_loss_l1_ssim_backward.argtypes = [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _sz, _vp]
+_lib.gsr_activate_forward.restype = _i
+_lib.gsr_activate_forward.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+_lib.gsr_activate_backward.restype = _i
+_lib.gsr_activate_backward.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+_lib.gsr_adam_step.restype = _i
+_lib.gsr_adam_step.argtypes = [_vp, C.POINTER(GsrAdamSegment), _i, _i64, _f, _f, _f]
+
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
-                    "gsr_accumulate_view_stats", "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
+                    "gsr_accumulate_view_stats", "gsr_loss_temp_bytes", "gsr_loss_l1_ssim_forward",
+                    "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step",
+                    "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches", "gsr_debug_approx_units",
@@ -568,3 +589,110 @@ def inclusive_scan(x: torch.Tensor, gather: torch.Tensor | None = None) -> torch
         _check(_lib.gsr_inclusive_scan_u32(_stream(dev), n, _ptr(x), _ptr(gather), _ptr(out), _ptr(temp), nt),
                "inclusive_scan")
     return out
+
+
+# ---- the training step either side of the rasterizer -------------------------
+def _req_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (no CPU path)")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous float32")
+    return t
+
+
+def loss_temp_bytes(C_: int, H: int, W: int) -> int:
+    return int(_lib.gsr_loss_temp_bytes(int(C_), int(H), int(W)))
+
+
+def loss_l1_ssim_forward(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float, out3: torch.Tensor | None = None,
+                         temp: torch.Tensor | None = None):
+    """-> (out3, temp): out3 = device float32[3] {Ll1, ssim, loss} (utils/loss_utils.py:17-18,33-62 composed as
+    train.py:91-92); temp holds the derivative maps loss_l1_ssim_backward needs."""
+    image, gt = _req_cuda_f32(image, "image"), _req_cuda_f32(gt, "gt")
+    if image.ndim != 3 or image.shape != gt.shape:
+        raise RuntimeError(f"image and gt must both be (C,H,W), got {tuple(image.shape)} and {tuple(gt.shape)}")
+    Cc, H, W = image.shape
+    dev = image.device
+    nb = loss_temp_bytes(Cc, H, W)
+    with torch.cuda.device(dev):
+        if temp is None or temp.numel() < nb:
+            temp = torch.empty(nb, dtype=torch.uint8, device=dev)
+        if out3 is None:
+            out3 = torch.empty(3, dtype=torch.float32, device=dev)
+        _check(_lib.gsr_loss_l1_ssim_forward(_stream(dev), Cc, H, W, image.data_ptr(), gt.data_ptr(), float(lambda_dssim),
+                                             out3.data_ptr(), temp.data_ptr(), temp.numel()), "loss_l1_ssim_forward")
+    return out3, temp
+
+
+def loss_l1_ssim_backward(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float, temp: torch.Tensor,
+                          dL_dloss: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """d loss / d image (C,H,W), scaled by the DEVICE scalar dL_dloss (None = 1)."""
+    image, gt = _req_cuda_f32(image, "image"), _req_cuda_f32(gt, "gt")
+    Cc, H, W = image.shape
+    dev = image.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty_like(image)
+        g = None
+        if dL_dloss is not None:
+            g = _req_cuda_f32(dL_dloss.reshape(-1), "dL_dloss")
+            assert g.numel() == 1
+        _check(_lib.gsr_loss_l1_ssim_backward(_stream(dev), Cc, H, W, image.data_ptr(), gt.data_ptr(), float(lambda_dssim),
+                                              _ptr(g), temp.data_ptr(), temp.numel(), _req_cuda_f32(out, "out").data_ptr()),
+               "loss_l1_ssim_backward")
+    return out
+
+
+def activate_forward(raw_scales, raw_rotations, raw_opacities, scales=None, rotations=None, opacities=None):
+    """exp / normalize / sigmoid of GaussianModel's getters (gaussian_model.py:95-115) in one kernel.
+    Any raw_* may be None.  -> (scales, rotations, opacities)"""
+    ref = next(t for t in (raw_scales, raw_rotations, raw_opacities) if t is not None)
+    dev, P = ref.device, ref.shape[0]
+    outs = []
+    for raw, o, name in ((raw_scales, scales, "scales"), (raw_rotations, rotations, "rotations"), (raw_opacities, opacities, "opacities")):
+        if raw is None:
+            outs.append(None)
+            continue
+        _req_cuda_f32(raw, "raw_" + name)
+        assert raw.shape[0] == P
+        outs.append(_req_cuda_f32(o, name) if o is not None else torch.empty_like(raw))
+    with torch.cuda.device(dev):
+        _check(_lib.gsr_activate_forward(_stream(dev), P, _ptr(raw_scales), _ptr(raw_rotations), _ptr(raw_opacities),
+                                         _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])), "activate_forward")
+    return tuple(outs)
+
+
+def activate_backward(raw_scales, raw_rotations, raw_opacities, g_scales, g_rotations, g_opacities):
+    """In place: g_* = dL/d(activated) -> dL/d(raw)."""
+    ref = next(t for t in (raw_scales, raw_rotations, raw_opacities) if t is not None)
+    dev, P = ref.device, ref.shape[0]
+    for raw, g, name in ((raw_scales, g_scales, "scales"), (raw_rotations, g_rotations, "rotations"), (raw_opacities, g_opacities, "opacities")):
+        if raw is not None:
+            _req_cuda_f32(raw, "raw_" + name), _req_cuda_f32(g, "g_" + name)
+            assert raw.numel() == g.numel() and raw.shape[0] == P
+    with torch.cuda.device(dev):
+        _check(_lib.gsr_activate_backward(_stream(dev), P, _ptr(raw_scales), _ptr(raw_rotations), _ptr(raw_opacities),
+                                          _ptr(g_scales if raw_scales is not None else None),
+                                          _ptr(g_rotations if raw_rotations is not None else None),
+                                          _ptr(g_opacities if raw_opacities is not None else None)), "activate_backward")
+
+
+def adam_step(segments, step: int, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-15):
+    """One launch of Adam over `segments`: dicts with param, grad, exp_avg, exp_avg_sq (same numel, contiguous CUDA
+    float32), lr, and optionally row_len / row_split / lr_rest (see gsr_adam_step).  Defaults are those of
+    gaussian_model.py:165 (eps=1e-15) and torch.optim.Adam (betas)."""
+    segs = (GsrAdamSegment * max(len(segments), 1))()
+    dev = None
+    keep = []
+    for k, sg in enumerate(segments):
+        p, g, m, v = (_req_cuda_f32(sg[n], n) for n in ("param", "grad", "exp_avg", "exp_avg_sq"))
+        assert p.numel() == g.numel() == m.numel() == v.numel(), "segment tensors differ in size"
+        dev = p.device if dev is None else dev
+        keep.append((p, g, m, v))
+        segs[k] = GsrAdamSegment(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(sg["lr"]),
+                                 float(sg.get("lr_rest", sg["lr"])), int(sg.get("row_len", 0)), int(sg.get("row_split", 0)))
+    if dev is None:
+        return
+    with torch.cuda.device(dev):
+        _check(_lib.gsr_adam_step(_stream(dev), segs, len(segments), int(step), float(beta1), float(beta2), float(eps)),
+               "adam_step")

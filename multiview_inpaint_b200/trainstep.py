@@ -1,0 +1,188 @@
+"""The training step around the rasterizer, fused -- opt-in; `render()` and the
+drop-in `diff_gaussian_rasterization` API stay as they are.
+
+What every training script of the reference does per iteration (gs-simp/train.py:86-128, same skeleton in
+sds_train.py and inpaint_rec.py) around the rasterizer call:
+
+    getters      get_scaling = exp(_scaling), get_rotation = normalize(_rotation), get_opacity = sigmoid(_opacity),
+                 get_features = cat((_features_dc, _features_rest), dim=1)       scene/gaussian_model.py:95-115
+    loss         (1 - l) * l1_loss(image, gt) + l * (1 - ssim(image, gt))        train.py:91-92, utils/loss_utils.py
+    backward     autograd through all of the above                               train.py:93
+    optimizer    Adam over six parameter groups, eps 1e-15                       train.py:127, gaussian_model.py:154-165
+
+Here:
+  * `GaussianParamArena`  raw parameters, Adam moments and activated values in flat allocations laid out exactly
+                          like `multiview.GradArena`; `_features_dc` / `_features_rest` are views of ONE (P,M,3)
+                          tensor, so `get_features` is that tensor (no cat, no split in backward);
+  * `activate()`          one kernel per STEP (the activated values are shared by all views of a multi-view step);
+  * `l1_ssim_loss()`      autograd Function over the two fused kernels of csrc/loss.cu;
+  * `apply_gradients()`   the activations' chain rule in place in the gradient arena + ONE Adam launch for all groups.
+  * `fused_train_step()`  the whole iteration for a batch of views: activate -> per view (K1..K6, loss fwd+bwd,
+                          K7) -> batched K8+K9 (-> all-reduce) -> chain rule -> Adam.
+Everything runs on the CUDA library (include/gsrast_b200.h); there is no torch fallback.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import _C
+from .multiview import GradArena, ViewPipeline, cuda_views_fwd_bwd
+
+#: the six groups of gaussian_model.py:154-161, in arena order; f_dc and f_rest share the (P,M,3) slice
+GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+
+
+def _numel(shp):
+    n = 1
+    for s in shp:
+        n *= s
+    return n
+
+
+class GaussianParamArena:
+    """Raw (pre-activation) Gaussian parameters in ONE flat fp32 allocation
+        [ _xyz (P,3) | _features (P,M,3) | _opacity (P,1) | _scaling (P,3) | _rotation (P,4) ]
+    with every slice starting on a 16-byte boundary -- slice for slice the layout of `GradArena.flat`, so a
+    gradient slice, its parameter slice and its two Adam moment slices have identical offsets.  Attribute names
+    follow GaussianModel (scene/gaussian_model.py:43-57)."""
+
+    def __init__(self, P: int, M: int, device):
+        self.P, self.M = int(P), int(M)
+        self.device = torch.device(device)
+        sizes = [("_xyz", (P, 3)), ("_features", (P, M, 3)), ("_opacity", (P, 1)), ("_scaling", (P, 3)),
+                 ("_rotation", (P, 4))]
+        offs, off = {}, 0
+        for name, shp in sizes:
+            offs[name] = off
+            off += (_numel(shp) + 3) // 4 * 4
+        self._offs, self._shapes, self.n_flat = offs, dict(sizes), off
+        z = lambda: torch.zeros(max(off, 4), dtype=torch.float32, device=self.device)
+        self.param, self.exp_avg, self.exp_avg_sq = z(), z(), z()
+        self.step_count = 0
+        # activated values handed to the rasterizer (what render() gets from the getters)
+        self.scales = torch.empty(P, 3, dtype=torch.float32, device=self.device)
+        self.rotations = torch.empty(P, 4, dtype=torch.float32, device=self.device)
+        self.opacities = torch.empty(P, 1, dtype=torch.float32, device=self.device)
+        for name, shp in sizes:
+            setattr(self, name, self._slice(self.param, name))
+        self._features_dc = self._features[:, :1, :]      # views: gaussian_model.py:142-143 keeps them as two tensors
+        self._features_rest = self._features[:, 1:, :]
+
+    def _slice(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        shp = self._shapes[name]
+        return flat[self._offs[name]:self._offs[name] + _numel(shp)].view(*shp)
+
+    @classmethod
+    def from_tensors(cls, xyz, features_dc, features_rest, opacity, scaling, rotation) -> "GaussianParamArena":
+        """From GaussianModel's six parameter tensors (gaussian_model.py:140-145): (P,3), (P,1,3), (P,M-1,3), (P,1),
+        (P,3), (P,4), all RAW (pre-activation)."""
+        P, M = xyz.shape[0], 1 + features_rest.shape[1]
+        a = cls(P, M, xyz.device)
+        with torch.no_grad():
+            a._xyz.copy_(xyz)
+            a._features[:, :1].copy_(features_dc)
+            if M > 1:
+                a._features[:, 1:].copy_(features_rest)
+            a._opacity.copy_(opacity.reshape(P, 1))
+            a._scaling.copy_(scaling)
+            a._rotation.copy_(rotation)
+        return a
+
+    # the getters of gaussian_model.py:95-115
+    @property
+    def get_xyz(self):
+        return self._xyz
+
+    @property
+    def get_features(self):
+        return self._features
+
+    def activate(self) -> dict:
+        """exp / normalize / sigmoid in one kernel -> the dict the multi-view entry points take."""
+        _C.activate_forward(self._scaling, self._rotation, self._opacity, self.scales, self.rotations, self.opacities)
+        return {"means3D": self._xyz, "shs": self._features, "opacities": self.opacities, "scales": self.scales,
+                "rotations": self.rotations}
+
+    def moments(self, name: str):
+        return self._slice(self.exp_avg, name), self._slice(self.exp_avg_sq, name)
+
+    def apply_gradients(self, arena: GradArena, lrs: dict, beta1: float = 0.9, beta2: float = 0.999,
+                        eps: float = 1e-15):
+        """`arena` holds dL/d(means3D, shs, opacities, scales, rotations) -- gradients with respect to the ACTIVATED
+        values, as the rasterizer's backward produces them.  Runs the activations' chain rule in place in the arena
+        (after which it holds what autograd would put in `.grad` of the six raw parameters), then one Adam launch.
+        `lrs`: learning rate per group of GROUPS (the xyz one is scheduled by the caller, gaussian_model.py:167-173)."""
+        assert arena.P == self.P and arena.M == self.M
+        g = arena.views
+        _C.activate_backward(self._scaling, self._rotation, self._opacity, g["dL_dscales"], g["dL_drotations"],
+                             g["dL_dopacity"])
+        self.step_count += 1
+        pairs = (("_xyz", "dL_dmeans3D", dict(lr=lrs["xyz"])),
+                 ("_features", "dL_dsh", dict(lr=lrs["f_dc"], lr_rest=lrs["f_rest"], row_len=3 * self.M, row_split=3)),
+                 ("_opacity", "dL_dopacity", dict(lr=lrs["opacity"])),
+                 ("_scaling", "dL_dscales", dict(lr=lrs["scaling"])),
+                 ("_rotation", "dL_drotations", dict(lr=lrs["rotation"])))
+        segs = []
+        for pname, gname, kw in pairs:
+            m, v = self.moments(pname)
+            segs.append(dict(param=getattr(self, pname), grad=g[gname], exp_avg=m, exp_avg_sq=v, **kw))
+        _C.adam_step(segs, self.step_count, beta1, beta2, eps)
+
+
+class _L1SSIMLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, gt, lambda_dssim):
+        image_c, gt_c = image.contiguous(), gt.contiguous()
+        out3, temp = _C.loss_l1_ssim_forward(image_c, gt_c, lambda_dssim)
+        ctx.save_for_backward(image_c, gt_c, temp)
+        ctx.lambda_dssim = lambda_dssim
+        l1, ss, loss = (t.clone() for t in out3.unbind(0))
+        ctx.mark_non_differentiable(l1, ss)
+        return loss, l1, ss
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_l1, _g_ss):
+        image, gt, temp = ctx.saved_tensors
+        g = _C.loss_l1_ssim_backward(image, gt, ctx.lambda_dssim, temp, dL_dloss=g_loss.contiguous())
+        return g, None, None
+
+
+def l1_ssim_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float = 0.2):
+    """-> (loss, Ll1, ssim), 0-dim CUDA tensors; `loss` = (1 - l) * l1_loss(image, gt) + l * (1 - ssim(image, gt))
+    (train.py:91-92) and is differentiable with respect to `image`; Ll1 is what training_report logs (train.py:107)."""
+    return _L1SSIMLoss.apply(image, gt, float(lambda_dssim))
+
+
+class ViewLoss:
+    """dL_dcolor callback of the multi-view entry points for one view: fused loss forward + backward against `gt`,
+    with preallocated temp / output buffers (no allocator traffic in the loop).  After the step, `out3` holds
+    {Ll1, ssim, loss} of the view on the device.  `weight`: dL/dloss seed (1/len(views) averages the batch)."""
+
+    def __init__(self, gt: torch.Tensor, lambda_dssim: float = 0.2, weight: float = 1.0):
+        self.gt = gt.contiguous()
+        self.lambda_dssim = float(lambda_dssim)
+        dev = gt.device
+        self.temp = torch.empty(_C.loss_temp_bytes(*gt.shape), dtype=torch.uint8, device=dev)
+        self.out3 = torch.zeros(3, dtype=torch.float32, device=dev)
+        self.dL = torch.empty_like(self.gt)
+        self.seed = None if weight == 1.0 else torch.full((1,), float(weight), dtype=torch.float32, device=dev)
+
+    def __call__(self, color: torch.Tensor) -> torch.Tensor:
+        _C.loss_l1_ssim_forward(color, self.gt, self.lambda_dssim, out3=self.out3, temp=self.temp)
+        return _C.loss_l1_ssim_backward(color, self.gt, self.lambda_dssim, self.temp, dL_dloss=self.seed, out=self.dL)
+
+
+def fused_train_step(params: GaussianParamArena, settings_list: Sequence, losses: Sequence[ViewLoss], arena: GradArena,
+                     lrs: dict, flags: int = 0, pipeline: ViewPipeline | None = None, all_reduce: bool = False,
+                     capacities=None, async_results=None, workspaces=None, chunks: int = 4):
+    """One optimisation step on this rank's views (train.py:86-128 for a batch of views; with `all_reduce` the
+    gradient arena is summed over ranks first).  Returns the per-view ViewState list; the densification
+    statistics of the step are in `arena` (grad_norm_accum / visible_count / max_radii)."""
+    g = params.activate()
+    states = cuda_views_fwd_bwd(g, settings_list, losses, arena, flags=flags, capacities=capacities,
+                                async_results=async_results, pipeline=pipeline, all_reduce=all_reduce, chunks=chunks,
+                                workspaces=workspaces)
+    params.apply_gradients(arena, lrs)
+    return states

@@ -113,3 +113,43 @@ def test_adam_per_element_lr_equals_two_groups(gold):
         sh, m, v = T.adam_step(sh, g, m, v, t + 1, lr)
     np.testing.assert_allclose(sh[:, :1], gold["adam_p5_f_dc"], rtol=0, atol=3e-7)
     np.testing.assert_allclose(sh[:, 1:], gold["adam_p5_f_rest"], rtol=0, atol=3e-7)
+
+
+@pytest.mark.parametrize("P,M", [(1, 1), (61, 4), (1001, 16), (7, 9)])
+def test_param_arena_layout_equals_grad_arena(P, M):
+    """Parameter, moment and gradient slices must sit at identical offsets (one Adam launch walks them together),
+    every slice 16-byte aligned, and _features_dc / _features_rest must be views of the one (P,M,3) SH tensor."""
+    import torch
+    from multiview_inpaint_b200.multiview import GradArena
+    from multiview_inpaint_b200.trainstep import GaussianParamArena
+    pa, ga = GaussianParamArena(P, M, "cpu"), GradArena(P, M, "cpu")
+    pairs = {"_xyz": "dL_dmeans3D", "_features": "dL_dsh", "_opacity": "dL_dopacity", "_scaling": "dL_dscales",
+             "_rotation": "dL_drotations"}
+    assert pa.n_flat == ga.flat.numel()
+    for pn, gn in pairs.items():
+        p, g = getattr(pa, pn), ga.views[gn]
+        assert p.shape == g.shape
+        assert (p.data_ptr() - pa.param.data_ptr()) == (g.data_ptr() - ga.flat.data_ptr())
+        assert (p.data_ptr() - pa.param.data_ptr()) % 16 == 0
+        m, v = pa.moments(pn)
+        assert m.shape == p.shape and (m.data_ptr() - pa.exp_avg.data_ptr()) == (p.data_ptr() - pa.param.data_ptr())
+    assert pa._features_dc.shape == (P, 1, 3) and pa._features_rest.shape == (P, M - 1, 3)
+    pa._features_dc.fill_(2.0)
+    assert torch.all(pa.get_features[:, 0] == 2.0)
+    x = torch.arange(P * 3, dtype=torch.float32).view(P, 3)
+    pb = GaussianParamArena.from_tensors(x, torch.ones(P, 1, 3), torch.zeros(P, M - 1, 3), torch.zeros(P, 1), x, torch.ones(P, 4))
+    assert torch.equal(pb._xyz, x) and torch.equal(pb._scaling, x) and torch.all(pb._features[:, 0] == 1)
+
+
+def test_trainstep_entry_points_refuse_cpu_tensors():
+    """no CPU / torch fallback: the product path fails loudly without a CUDA device"""
+    import torch
+    from multiview_inpaint_b200 import _C
+    x = torch.zeros(3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _C.loss_l1_ssim_forward(x, x, 0.2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _C.activate_forward(torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _C.adam_step([dict(param=x, grad=x, exp_avg=x, exp_avg_sq=x, lr=0.1)], 1)
+    assert _C.loss_temp_bytes(3, 1008, 1600) >= 3 * 3 * 1008 * 1600 * 4
