@@ -233,13 +233,13 @@ typedef struct {
   float* exp_avg;
   float* exp_avg_sq;
   uint64_t n;        /* floats in the segment */
-  float lr;
-  float lr_rest;
+  double lr;         /* doubles, like the python floats torch keeps them as: 1 - beta2 and lr / (1 - beta1^t) are  */
+  double lr_rest;    /* formed in double and rounded to fp32 once (a float 0.999 would put 1.3e-5 into 1 - beta2) */
   int row_len;       /* 0 = flat segment */
   int row_split;
 } gsr_adam_segment;
-int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, float beta1,
-                  float beta2, float eps);
+int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, double beta1,
+                  double beta2, double eps);
 
 /* ---- neighbour distances --------------------------------------------------------
  * Replaces `simple_knn._C.distCUDA2(points) -> Tensor[P]` (third-party simple-knn extension, source not in the

@@ -117,7 +117,7 @@ _lib.gsr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(_i64)]
 
 class GsrAdamSegment(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_uint64),
-                ("lr", _f), ("lr_rest", _f), ("row_len", _i), ("row_split", _i)]
+                ("lr", C.c_double), ("lr_rest", C.c_double), ("row_len", _i), ("row_split", _i)]
 
 
 _lib.gsr_loss_temp_bytes.restype = _sz
@@ -131,7 +131,7 @@ _lib.gsr_activate_forward.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.gsr_activate_backward.restype = _i
 _lib.gsr_activate_backward.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.gsr_adam_step.restype = _i
-_lib.gsr_adam_step.argtypes = [_vp, C.POINTER(GsrAdamSegment), _i, _i64, _f, _f, _f]
+_lib.gsr_adam_step.argtypes = [_vp, C.POINTER(GsrAdamSegment), _i, _i64, C.c_double, C.c_double, C.c_double]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
                     "gsr_accumulate_view_stats", "gsr_loss_temp_bytes", "gsr_loss_l1_ssim_forward",

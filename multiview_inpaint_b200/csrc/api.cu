@@ -255,10 +255,10 @@ int gsr_activate_backward(void* stream, int P, const float* raw_scales, const fl
   return 0;
 }
 
-int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, float beta1,
-                  float beta2, float eps) {
-  if (n_segs < 0 || n_segs > 8 || (n_segs > 0 && !segs_host) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
-      !(beta2 >= 0.f && beta2 < 1.f))
+int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, double beta1,
+                  double beta2, double eps) {
+  if (n_segs < 0 || n_segs > 8 || (n_segs > 0 && !segs_host) || step < 1 || !(beta1 >= 0.0 && beta1 < 1.0) ||
+      !(beta2 >= 0.0 && beta2 < 1.0))
     return fail(GSR_E_INVALID, "gsr_adam_step: bad argument (1..8 segments, step >= 1, betas in [0,1))");
   for (int k = 0; k < n_segs; k++) {
     const gsr_adam_segment& g = segs_host[k];

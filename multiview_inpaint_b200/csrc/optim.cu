@@ -193,19 +193,19 @@ cudaError_t launch_activate_backward(cudaStream_t s, int P, const float* raw_sca
   return cudaGetLastError();
 }
 
-cudaError_t launch_adam(cudaStream_t s, const gsr_adam_segment* segs, int n_segs, int64_t step, float beta1,
-                        float beta2, float eps) {
+cudaError_t launch_adam(cudaStream_t s, const gsr_adam_segment* segs, int n_segs, int64_t step, double beta1,
+                        double beta2, double eps) {
   AdamArgs A;
   A.n_segs = 0;
-  A.beta1 = beta1;
-  A.beta2 = beta2;
   // torch keeps these as python doubles and rounds them to the tensors' dtype when the op is applied
-  A.one_minus_beta1 = (float)(1.0 - (double)beta1);
-  A.one_minus_beta2 = (float)(1.0 - (double)beta2);
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  A.beta1 = (float)beta1;
+  A.beta2 = (float)beta2;
+  A.one_minus_beta1 = (float)(1.0 - beta1);
+  A.one_minus_beta2 = (float)(1.0 - beta2);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   A.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  A.eps = eps;
+  A.eps = (float)eps;
   unsigned long long blocks = 0;
   for (int k = 0; k < n_segs; k++) {
     const gsr_adam_segment& in = segs[k];
@@ -216,8 +216,8 @@ cudaError_t launch_adam(cudaStream_t s, const gsr_adam_segment* segs, int n_segs
     S.first_block = (unsigned int)blocks;
     S.row_len = in.row_len;
     S.row_split = in.row_split;
-    S.step_size = (float)(-(double)in.lr / bc1);
-    S.step_size_rest = (float)(-(double)in.lr_rest / bc1);
+    S.step_size = (float)(-in.lr / bc1);
+    S.step_size_rest = (float)(-in.lr_rest / bc1);
     S.vec = aligned16(in.param) && aligned16(in.grad) && aligned16(in.exp_avg) && aligned16(in.exp_avg_sq) &&
             (in.row_len == 0 || in.row_len >= 4);
     blocks += (in.n + ADAM_PER_BLOCK - 1) / ADAM_PER_BLOCK;
