@@ -241,6 +241,15 @@ typedef struct {
 int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, double beta1,
                   double beta2, double eps);
 
+/* ---- image output of the inference loops ---------------------------------------------
+ * The tensor half of `torchvision.utils.save_image(t, path)` as called after render() in gs-simp/render.py:36-39,
+ * render_depth.py:39, gen_seq.py:45-55, vis_render.py:48-51: image (C,H,W) float32 with C = 3, or C = 1 (repeated to
+ * three channels, as make_grid does) -> rgb8 (H,W,3) uint8 with u8 = trunc(clamp(x * 255 + 0.5, 0, 255)) (two fp32
+ * roundings, as torch's mul(255).add_(0.5)).  `affine` (optional DEVICE float[2] = {lo, inv_range}) first maps
+ * x -> (x - lo) * inv_range: scene/helpers.py:159-162 normalize_0_to_1 without a host round trip for min / max.
+ * Bit-exact integer output.  The 3-bytes-per-pixel result is what an asynchronous PNG writer copies to the host. */
+int gsr_quantize_rgb8(void* stream, int C, int H, int W, const float* image, const float* affine, uint8_t* rgb8);
+
 /* ---- neighbour distances --------------------------------------------------------
  * Replaces `simple_knn._C.distCUDA2(points) -> Tensor[P]` (third-party simple-knn extension, source not in the
  * reference tree), imported at gs-simp/scene/gaussian_model.py:20 and called at :134, :546, :623:

@@ -130,12 +130,14 @@ _lib.gsr_activate_forward.restype = _i
 _lib.gsr_activate_forward.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
 _lib.gsr_activate_backward.restype = _i
 _lib.gsr_activate_backward.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]
+_lib.gsr_quantize_rgb8.restype = _i
+_lib.gsr_quantize_rgb8.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
 _lib.gsr_adam_step.restype = _i
 _lib.gsr_adam_step.argtypes = [_vp, C.POINTER(GsrAdamSegment), _i, _i64, C.c_double, C.c_double, C.c_double]
 
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
                     "gsr_accumulate_view_stats", "gsr_loss_temp_bytes", "gsr_loss_l1_ssim_forward",
-                    "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step",
+                    "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step", "gsr_quantize_rgb8",
                     "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
@@ -696,3 +698,22 @@ def adam_step(segments, step: int, beta1: float = 0.9, beta2: float = 0.999, eps
     with torch.cuda.device(dev):
         _check(_lib.gsr_adam_step(_stream(dev), segs, len(segments), int(step), float(beta1), float(beta2), float(eps)),
                "adam_step")
+
+
+def quantize_rgb8(image: torch.Tensor, out: torch.Tensor | None = None, affine: torch.Tensor | None = None) -> torch.Tensor:
+    """(C,H,W) float32, C in {1,3} -> (H,W,3) uint8 exactly as torchvision.utils.save_image quantises
+    (gsr_quantize_rgb8); `affine` = device float[2] {lo, inv_range} applies (x - lo) * inv_range first."""
+    image = _req_cuda_f32(image, "image")
+    if image.ndim != 3 or image.shape[0] not in (1, 3):
+        raise RuntimeError(f"image must be (1|3,H,W), got {tuple(image.shape)}")
+    Cc, H, W = image.shape
+    dev = image.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(H, W, 3, dtype=torch.uint8, device=dev)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == H * W * 3
+        if affine is not None:
+            affine = _req_cuda_f32(affine, "affine")
+            assert affine.numel() == 2
+        _check(_lib.gsr_quantize_rgb8(_stream(dev), Cc, H, W, image.data_ptr(), _ptr(affine), out.data_ptr()), "quantize_rgb8")
+    return out

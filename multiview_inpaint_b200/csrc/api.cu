@@ -271,6 +271,14 @@ int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, i
   return 0;
 }
 
+int gsr_quantize_rgb8(void* stream, int C, int H, int W, const float* image, const float* affine, uint8_t* rgb8) {
+  if ((C != 1 && C != 3) || H < 0 || W < 0) return fail(GSR_E_INVALID, "gsr_quantize_rgb8: C must be 1 or 3");
+  if ((size_t)H * (size_t)W == 0) return 0;
+  if (!image || !rgb8) return fail(GSR_E_INVALID, "gsr_quantize_rgb8: null argument");
+  GSR_CUDA(launch_quantize_rgb8(reinterpret_cast<cudaStream_t>(stream), C, H, W, image, affine, rgb8), "quantize_rgb8");
+  return 0;
+}
+
 size_t gsr_knn_temp_bytes(int P) { return knn_temp_bytes(P); }
 int gsr_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, char* temp, size_t temp_bytes) {
   if (P < 0) return fail(GSR_E_INVALID, "gsr_knn3_mean_dist2: P < 0");

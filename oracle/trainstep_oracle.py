@@ -136,3 +136,21 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr, beta1: float = 0.
     denom = (np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)).astype(f)
     p = (p - step_size.astype(f) * (m / denom)).astype(f)                 # addcdiv_(exp_avg, denom, value=-step_size)
     return p, m, v
+
+
+# ---------------------------------------------------------------------------------------------- image output
+def save_image_u8(image, affine=None) -> np.ndarray:
+    """The tensor half of torchvision.utils.save_image for one image, as the reference calls it after render()
+    (gs-simp/render.py:36-39, render_depth.py:39, gen_seq.py:45-55): make_grid repeats a 1-channel image to 3
+    channels; then `grid.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(uint8)` -- fp32 multiply, fp32 add,
+    clamp, truncation.  torchvision is an unpinned third-party dependency of the reference (not importable here);
+    this restates its published algorithm.  `affine` = (lo, inv_range): normalize_0_to_1 of scene/helpers.py:159-162
+    applied first, in fp32.  (C,H,W) float -> (H,W,3) uint8.  NaN -> 0."""
+    x = np.asarray(image, dtype=np.float32)
+    if affine is not None:
+        x = ((x - np.float32(affine[0])).astype(np.float32) * np.float32(affine[1])).astype(np.float32)
+    if x.shape[0] == 1:
+        x = np.repeat(x, 3, axis=0)
+    v = ((x * np.float32(255.0)).astype(np.float32) + np.float32(0.5)).astype(np.float32)
+    v = np.where(np.isnan(v), np.float32(0), v)
+    return np.clip(v, 0, 255).astype(np.uint8).transpose(1, 2, 0).copy()

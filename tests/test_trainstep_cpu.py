@@ -153,3 +153,29 @@ def test_trainstep_entry_points_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="CUDA"):
         _C.adam_step([dict(param=x, grad=x, exp_avg=x, exp_avg_sq=x, lr=0.1)], 1)
     assert _C.loss_temp_bytes(3, 1008, 1600) >= 3 * 3 * 1008 * 1600 * 4
+
+
+def test_png_encoder_round_trips_through_pil(tmp_path):
+    """The fallback PNG encoder of the async writer (used when PIL is absent) must decode to the same pixels."""
+    PIL = pytest.importorskip("PIL.Image")
+    from multiview_inpaint_b200.imagewriter import encode_png_rgb8
+    rng = np.random.default_rng(0)
+    for shape in ((1, 1, 3), (7, 13, 3), (64, 48, 3)):
+        rgb = rng.integers(0, 256, shape, dtype=np.uint8)
+        p = tmp_path / f"a{shape[0]}.png"
+        p.write_bytes(encode_png_rgb8(rgb))
+        assert np.array_equal(np.asarray(PIL.open(p).convert("RGB")), rgb)
+
+
+def test_save_image_quantisation_oracle_matches_torch_expression():
+    """oracle save_image_u8 == the torch expression torchvision.utils.save_image applies (mul(255).add_(0.5)
+    .clamp_(0, 255).to(uint8)), evaluated with torch on the CPU, including values outside [0,1] and ties."""
+    import torch
+    torch.manual_seed(1)
+    x = torch.rand(3, 33, 47) * 1.4 - 0.2
+    x[0, 0, :6] = torch.tensor([0.0, 1.0, 0.5 / 255, 1.5 / 255, 254.5 / 255, 2.0])
+    ref = x.clone().mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8).numpy()
+    assert np.array_equal(T.save_image_u8(x.numpy()), ref)
+    g = torch.rand(1, 5, 9)
+    ref1 = g.expand(3, -1, -1).clone().mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8).numpy()
+    assert np.array_equal(T.save_image_u8(g.numpy()), ref1)
