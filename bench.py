@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")
     ap.add_argument("--no-train-step", action="store_true", help="skip the fused-optimisation-step leg (SURVEY 8f rows 1, 4)")
+    ap.add_argument("--files", type=int, default=0, help="infer mode: also time views/s all the way to PNG files with N writer threads "
+                    "(AsyncImageWriter) against the reference's blocking save_image structure")
     ap.add_argument("--cpu-tile-step", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     return ap.parse_args()
 
@@ -709,6 +711,59 @@ def run_infer(args):
                               "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
         "stages": {k: {"ms_per_launch": round(per_launch[k], 4), "alg_bytes_per_view": alg.get(k)} for k in per_launch},
     }
+    to_disk = None
+    if args.files > 0 and world == 1:
+        # render.py:32-39 all the way to PNG files: batched render + AsyncImageWriter (GPU quantisation, 3 B/pixel D2H,
+        # encode on worker threads) against the structure of the reference (per view: blocking float D2H, 8-bit
+        # conversion on the CPU, PIL encode on the calling thread -- what torchvision.utils.save_image does).
+        import shutil
+        import tempfile
+        import numpy as np
+        from multiview_inpaint_b200.imagewriter import AsyncImageWriter
+        try:
+            from PIL import Image
+        except Exception:
+            Image = None
+        tmp = tempfile.mkdtemp(prefix="gsr_png_")
+        try:
+            writer = AsyncImageWriter(dev, slots=2 * len(mine), workers=args.files, use_pil=True)   # same encoder as the sync leg
+
+            def step_async():
+                mv.cuda_views_render(gauss, [settings(cams_dev[v]) for v in mine], flags=args.flags,
+                                     capacities=[av.capacity(v) for v in mine], async_results=[av.slot(v) for v in mine],
+                                     pipeline=pipe, workspaces=workspaces,
+                                     sink=lambda k, color, depth, radii: writer.submit_png(os.path.join(tmp, f"a{k:05d}.png"), color))
+            step_async()
+            writer.flush()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_async()
+            writer.flush()
+            t_async = time.perf_counter() - t0
+            writer.close()
+
+            def step_sync():
+                for k, v in enumerate(mine):
+                    r = mv.cuda_views_render(gauss, [settings(cams_dev[v])], flags=args.flags)[0]
+                    arr = r.color.mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to("cpu", torch.uint8).numpy()
+                    if Image is not None:
+                        Image.fromarray(arr).save(os.path.join(tmp, f"s{k:05d}.png"))
+                    else:
+                        np.save(os.path.join(tmp, f"s{k:05d}.npy"), arr)
+            step_sync()
+            n_sync = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(n_sync):
+                step_sync()
+            t_sync = time.perf_counter() - t0
+            to_disk = {"async_writer_views_per_s": len(mine) * args.steps / t_async, "writer_threads": args.files,
+                       "sync_structure_views_per_s": len(mine) * n_sync / t_sync, "host_cores": os.cpu_count(),
+                       "encoder": "PIL" if Image is not None else "zlib", "d2h_bytes_per_view": 3 * H * W,
+                       "note": "wall clock, files on the box's /tmp; both legs are bound by PNG encoding on the host"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    if to_disk is not None:
+        line["to_disk"] = to_disk
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

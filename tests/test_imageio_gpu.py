@@ -67,10 +67,12 @@ def test_async_writer_png_and_npy(C, tmp_path, use_pil):
     depth = torch.rand(1, 120, 200, device=DEV) * 15
     side = torch.cuda.Stream()
     with AsyncImageWriter(DEV, slots=3, workers=2, use_pil=use_pil) as w:     # fewer slots than images: back-pressure path
+        side.wait_stream(torch.cuda.current_stream())          # the images were produced on the current stream
         for k, im in enumerate(imgs):
-            with torch.cuda.stream(side if k % 2 else torch.cuda.current_stream()):
-                if k % 2:
-                    side.wait_stream(torch.cuda.default_stream())
+            if k % 2:
+                with torch.cuda.stream(side):
+                    w.submit_png(str(tmp_path / f"{k:05d}.png"), im)
+            else:
                 w.submit_png(str(tmp_path / f"{k:05d}.png"), im)
         w.submit_npy(str(tmp_path / "depth.npy"), depth)
         w.flush()
