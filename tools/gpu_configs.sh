@@ -2,12 +2,12 @@
 # BASELINE.json configs 2-5 on one B200 (run under gpurun): one bench line each into gpurun_out/configs.jsonl
 mkdir -p gpurun_out
 : > gpurun_out/configs.jsonl
-B="--no-cpu-baseline --no-reference-structure --steps 5 --warmup 3"
+B="--no-cpu-baseline --no-reference-structure --no-train-step --steps 5 --warmup 3"
 timeout 300 python bench.py --workload mip360 --views-per-rank 4 $B >> gpurun_out/configs.jsonl 2> gpurun_out/cfg_mip360.err
 timeout 300 python bench.py --workload svd_orbit --views-per-rank 25 --orbit-deg 30 $B >> gpurun_out/configs.jsonl 2> gpurun_out/cfg_svd.err
 timeout 400 python bench.py --workload inference --mode infer --views-per-rank 8 --orbit-deg 30 $B >> gpurun_out/configs.jsonl 2> gpurun_out/cfg_infer.err
 timeout 300 python bench.py --workload headline --mode infer --views-per-rank 8 $B >> gpurun_out/configs.jsonl 2> gpurun_out/cfg_infer_headline.err
-timeout 600 python bench.py --workload stress --views-per-rank 2 --steps 3 --warmup 3 --no-cpu-baseline --no-reference-structure >> gpurun_out/configs.jsonl 2> gpurun_out/cfg_stress.err
+timeout 600 python bench.py --workload stress --views-per-rank 2 --steps 3 --warmup 3 --no-cpu-baseline --no-reference-structure --no-train-step >> gpurun_out/configs.jsonl 2> gpurun_out/cfg_stress.err
 wc -l gpurun_out/configs.jsonl
 python - <<'PY'
 import json
