@@ -34,7 +34,8 @@ extern "C" {
 #define GSR_E_INVALID     (-1) /* bad argument (shape/alignment/null)                            */
 #define GSR_E_PREFILTERED (-2) /* `prefiltered` set but a point was culled (the reference traps) */
 #define GSR_E_ALLOC       (-3) /* a buffer-grower callback returned NULL                         */
-#define GSR_E_OVERFLOW    (-4) /* num_rendered does not fit the 30-bit sort prefix / uint32      */
+#define GSR_E_OVERFLOW    (-4) /* num_rendered does not fit uint32 positions (GSR_MAX_INSTANCES)  */
+#define GSR_MAX_INSTANCES 0xFFFF0000ll /* (tile, Gaussian) instances per view; the reference's offsets are uint32 too */
 
 /* flags for gsr_forward */
 #define GSR_FLAG_BINNING_KEY64 1u /* bin exactly like the reference: one 64-bit (tile|depth) onesweep

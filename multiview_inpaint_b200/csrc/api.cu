@@ -475,7 +475,10 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
     return 0;
   };
 
-  if (capacity_hint > 0 && capacity_hint < (1ll << 30)) {
+  // Instance limit: uint32 positions (the reference's point_offsets are uint32 as well) for the default two-level
+  // binning; the literal 64-bit-key paths (GSR_FLAG_BINNING_KEY64 / REFERENCE) keep index arithmetic validated to 2^30.
+  const int64_t n_limit = k64 ? (1ll << 30) : GSR_MAX_INSTANCES;
+  if (capacity_hint > 0 && capacity_hint < n_limit) {
     // Speculative path: queue binning + blend for the hinted capacity BEFORE learning N, so the
     // GPU never idles on the host.  The host then waits for N only (copied right after the scan,
     // early in the queue) while the GPU keeps working, or does not wait at all (GSR_FLAG_ASYNC).
@@ -492,9 +495,9 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
     }
     GSR_CUDA(cudaEventSynchronize(ev), "sync num_rendered");
     cudaEventDestroy(ev);
-    N = result[0];  // full 64-bit sum: >= 2^30 is rejected below
+    N = result[0];  // full 64-bit sum: beyond the limit is rejected below
     if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
-    if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
+    if (N >= n_limit) return fail(GSR_E_OVERFLOW, "gsr_forward: too many (tile, Gaussian) instances (limit 2^32 - 65536; 2^30 with GSR_FLAG_BINNING_KEY64 / GSR_FLAG_REFERENCE)");
     if (N > capacity_hint) {  // rare: the hint was too small, redo binning + blend at the exact size
       GSR_CUDA(cudaMemsetAsync(status + 1, 0, 4, s), "clear overflow");
       if (int rc = bin_and_blend(N)) return rc;
@@ -507,9 +510,9 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   if (P > 0) {
     if (int rc = fetch_result()) return rc;
     GSR_CUDA(cudaStreamSynchronize(s), "sync num_rendered");
-    N = result[0];  // full 64-bit sum: >= 2^30 is rejected below
+    N = result[0];  // full 64-bit sum: beyond the limit is rejected below
     if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
-    if (N >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_forward: more than 2^30 (tile, Gaussian) instances");
+    if (N >= n_limit) return fail(GSR_E_OVERFLOW, "gsr_forward: too many (tile, Gaussian) instances (limit 2^32 - 65536; 2^30 with GSR_FLAG_BINNING_KEY64 / GSR_FLAG_REFERENCE)");
   }
   *num_rendered_host = N;
   return bin_and_blend(N);
@@ -717,7 +720,7 @@ int gsr_mark_visible(void* stream, int P, const float* means3D, const float* vie
 int gsr_sort_pairs_u64(void* stream, int64_t n, const uint64_t* keys_in, const uint32_t* vals_in,
                        uint64_t* keys_out, uint32_t* vals_out, int end_bit, char* temp, size_t temp_bytes) {
   if (n < 0 || end_bit < 1 || end_bit > 64) return fail(GSR_E_INVALID, "gsr_sort_pairs_u64: bad argument");
-  if (n >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_sort_pairs_u64: n >= 2^30");
+  if (n >= GSR_MAX_INSTANCES) return fail(GSR_E_OVERFLOW, "gsr_sort_pairs_u64: n >= 2^32 - 65536");
   if (n == 0) return 0;
   if (!keys_in || !keys_out || !vals_out || !temp || temp_bytes < gsr_sort_temp_bytes(n, 8, end_bit))
     return fail(GSR_E_INVALID, "gsr_sort_pairs_u64: null argument or temp too small");
@@ -732,7 +735,7 @@ int gsr_sort_pairs_u64(void* stream, int64_t n, const uint64_t* keys_in, const u
 int gsr_sort_pairs_u32(void* stream, int64_t n, const uint32_t* keys_in, const uint32_t* vals_in,
                        uint32_t* keys_out, uint32_t* vals_out, int end_bit, char* temp, size_t temp_bytes) {
   if (n < 0 || end_bit < 1 || end_bit > 32) return fail(GSR_E_INVALID, "gsr_sort_pairs_u32: bad argument");
-  if (n >= (1ll << 30)) return fail(GSR_E_OVERFLOW, "gsr_sort_pairs_u32: n >= 2^30");
+  if (n >= GSR_MAX_INSTANCES) return fail(GSR_E_OVERFLOW, "gsr_sort_pairs_u32: n >= 2^32 - 65536");
   if (n == 0) return 0;
   if (!keys_in || !keys_out || !vals_out || !temp || temp_bytes < gsr_sort_temp_bytes(n, 4, end_bit))
     return fail(GSR_E_INVALID, "gsr_sort_pairs_u32: null argument or temp too small");

@@ -124,9 +124,20 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 8;
-constexpr uint32_t RS_FLAG_AGG = 1u << 30;
-constexpr uint32_t RS_FLAG_INC = 2u << 30;
-constexpr uint32_t RS_VAL_MASK = (1u << 30) - 1;
+// Look-back status word of one (tile, digit): 2 flag bits + the count / inclusive prefix.  32-bit words (30-bit
+// prefix) below 2^30 elements; 64-bit words (62-bit prefix) from there up to the 2^32 - 1 elements that uint32
+// positions can address -- the reference's own limit (its point_offsets are uint32).
+constexpr int64_t RS_WIDE_FROM = 1ll << 30;
+template <typename StatusT> struct RsStatus;
+template <> struct RsStatus<uint32_t> {
+  static constexpr int SHIFT = 30;
+  static constexpr uint32_t AGG = 1u << 30, INC = 2u << 30, MASK = (1u << 30) - 1;
+};
+template <> struct RsStatus<unsigned long long> {
+  static constexpr int SHIFT = 62;
+  static constexpr unsigned long long AGG = 1ull << 62, INC = 2ull << 62, MASK = (1ull << 62) - 1;
+};
+static size_t rs_status_bytes(int64_t n) { return n >= RS_WIDE_FROM ? 8 : 4; }
 
 template <typename KeyT> struct RsCfg;
 template <> struct RsCfg<uint32_t> { static constexpr int ITEMS = 16; };
@@ -142,7 +153,7 @@ size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
   const int passes = rs_passes(end_bit);
   const int64_t tiles = (n + rs_tile(key_bytes) - 1) / rs_tile(key_bytes);
   return align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4) + align_up(64) +
-         align_up((size_t)passes * (size_t)(tiles > 0 ? tiles : 1) * RS_RADIX * 4);
+         align_up((size_t)passes * (size_t)(tiles > 0 ? tiles : 1) * RS_RADIX * rs_status_bytes(n));
 }
 
 template <typename KeyT>
@@ -199,13 +210,14 @@ __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift, uint32_t mask) {
   return (uint32_t)(k >> shift) & mask;
 }
 
-template <typename KeyT, int ITEMS>
+template <typename KeyT, int ITEMS, typename StatusT>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                    KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
                    const uint32_t* __restrict__ n_dev, int shift, int nbits,
-                   const uint32_t* __restrict__ global_base, volatile uint32_t* status,
+                   const uint32_t* __restrict__ global_base, volatile StatusT* status,
                    uint32_t* ticket) {
+  using ST = RsStatus<StatusT>;
   constexpr int TILE = RS_THREADS * ITEMS;
   // the element count may live on the device (no host round trip): grid is sized by capacity and
   // surplus CTAs retire before taking a ticket
@@ -286,23 +298,23 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
     const uint32_t digit_off = wp + x - count;
     s_digit_off[d] = digit_off;
 
-    uint32_t excl = 0;
-    volatile uint32_t* my = status + (size_t)tile * RS_RADIX + d;
+    StatusT excl = 0;
+    volatile StatusT* my = status + (size_t)tile * RS_RADIX + d;
     if (tile == 0) {
-      *my = RS_FLAG_INC | count;
+      *my = ST::INC | (StatusT)count;
     } else {
-      *my = RS_FLAG_AGG | count;
+      *my = ST::AGG | (StatusT)count;
       int64_t t = (int64_t)tile - 1;
       while (true) {
-        uint32_t st;
-        do { st = status[(size_t)t * RS_RADIX + d]; } while ((st >> 30) == 0);
-        excl += st & RS_VAL_MASK;
-        if (st & RS_FLAG_INC) break;
+        StatusT st;
+        do { st = status[(size_t)t * RS_RADIX + d]; } while ((st >> ST::SHIFT) == 0);
+        excl += st & ST::MASK;
+        if (st & ST::INC) break;
         t--;
       }
-      *my = RS_FLAG_INC | ((excl + count) & RS_VAL_MASK);
+      *my = ST::INC | ((excl + (StatusT)count) & ST::MASK);
     }
-    s_global_off[d] = global_base[d] + excl - digit_off;
+    s_global_off[d] = global_base[d] + (uint32_t)excl - digit_off;   // positions are < 2^32: mod-2^32 arithmetic
   }
   __syncthreads();
 
@@ -358,11 +370,15 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_
   }
 
   const size_t smem = sizeof(KeyT) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 16);
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool wide = n >= RS_WIDE_FROM;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[wide]) {
+    e = wide ? cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, ITEMS, unsigned long long>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+             : cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, ITEMS, uint32_t>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[wide] = true;
   }
   // ping-pong so that the LAST pass lands in (keys_out, vals_out); inputs are never written
   const KeyT* kin = keys_in;
@@ -372,9 +388,14 @@ static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_
     KeyT* kout = to_out ? keys_out : keys_alt;
     uint32_t* vout = to_out ? vals_out : vals_alt;
     const int bits = (end_bit - 8 * p) < 8 ? (end_bit - 8 * p) : 8;
-    rs_onesweep_kernel<KeyT, ITEMS><<<(unsigned)tiles, RS_THREADS, smem, s>>>(
-        kin, vin, kout, vout, n, n_dev, 8 * p, bits, hist + p * RS_RADIX,
-        status + (size_t)p * tiles * RS_RADIX, tickets + p);
+    if (wide)
+      rs_onesweep_kernel<KeyT, ITEMS, unsigned long long><<<(unsigned)tiles, RS_THREADS, smem, s>>>(
+          kin, vin, kout, vout, n, n_dev, 8 * p, bits, hist + p * RS_RADIX,
+          reinterpret_cast<unsigned long long*>(status) + (size_t)p * tiles * RS_RADIX, tickets + p);
+    else
+      rs_onesweep_kernel<KeyT, ITEMS, uint32_t><<<(unsigned)tiles, RS_THREADS, smem, s>>>(
+          kin, vin, kout, vout, n, n_dev, 8 * p, bits, hist + p * RS_RADIX,
+          status + (size_t)p * tiles * RS_RADIX, tickets + p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     kin = kout;

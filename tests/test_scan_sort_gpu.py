@@ -87,3 +87,34 @@ def test_sort_agrees_with_cub(C_):
     assert torch.equal(ko, ck) and torch.equal(vo.long(), ci)
     cs = C_.inclusive_scan(torch.ones(n, dtype=torch.int32).cuda())
     assert torch.equal(cs.long(), torch.arange(1, n + 1).cuda())
+
+
+def test_sort_pairs_u32_beyond_2pow30(C_):
+    """More than 2^30 pairs: the onesweep switches to 64-bit look-back words (a 30-bit prefix would wrap).
+    Size-independent properties at a size no CPU reference sorts in seconds: the output is ordered on the masked
+    key, equal keys keep their input order (values are the input positions), and the values are a permutation."""
+    n = (1 << 30) + 123_457
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * (1 << 30):
+        pytest.skip("needs ~40 GB of device memory")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    # 15-bit tile ids (two 8-bit passes), skewed so that one digit alone exceeds 2^30 / 4 elements, + junk above end_bit
+    keys = torch.randint(0, 32400, (n,), generator=g, dtype=torch.int32, device="cuda")
+    keys[: n // 3] = 77
+    keys |= (torch.randint(0, 4, (n,), generator=g, dtype=torch.int32, device="cuda") << 20)
+    vals = torch.arange(n, dtype=torch.int32, device="cuda")          # wraps negative above 2^31: compared as uint32 below
+    ko, vo = C_.sort_pairs(keys, vals, 15)
+    del keys, vals
+    torch.cuda.synchronize()
+    bad = 0
+    s = 0
+    step = 1 << 27
+    for a in range(0, n, step):
+        b = min(n, a + step + 1)
+        k = (ko[a:b] & 0x7FFF).long()
+        v = vo[a:b].long() & 0xFFFFFFFF
+        bad += int(((k[1:] < k[:-1]) | ((k[1:] == k[:-1]) & (v[1:] <= v[:-1]))).sum().item())
+        s += int(v[: min(step, b - a)].sum().item())
+    assert bad == 0
+    assert s == n * (n - 1) // 2
+    assert int((ko[: n // 3 + 100] & 0x7FFF).min().item()) == 0     # sorted front starts at tile 0
