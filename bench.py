@@ -352,29 +352,42 @@ def run_ours(args):
 
     n_slots = max(args.streams, 1)
     cam_stage = {v: torch.empty(35, device=dev) for v in mine}   # per view: the batched K8+K9 reads every view's camera at the end
-    wt_stage = [torch.empty(3, H, W, device=dev) for _ in range(n_slots)]
+    wt_stage = {v: torch.empty(3, H, W, device=dev) for v in mine}
     loss_parts = [torch.zeros((), device=dev) for _ in range(n_slots)]
+    # Host -> device staging on its own stream (copy engine): a view's camera is needed when its K1 starts, its loss
+    # weights ("GT image", 19 MB) only after its forward -- issued at the top of the step, the copies run under the
+    # first views' kernels instead of in front of them.  All cameras first (140 B each), then the images.
+    copy_stream = torch.cuda.Stream(dev)
+    cam_done = {v: torch.cuda.Event() for v in mine}
+    wt_done = {v: torch.cuda.Event() for v in mine}
 
     def step_e2e():
         for lp in loss_parts:
             lp.zero_()
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))   # last step's readers of the staging buffers are done
+        with torch.cuda.stream(copy_stream):
+            for v in mine:
+                cam_stage[v].copy_(cam_pinned[v], non_blocking=True)
+                cam_done[v].record(copy_stream)
+            for v in mine:
+                wt_stage[v].copy_(wts_cpu[v], non_blocking=True)
+                wt_done[v].record(copy_stream)
         stages, grads = [], []
         if True:
             for v in mine:
-                def stage(v=v):   # runs on the view's stream: H2D of this view's camera and loss weights ("GT image")
-                    k = pipe.slot if pipe else 0
-                    cam_stage[v].copy_(cam_pinned[v], non_blocking=True)
-                    wt_stage[k].copy_(wts_cpu[v], non_blocking=True)
+                def stage(v=v):   # runs on the view's stream
+                    torch.cuda.current_stream(dev).wait_event(cam_done[v])
                     c = cams_cpu[v]
                     return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy,
                                                          bg=bg, scale_modifier=1.0, viewmatrix=cam_stage[v][:16].view(4, 4),
                                                          projmatrix=cam_stage[v][16:32].view(4, 4), sh_degree=D,
                                                          campos=cam_stage[v][32:35], prefiltered=False)
 
-                def loss_grad(col):
+                def loss_grad(col, v=v):
                     k = pipe.slot if pipe else 0
-                    loss_parts[k].add_((col * wt_stage[k]).sum())
-                    return wt_stage[k]
+                    torch.cuda.current_stream(dev).wait_event(wt_done[v])
+                    loss_parts[k].add_((col * wt_stage[v]).sum())
+                    return wt_stage[v]
                 stages.append(stage)
                 grads.append(loss_grad)
         if args.per_view_backward:

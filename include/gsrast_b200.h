@@ -242,6 +242,26 @@ typedef struct {
 int gsr_adam_step(void* stream, const gsr_adam_segment* segs_host, int n_segs, int64_t step, double beta1,
                   double beta2, double eps);
 
+/* ---- densification re-pack of the flat arenas ------------------------------------------
+ * What gs-simp/scene/gaussian_model.py does to the six parameter tensors and their Adam state when the model changes
+ * size -- densify_and_prune :467-480 = cat_tensors_to_optimizer :385-406 (clone, split) + _prune_optimizer :346-363
+ * (split parents, final prune), and prune_points :365-383 on its own -- as ONE row gather over all segments:
+ *     dst[i*row_f32 + c] = (zero_new && i >= n_keep_state) ? 0 : src[src_row[i]*row_f32 + c],  i < n_dst, c < row_f32
+ * src_row: device int32[n_dst], every entry in [0, n_src) (composed on the host side of the binding from the clone /
+ * split / prune masks); n_keep_state: the leading destination rows that keep their optimizer state (surviving
+ * original rows; cloned and split rows follow them and start from zero moments, as torch.zeros_like appends them).
+ * Segments with zero_new = 0 are parameter slices, zero_new = 1 moment slices.  src and dst must not overlap;
+ * slices whose row_f32 is a multiple of 4 must be 16-byte aligned.  Pure data movement: bit-exact. */
+#define GSR_GATHER_MAX_SEGS 16
+typedef struct {
+  const float* src;
+  float* dst;
+  int row_f32;       /* floats per row (3, 3M, 1, 3, 4 for xyz / features / opacity / scaling / rotation) */
+  int zero_new;      /* 1: rows >= n_keep_state are zero-filled instead of copied */
+} gsr_gather_segment;
+int gsr_gather_rows(void* stream, int64_t n_dst, int64_t n_src, int64_t n_keep_state, const int32_t* src_row,
+                    const gsr_gather_segment* segs_host, int n_segs);
+
 /* ---- image output of the inference loops ---------------------------------------------
  * The tensor half of `torchvision.utils.save_image(t, path)` as called after render() in gs-simp/render.py:36-39,
  * render_depth.py:39, gen_seq.py:45-55, vis_render.py:48-51: image (C,H,W) float32 with C = 3, or C = 1 (repeated to

@@ -135,9 +135,17 @@ _lib.gsr_quantize_rgb8.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp]
 _lib.gsr_adam_step.restype = _i
 _lib.gsr_adam_step.argtypes = [_vp, C.POINTER(GsrAdamSegment), _i, _i64, C.c_double, C.c_double, C.c_double]
 
+class GsrGatherSegment(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("row_f32", _i), ("zero_new", _i)]
+
+
+GATHER_MAX_SEGS = 16
+_lib.gsr_gather_rows.restype = _i
+_lib.gsr_gather_rows.argtypes = [_vp, _i64, _i64, _i64, _vp, C.POINTER(GsrGatherSegment), _i]
+
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
                     "gsr_accumulate_view_stats", "gsr_loss_temp_bytes", "gsr_loss_l1_ssim_forward",
-                    "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step", "gsr_quantize_rgb8",
+                    "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step", "gsr_quantize_rgb8", "gsr_gather_rows",
                     "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
@@ -717,3 +725,28 @@ def quantize_rgb8(image: torch.Tensor, out: torch.Tensor | None = None, affine: 
             assert affine.numel() == 2
         _check(_lib.gsr_quantize_rgb8(_stream(dev), Cc, H, W, image.data_ptr(), _ptr(affine), out.data_ptr()), "quantize_rgb8")
     return out
+
+
+def gather_rows(src_row: torch.Tensor, n_src: int, segments, n_keep_state: int | None = None):
+    """ONE launch of gsr_gather_rows: for every segment dict(src=(n_src, ...), dst=(n_dst, ...), zero_new=bool) sets
+    dst[i] = src[src_row[i]], or zeros for rows i >= n_keep_state of a zero_new segment (the Adam moments of cloned /
+    split Gaussians).  src_row: CUDA int32 (n_dst,), entries in [0, n_src) -- the caller guarantees the range
+    (densify.py builds it from masks).  All tensors contiguous CUDA float32; src and dst must not alias."""
+    if not src_row.is_cuda or src_row.dtype != torch.int32 or not src_row.is_contiguous():
+        raise RuntimeError("src_row must be a contiguous CUDA int32 tensor (this library has no CPU path)")
+    dev, n_dst = src_row.device, src_row.numel()
+    n_keep_state = n_dst if n_keep_state is None else int(n_keep_state)
+    if len(segments) > GATHER_MAX_SEGS:
+        raise RuntimeError(f"at most {GATHER_MAX_SEGS} segments per launch")
+    segs = (GsrGatherSegment * max(len(segments), 1))()
+    for k, sg in enumerate(segments):
+        src, dst = _req_cuda_f32(sg["src"], "src"), _req_cuda_f32(sg["dst"], "dst")
+        rs = src.numel() // n_src if n_src else 0
+        rd = dst.numel() // n_dst if n_dst else rs
+        if src.numel() != rs * n_src or dst.numel() != rd * n_dst or (n_src and n_dst and rs != rd):
+            raise RuntimeError(f"segment {k}: src {tuple(src.shape)} / dst {tuple(dst.shape)} do not have {n_src} / {n_dst} "
+                               "rows of equal length")
+        segs[k] = GsrGatherSegment(_ptr(src), _ptr(dst), rd, 1 if sg.get("zero_new") else 0)
+    with torch.cuda.device(dev):
+        _check(_lib.gsr_gather_rows(_stream(dev), n_dst, int(n_src), n_keep_state, _ptr(src_row), segs, len(segments)),
+               "gather_rows")

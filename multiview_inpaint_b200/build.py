@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgsrast_b200.so")
 SOURCES = ["api.cu", "preprocess.cu", "scan_sort.cu", "binning.cu", "blend_forward.cu",
-           "blend_backward.cu", "geom_backward.cu", "geom_backward_multi.cu", "nvls_allreduce.cu", "refstruct.cu", "knn.cu", "loss.cu", "optim.cu", "image_io.cu"]
+           "blend_backward.cu", "geom_backward.cu", "geom_backward_multi.cu", "nvls_allreduce.cu", "refstruct.cu", "knn.cu", "loss.cu", "optim.cu", "image_io.cu", "densify.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "--threads", "0"]

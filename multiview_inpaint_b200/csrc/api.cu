@@ -279,6 +279,30 @@ int gsr_quantize_rgb8(void* stream, int C, int H, int W, const float* image, con
   return 0;
 }
 
+int gsr_gather_rows(void* stream, int64_t n_dst, int64_t n_src, int64_t n_keep_state, const int32_t* src_row,
+                    const gsr_gather_segment* segs_host, int n_segs) {
+  if (n_dst < 0 || n_src < 0 || n_keep_state < 0 || n_segs < 0 || n_segs > GSR_GATHER_MAX_SEGS)
+    return fail(GSR_E_INVALID, "gsr_gather_rows: bad size (n_segs <= GSR_GATHER_MAX_SEGS)");
+  if (n_dst >= ((int64_t)1 << 31) || n_src >= ((int64_t)1 << 31)) return fail(GSR_E_OVERFLOW, "gsr_gather_rows: more than 2^31 - 1 rows");
+  if (n_dst == 0 || n_segs == 0) return 0;
+  if (n_src == 0) return fail(GSR_E_INVALID, "gsr_gather_rows: rows requested from an empty source");
+  if (!src_row || !segs_host) return fail(GSR_E_INVALID, "gsr_gather_rows: null argument");
+  for (int s = 0; s < n_segs; s++) {
+    const gsr_gather_segment& g = segs_host[s];
+    if (g.row_f32 < 0 || g.row_f32 > 4096) return fail(GSR_E_INVALID, "gsr_gather_rows: row_f32 out of range");
+    if (g.row_f32 == 0) continue;
+    if (!g.src || !g.dst) return fail(GSR_E_INVALID, "gsr_gather_rows: null segment pointer");
+    if ((g.row_f32 & 3) == 0 && (((uintptr_t)g.src | (uintptr_t)g.dst) & 15))
+      return fail(GSR_E_INVALID, "gsr_gather_rows: segments with row_f32 % 4 == 0 must be 16-byte aligned");
+    const char* s0 = (const char*)g.src; const char* s1 = s0 + (size_t)n_src * g.row_f32 * 4;
+    const char* d0 = (const char*)g.dst; const char* d1 = d0 + (size_t)n_dst * g.row_f32 * 4;
+    if (s0 < d1 && d0 < s1) return fail(GSR_E_INVALID, "gsr_gather_rows: src and dst overlap");
+  }
+  GSR_CUDA(launch_gather_rows(reinterpret_cast<cudaStream_t>(stream), (long long)n_dst, (long long)n_keep_state, src_row,
+                              segs_host, n_segs), "gather_rows");
+  return 0;
+}
+
 size_t gsr_knn_temp_bytes(int P) { return knn_temp_bytes(P); }
 int gsr_knn3_mean_dist2(void* stream, int P, const float* points, float* mean_dist2, char* temp, size_t temp_bytes) {
   if (P < 0) return fail(GSR_E_INVALID, "gsr_knn3_mean_dist2: P < 0");

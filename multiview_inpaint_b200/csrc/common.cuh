@@ -236,6 +236,8 @@ cudaError_t launch_activate_forward(cudaStream_t s, int P, const float* raw_scal
 cudaError_t launch_activate_backward(cudaStream_t s, int P, const float* raw_scale, const float* raw_rot,
                                      const float* raw_opacity, float* g_scale, float* g_rot, float* g_opacity);
 cudaError_t launch_quantize_rgb8(cudaStream_t s, int C, int H, int W, const float* in, const float* affine, uint8_t* out);
+cudaError_t launch_gather_rows(cudaStream_t s, long long n_dst, long long n_keep_state, const int* src_row,
+                               const gsr_gather_segment* segs, int n_segs);
 cudaError_t launch_adam(cudaStream_t s, const gsr_adam_segment* segs, int n_segs, int64_t step, double beta1,
                         double beta2, double eps);
 

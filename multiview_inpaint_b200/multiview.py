@@ -169,6 +169,25 @@ class GradArena:
         if post_barrier:
             h.barrier()
 
+    def resized(self, P: int) -> "GradArena":
+        """A zeroed arena for a model of P Gaussians on the same device / group / memory kind -- what the caller
+        swaps in after `GaussianParamArena.densify_and_prune` (densification_postfix zeroes the statistics,
+        gaussian_model.py:423-425).  With symmetric memory this is a collective call (rendezvous)."""
+        new = GradArena(P, self.M, self.storage.device, symmetric=self._handle is not None, group=self.group)
+        new.sparse = self.sparse
+        new.method = self.method if new._mc else "nccl"
+        return new
+
+    def pruned(self, mask: torch.Tensor) -> "GradArena":
+        """The arena after `prune_points(mask)`: statistics of the surviving Gaussians carried over
+        (gaussian_model.py:379-383), gradients zero."""
+        keep = ~mask.reshape(-1).bool().to(self.storage.device)
+        new = self.resized(int(keep.sum()))
+        new.grad_norm_accum.copy_(self.grad_norm_accum[keep])
+        new.visible_count.copy_(self.visible_count[keep])
+        new.max_radii.copy_(self.max_radii[keep])
+        return new
+
     def barrier(self):
         """Cross-rank barrier on the current stream (symmetric-memory signal pads)."""
         self._handle.barrier()

@@ -17,6 +17,8 @@ Here:
   * `activate()`          one kernel per STEP (the activated values are shared by all views of a multi-view step);
   * `l1_ssim_loss()`      autograd Function over the two fused kernels of csrc/loss.cu;
   * `apply_gradients()`   the activations' chain rule in place in the gradient arena + ONE Adam launch for all groups.
+  * `densify_and_prune()` / `prune_points()` / `reset_opacity()`  the model-size changes of train.py:117-123 on the
+                          arenas: one row-gather launch (densify.py, csrc/densify.cu);
   * `fused_train_step()`  the whole iteration for a batch of views: activate -> per view (K1..K6, loss fwd+bwd,
                           K7) -> batched K8+K9 (-> all-reduce) -> chain rule -> Adam.
 Everything runs on the CUDA library (include/gsrast_b200.h); there is no torch fallback.
@@ -129,6 +131,59 @@ class GaussianParamArena:
             m, v = self.moments(pname)
             segs.append(dict(param=getattr(self, pname), grad=g[gname], exp_avg=m, exp_avg_sq=v, **kw))
         _C.adam_step(segs, self.step_count, beta1, beta2, eps)
+
+
+    # ---- model-size changes (gaussian_model.py:263-266, :365-383, :467-480), see densify.py ----
+    def densify_and_prune(self, stats: GradArena, max_grad: float, min_opacity: float, extent: float, max_screen_size,
+                          percent_dense: float = 0.01, generator=None, sync_ranks: bool = True):
+        """`gaussians.densify_and_prune(opt.densify_grad_threshold, 0.005, scene.cameras_extent, size_threshold)`
+        (train.py:120) from the statistics accumulated in `stats` (grad_norm_accum = xyz_gradient_accum,
+        visible_count = denom).  Clone / split / prune are composed into one index map and the parameter arena and
+        both moment arenas move in ONE gather launch.  In place; returns the DensifyPlan (counts for logging).
+        The model size changes: the caller replaces `stats` by `stats.resized(self.P)` (zeroed statistics, which is
+        what densification_postfix leaves, :423-425) and drops per-view workspaces / capacity hints sized for the old P.
+        Multi-rank: every rank holds the same model and the same all-reduced statistics; the split's random samples
+        are made identical by broadcasting rank 0's generator state first (`sync_ranks`)."""
+        import torch.distributed as dist
+        from . import densify
+        assert stats.P == self.P
+        if sync_ranks and dist.is_available() and dist.is_initialized() and dist.get_world_size(stats.group) > 1:
+            cuda = self.device.type == "cuda"
+            if generator is not None:
+                state = generator.get_state()
+            else:
+                state = torch.cuda.get_rng_state(self.device) if cuda else torch.get_rng_state()
+            state = state.to(self.device)
+            dist.broadcast(state, 0, group=stats.group)
+            if generator is not None:
+                generator.set_state(state.cpu())
+            elif cuda:
+                torch.cuda.set_rng_state(state.cpu(), self.device)
+            else:
+                torch.set_rng_state(state.cpu())
+        plan = densify.plan_densify_and_prune(self._xyz, self._scaling, self._rotation, self._opacity,
+                                              stats.grad_norm_accum, stats.visible_count, max_grad, min_opacity, extent,
+                                              max_screen_size, percent_dense=percent_dense, generator=generator)
+        densify.apply_plan(self, plan)
+        return plan
+
+    def prune_points(self, mask: torch.Tensor):
+        """`gaussians.prune_points(mask)` (:365-383): Gaussians with mask == True are removed, order and optimizer
+        state of the rest kept.  The caller carries the statistics over with `stats.pruned(mask)`."""
+        from . import densify
+        plan = densify.plan_prune(mask.to(self.device))
+        assert plan.n_src == self.P
+        densify.apply_plan(self, plan)
+        return plan
+
+    def reset_opacity(self):
+        """`gaussians.reset_opacity()` (:263-266, train.py:122-123): opacities capped at 0.01, their Adam moments
+        zeroed (replace_tensor_to_optimizer :331-344).  P floats: the reference's own torch expression."""
+        from . import densify
+        with torch.no_grad():
+            self._opacity.copy_(densify.reset_opacity_values(self._opacity))
+            for m in self.moments("_opacity"):
+                m.zero_()
 
 
 class _L1SSIMLoss(torch.autograd.Function):
