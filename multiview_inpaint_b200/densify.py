@@ -120,6 +120,40 @@ def plan_densify_and_prune(xyz: torch.Tensor, scaling_raw: torch.Tensor, rotatio
                        dict(cloned=int(idx_c.numel()), split=int(par.numel()), pruned=int(prune.sum())))
 
 
+class DensificationStats:
+    """`xyz_gradient_accum` / `denom` / `max_radii2D` of GaussianModel (gaussian_model.py:151-152, :66): the
+    statistics summed over the iterations BETWEEN two densifications (train.py:115-116 every iteration, consumed at
+    :120 every `densification_interval`).  `GradArena` holds the statistics of ONE step (they travel with the
+    gradients through the all-reduce, so they are overwritten per step); `add_step` folds them in.  Same attribute
+    names as GradArena, so either can be handed to `GaussianParamArena.densify_and_prune`."""
+
+    def __init__(self, P: int, device, group=None):
+        self.P, self.group = int(P), group
+        self.grad_norm_accum = torch.zeros(P, dtype=torch.float32, device=device)
+        self.visible_count = torch.zeros(P, dtype=torch.int32, device=device)
+        self.max_radii = torch.zeros(P, dtype=torch.int32, device=device)
+
+    def add_step(self, arena):
+        """after a (multi-view) step, once its all-reduce is done: train.py:115-116 for all views of the step"""
+        assert arena.P == self.P
+        self.grad_norm_accum += arena.grad_norm_accum
+        self.visible_count += arena.visible_count
+        torch.maximum(self.max_radii, arena.max_radii, out=self.max_radii)
+
+    def resized(self, P: int) -> "DensificationStats":
+        """zeroed statistics for the densified model (densification_postfix, gaussian_model.py:423-425)"""
+        return DensificationStats(P, self.grad_norm_accum.device, self.group)
+
+    def pruned(self, mask: torch.Tensor) -> "DensificationStats":
+        """prune_points carries the survivors' statistics over (gaussian_model.py:379-383)"""
+        keep = ~mask.reshape(-1).bool().to(self.grad_norm_accum.device)
+        new = DensificationStats(int(keep.sum()), self.grad_norm_accum.device, self.group)
+        new.grad_norm_accum.copy_(self.grad_norm_accum[keep])
+        new.visible_count.copy_(self.visible_count[keep])
+        new.max_radii.copy_(self.max_radii[keep])
+        return new
+
+
 def reset_opacity_values(opacity_raw: torch.Tensor) -> torch.Tensor:
     """`reset_opacity` (:263-266): inverse_sigmoid(min(sigmoid(o), 0.01)), utils/general_utils.py:18-19."""
     o = torch.sigmoid(opacity_raw)

@@ -134,16 +134,17 @@ class GaussianParamArena:
 
 
     # ---- model-size changes (gaussian_model.py:263-266, :365-383, :467-480), see densify.py ----
-    def densify_and_prune(self, stats: GradArena, max_grad: float, min_opacity: float, extent: float, max_screen_size,
+    def densify_and_prune(self, stats, max_grad: float, min_opacity: float, extent: float, max_screen_size,
                           percent_dense: float = 0.01, generator=None, sync_ranks: bool = True):
         """`gaussians.densify_and_prune(opt.densify_grad_threshold, 0.005, scene.cameras_extent, size_threshold)`
-        (train.py:120) from the statistics accumulated in `stats` (grad_norm_accum = xyz_gradient_accum,
-        visible_count = denom).  Clone / split / prune are composed into one index map and the parameter arena and
+        (train.py:120) from the statistics in `stats` (grad_norm_accum = xyz_gradient_accum, visible_count = denom):
+        a `densify.DensificationStats` accumulated over the steps since the last densification (train.py:115-116),
+        or a step's `GradArena`.  Clone / split / prune are composed into one index map and the parameter arena and
         both moment arenas move in ONE gather launch.  In place; returns the DensifyPlan (counts for logging).
-        The model size changes: the caller replaces `stats` by `stats.resized(self.P)` (zeroed statistics, which is
-        what densification_postfix leaves, :423-425) and drops per-view workspaces / capacity hints sized for the old P.
-        Multi-rank: every rank holds the same model and the same all-reduced statistics; the split's random samples
-        are made identical by broadcasting rank 0's generator state first (`sync_ranks`)."""
+        The model size changes: the caller replaces `stats` and its GradArena by `.resized(self.P)` (zeroed
+        statistics, which is what densification_postfix leaves, :423-425) and drops per-view workspaces / capacity
+        hints sized for the old P.  Multi-rank: every rank holds the same model and the same all-reduced statistics;
+        the split's random samples are made identical by broadcasting rank 0's generator state first (`sync_ranks`)."""
         import torch.distributed as dist
         from . import densify
         assert stats.P == self.P

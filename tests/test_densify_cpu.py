@@ -133,3 +133,40 @@ def test_grad_arena_resized_and_pruned_cpu():
     c = a.resized(25)
     assert c.P == 25 and c.M == 4 and float(c.storage.abs().max()) == 0.0
     assert c.views["dL_dsh"].shape == (25, 4, 3)
+
+
+def test_densification_stats_accumulate_like_train_py():
+    """train.py:115-116 over several steps: SUM of per-step gradient norms, SUM of visibility counts, MAX of radii."""
+    from multiview_inpaint_b200.multiview import GradArena
+    torch.manual_seed(1)
+    P = 50
+    st = densify.DensificationStats(P, "cpu")
+    arena = GradArena(P, 1, "cpu")
+    want_g, want_c, want_r = torch.zeros(P), torch.zeros(P, dtype=torch.int32), torch.zeros(P, dtype=torch.int32)
+    for step in range(4):
+        arena.grad_norm_accum.copy_(torch.rand(P))
+        arena.visible_count.copy_(torch.randint(0, 3, (P,), dtype=torch.int32))
+        arena.max_radii.copy_(torch.randint(0, 40, (P,), dtype=torch.int32))
+        st.add_step(arena)
+        want_g += arena.grad_norm_accum
+        want_c += arena.visible_count
+        want_r = torch.maximum(want_r, arena.max_radii)
+    assert torch.equal(st.grad_norm_accum, want_g) and torch.equal(st.visible_count, want_c)
+    assert torch.equal(st.max_radii, want_r)
+    mask = torch.rand(P) < 0.4
+    p = st.pruned(mask)
+    assert p.P == int((~mask).sum()) and torch.equal(p.visible_count, want_c[~mask])
+    z = st.resized(70)
+    assert z.P == 70 and int(z.visible_count.abs().max()) == 0 and float(z.grad_norm_accum.abs().max()) == 0.0
+    # the accumulator feeds the plan exactly like the reference's two tensors
+    m, _ = make_plan("a")
+    st2 = densify.DensificationStats(m["xyz"].shape[0], "cpu")
+    st2.grad_norm_accum.copy_(m["xyz_gradient_accum"].reshape(-1))
+    st2.visible_count.copy_(m["denom"].reshape(-1).to(torch.int32))
+    max_grad, min_op, extent, mss, percent_dense, nseed = GOLD["a_args"].tolist()
+    torch.manual_seed(int(nseed))
+    plan = densify.plan_densify_and_prune(m["xyz"], m["scaling"], m["rotation"], m["opacity"], st2.grad_norm_accum,
+                                          st2.visible_count, max_grad, min_op, extent, int(mss), percent_dense=percent_dense)
+    torch.manual_seed(int(nseed))
+    _, ref = make_plan("a")
+    assert torch.equal(plan.src_row, ref.src_row) and torch.equal(plan.child_xyz, ref.child_xyz)

@@ -229,3 +229,62 @@ def test_full_size_repack_checksum(C):
     for k in before:
         assert torch.equal(row_sum(new, getattr(new, k)), before[k][~mask]), k
     assert ms < 5.0
+
+
+def test_training_loop_through_a_densification():
+    """train.py:86-128 with the fused step: optimise, densify_and_prune on the accumulated statistics, swap the
+    statistics arena for one of the new size, keep optimising.  The model grows, nothing sized for the old P
+    is touched, the loss stays finite and the surviving originals keep their Adam state."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    from multiview_inpaint_b200 import scenes as S
+    from multiview_inpaint_b200.multiview import GradArena
+    from multiview_inpaint_b200.trainstep import GaussianParamArena, ViewLoss, fused_train_step
+    from tests.util import small_scene
+    W, H, deg = 112, 80, 1
+    sc = small_scene(P=2000, W=W, H=H, deg=deg, seed=77)
+    raw = [sc["means3D"], sc["shs"][:, :1].contiguous(), sc["shs"][:, 1:].contiguous(),
+           torch.logit(sc["opacities"].clamp(1e-4, 1 - 1e-4)).reshape(-1, 1), torch.log(sc["scales"]), sc["rotations"]]
+    pa = GaussianParamArena.from_tensors(*(t.to(DEV) for t in raw))
+    cams = [c.to(DEV) for c in S.orbit_cameras(2, W, H, max_deg=6.0)]
+    bg = torch.zeros(3, device=DEV)
+    settings = [GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bg,
+                                              scale_modifier=1.0, viewmatrix=c.world_view_transform,
+                                              projmatrix=c.full_proj_transform, sh_degree=deg, campos=c.camera_center,
+                                              prefiltered=False) for c in cams]
+    torch.manual_seed(3)
+    losses = [ViewLoss(torch.rand(3, H, W, device=DEV), 0.2) for _ in cams]
+    lrs = dict(xyz=0.00016, f_dc=0.0025, f_rest=0.0025 / 20, opacity=0.05, scaling=0.005, rotation=0.001)
+    from multiview_inpaint_b200.densify import DensificationStats
+    arena = GradArena(pa.P, pa.M, DEV)
+    stats = DensificationStats(pa.P, DEV)
+    hist = []
+    for it in range(3):
+        fused_train_step(pa, settings, losses, arena, lrs)
+        stats.add_step(arena)                                   # train.py:115-116
+        hist.append(sum(float(l.out3[2]) for l in losses))
+    assert 0 < int(arena.visible_count.max()) <= len(cams)      # the arena holds ONE step's statistics ...
+    assert int(stats.visible_count.max()) == 3 * int(arena.visible_count.max())   # ... the accumulator all three
+    P0 = pa.P
+    xyz_m_before = pa.moments("_xyz")[0].clone()
+    # thresholds chosen so that the small test scene both clones and splits
+    g = stats.grad_norm_accum / stats.visible_count.clamp(min=1)
+    thr = float(g[stats.visible_count > 0].median())
+    extent = float(torch.exp(pa._scaling).max(dim=1).values.median()) / 0.01
+    plan = pa.densify_and_prune(stats, thr, 0.005, extent, None)
+    assert plan.counts["cloned"] > 0 and plan.counts["split"] > 0
+    assert pa.P == P0 + plan.counts["cloned"] + plan.counts["split"] - plan.counts["pruned"] and pa.P != P0
+    kept = plan.src_row[:plan.n_keep_state].long()
+    assert torch.equal(pa.moments("_xyz")[0][:plan.n_keep_state], xyz_m_before[kept])
+    assert float(pa.moments("_xyz")[0][plan.n_keep_state:].abs().max()) == 0.0
+    arena, stats = arena.resized(pa.P), stats.resized(pa.P)
+    for it in range(2):
+        fused_train_step(pa, settings, losses, arena, lrs)
+        stats.add_step(arena)
+        hist.append(sum(float(l.out3[2]) for l in losses))
+    torch.cuda.synchronize()
+    assert all(np.isfinite(h) for h in hist), hist
+    assert pa.step_count == 5 and bool(torch.isfinite(pa.param).all())
+    assert 0 < int(stats.visible_count.max()) <= 2 * len(cams)  # statistics restarted after the densification
+    pa.reset_opacity()
+    fused_train_step(pa, settings, losses, arena, lrs)
+    assert bool(torch.isfinite(pa.param).all()) and float(torch.sigmoid(pa._opacity).max()) < 0.2
