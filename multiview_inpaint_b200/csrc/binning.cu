@@ -191,7 +191,12 @@ bin_expand_kernel(int P, const uint32_t* __restrict__ order, const ushort4* __re
     // Large rects would serialise the warp (depth order puts the nearest = largest splats into the
     // same few CTAs): they are queued and expanded by bin_expand_big_kernel, one warp per item.
     const bool big = cnt[r] > BE_BIG;
-    if (big) {
+    // Only rects whose first slot lies inside the capacity are queued: at most cap / (BE_BIG + 1) + 1 = big_cap of
+    // them exist, so every slot below `cap` is written by somebody.  (When the speculative capacity is too small --
+    // N > cap -- the rects beyond it used to compete for the work list's slots in arrival order and could push out
+    // rects that start below cap: their key / value slots then kept whatever the recycled buffer held, and the blend
+    // of the discarded speculative pass dereferenced those stale ids.)
+    if (big && start < cap) {
       const uint32_t slot = atomicAdd(reinterpret_cast<uint32_t*>(status + 4), 1u);
       if (slot < big_cap) big_items[slot] = make_uint4(id[r], xy0[r], wh[r], start);
     }

@@ -245,6 +245,37 @@ def test_capacity_hint_and_async_paths_give_identical_results(oracle):
     assert a[0] == b[0] == n and torch.equal(a[1], b[1])
 
 
+def test_tiny_capacity_hint_with_large_splats_on_recycled_memory():
+    """Regression (found at the mip360 size right after tests that left the caching allocator full of used blocks):
+    with a speculative capacity far below N and many rects above the work-list threshold (> 64 tiles), rects beyond
+    the capacity competed for the work list's slots and could push out rects that start below it; their key / value
+    slots kept whatever the recycled buffer held and the blend of the (discarded) speculative pass dereferenced
+    those ids -> illegal address.  Poison the allocator's cache with 0xFF, then run tiny hints on a large-splat
+    scene: must not fault and must re-bin to the exact-size result bit for bit."""
+    sc = small_scene(6000, 400, 304, 1, 57, 70.0)          # ~70 px splats: most rects cover > 64 tiles
+    ref, d, cam, bg = cuda_forward(sc, capacity=0)
+    n = ref[0]
+    st_ref = _state(ref, sc, cam, 0)
+    assert n > 300_000
+    for cap in (1000, max(n // 50, 1), n // 2, n - 1):
+        junk = torch.full((96 << 20,), -1, dtype=torch.int32, device="cuda")   # 384 MB of 0xFFFFFFFF ...
+        del junk                                                                # ... back into the cache, unsynchronised
+        out, *_ = cuda_forward(sc, capacity=cap)
+        torch.cuda.synchronize()
+        assert out[0] == n
+        st = _state(out, sc, cam, 0)
+        assert torch.equal(out[1], ref[1]) and torch.equal(out[6], ref[6]) and torch.equal(out[2], ref[2])
+        np.testing.assert_array_equal(st["point_list"], st_ref["point_list"])
+        np.testing.assert_array_equal(st["ranges"], st_ref["ranges"])
+    # async flavour: overflow is reported and nothing faults
+    slot = torch.zeros(2, dtype=torch.int64).pin_memory()
+    junk = torch.full((96 << 20,), -1, dtype=torch.int32, device="cuda")
+    del junk
+    cuda_forward(sc, capacity=2000, async_result=slot)
+    torch.cuda.synchronize()
+    assert int(slot[0]) == n and (int(slot[1]) >> 32) != 0
+
+
 def test_accumulate_flag_adds_into_outputs(oracle):
     from multiview_inpaint_b200 import _C, multiview as mv
     sc = small_scene(6000, 160, 96, 2, 53, 6.0)
