@@ -23,3 +23,19 @@ def oracle():
 def golden():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "reference_fragments.npz"))
+
+
+@pytest.fixture(autouse=True)
+def _poison_recycled_device_memory(request):
+    """GPU tests run on a DIRTY caching-allocator pool: before each one a block of 0xFF bytes is allocated and handed
+    back, so scratch buffers are carved out of poisoned memory instead of freshly mapped (zero) pages.  A kernel that
+    reads a slot nobody wrote then sees 0xFFFFFFFF ids / NaNs and fails loudly instead of passing by luck (this is how
+    the speculative-capacity overflow bug of DESIGN.md section 5 surfaced).  GSR_TEST_POISON_MB=0 turns it off."""
+    mb = int(os.environ.get("GSR_TEST_POISON_MB", "512"))
+    if mb > 0 and request.node.get_closest_marker("gpu") is not None:
+        import torch
+        if torch.cuda.is_available():
+            for dev in range(torch.cuda.device_count()):
+                junk = torch.full((mb << 18,), -1, dtype=torch.int32, device=f"cuda:{dev}")
+                del junk
+    yield
