@@ -28,13 +28,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "fwd+bwd views/s"
+FWD_STAGES = ("preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward")
+BWD_STAGES = ("accum_clear", "blend_backward", "geom_backward")
 UNIT = "views/s"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
@@ -541,6 +543,12 @@ def run_ours(args):
                      "view": {"alg_bytes": b_view, "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
                               "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
         "stages": stages,
+        # SURVEY 8d timing protocol: forward, backward and forward+backward reported separately (stage-profiler pass,
+        # one stream, per view; the two-stream timed loop above overlaps them: ms_per_step / views < the sum)
+        "split": {"fwd_ms_per_view": round(sum(per_view[k] for k in FWD_STAGES if k in per_view), 4),
+                  "bwd_ms_per_view": round(sum(per_view[k] for k in BWD_STAGES if k in per_view), 4),
+                  "fwd_bwd_ms_per_view_serial": round(sum(per_view[k] for k in FWD_STAGES + BWD_STAGES if k in per_view), 4),
+                  "fwd_bwd_ms_per_view_pipelined": round(ms_view, 4)},
     }
     if ref_struct is not None:
         line["reference_structure"] = ref_struct
