@@ -540,6 +540,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": alg[dom],
                      "ms_per_launch": per_launch[dom],
+                     "note": ("the blend kernels gather through L2 and are bound by instruction issue, not by HBM (ncu: ~80 % "
+                              "issue-active, ~2 % DRAM; profiles/r01_v4_ncu_full.md), so their fraction of the HBM peak is low by "
+                              "construction; the HBM-bound stages are in `stages` (gbps) and the whole view in `view`")
+                             if dom.startswith("blend") else None,
                      "view": {"alg_bytes": b_view, "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
                               "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
         "stages": stages,
