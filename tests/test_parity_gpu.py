@@ -468,3 +468,66 @@ def test_approx_units_identities_the_branch_free_backward_relies_on():
     nz = xs != 0
     assert ((out[nz, 0] * xs[nz] - 1).abs() < 2e-7 * 4).all()            # rcp.approx: ~1 ulp
     assert ((out[:, 1] / torch.exp2(xs) - 1).abs() < 5e-7).all()         # ex2.approx: 2^-22
+
+
+# ---------------------------------------------------------------- pinned on vectors the reference's own code produced
+def _fragment_scene(xyz, shs, scales, rotations, deg, cam, campos=None):
+    from dataclasses import replace
+    P = xyz.shape[0]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    if campos is not None:
+        cam = replace(cam, camera_center=t(campos))
+    return dict(means3D=t(xyz), shs=t(shs), scales=t(scales), rotations=t(rotations), opacities=torch.ones(P, 1),
+                sh_degree=deg, bg=torch.zeros(3), camera=cam, W=cam.image_width, H=cam.image_height, P=P, M=shs.shape[1])
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_cuda_sh_to_rgb_matches_reference_eval_sh(golden, deg):
+    """K1's SH -> RGB on the device against the REFERENCE's own eval_sh + clamp_min(+0.5, 0) (utils/sh_utils.py:57-112,
+    gaussian_renderer/__init__.py:73-78; vectors in tests/golden/reference_fragments.npz): the two branches of
+    render() -- convert_SHs_python or not -- must agree.  2e-6 absolute (fp32 evaluation order differs)."""
+    xyz, campos, feats = golden["sh_xyz"], golden["sh_campos"], golden["sh_features"]
+    P = xyz.shape[0]
+    cam = S.make_camera(64, 64, T=np.array([0.0, 0.0, 30.0]))
+    sc = _fragment_scene(xyz, feats, np.full((P, 3), 0.5, np.float32), np.tile([1, 0, 0, 0], (P, 1)), deg, cam, campos)
+    out, d, camd, bg = cuda_forward(sc)
+    st = _state(out, sc, camd, 0)
+    vis = out[2].cpu().numpy() > 0
+    assert vis.sum() > P // 3
+    ref = golden[f"sh_rgb_deg{deg}"]
+    np.testing.assert_allclose(st["rgb"][vis], ref[vis], rtol=0, atol=2e-6)
+    bits = np.stack([(st["clamped"][vis] >> c) & 1 for c in range(3)], 1).astype(bool)     # bit c <=> channel c clamped
+    np.testing.assert_array_equal(bits, (ref[vis] == 0.0) & (st["rgb"][vis] == 0.0))
+    # ... and the image rendered from the reference's colours (colors_precomp branch) is the image of the SH branch
+    sc["colors_precomp"] = torch.from_numpy(ref.copy())
+    out_c, *_ = cuda_forward(sc, use_colors=True)
+    assert torch.equal(out_c[2], out[2])
+    assert float((out_c[1] - out[1]).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("mod", [1.0, 0.7])
+def test_cuda_cov3d_branch_matches_reference_covariance(golden, mod):
+    """compute_cov3D_python branch (gaussian_renderer/__init__.py:59-66): feeding the REFERENCE's own
+    strip_symmetric(L L^T) (utils/general_utils.py:66-112, gaussian_model.py:27-31) as cov3D_precomp must render what
+    the scale + rotation branch renders.  The two covariances differ in the last ulps (torch matmul vs the kernel's
+    explicit op order), so: conic 1e-4 relative, radii within 1 px, colour 1e-5 outside a handful of threshold pixels."""
+    s, q = golden["cov_scaling"], golden["cov_rotation"]
+    q = (q / np.linalg.norm(q, axis=1, keepdims=True)).astype(np.float32)
+    P = s.shape[0]
+    g = np.random.default_rng(7)
+    xyz = np.stack([g.uniform(-1.5, 1.5, P), g.uniform(-1.0, 1.0, P), g.uniform(3.0, 8.0, P)], 1).astype(np.float32)
+    shs = g.normal(0, 0.5, (P, 1, 3)).astype(np.float32)
+    cam = S.make_camera(160, 112)
+    sc = _fragment_scene(xyz, shs, s, q, 0, cam)
+    a, d, camd, bg = cuda_forward(sc, scale_modifier=mod)
+    sc["cov3D_precomp"] = torch.from_numpy(golden[f"cov3D_mod{mod}"].copy())
+    b, *_ = cuda_forward(sc, use_cov3D=True, scale_modifier=mod)
+    sa, sb = _state(a, sc, camd, 0), _state(b, sc, camd, 0)
+    ra, rb = a[2].cpu().numpy(), b[2].cpu().numpy()
+    assert (ra > 0).sum() > P // 2 and ((ra > 0) == (rb > 0)).all()
+    assert np.abs(ra - rb).max() <= 1
+    vis = ra > 0
+    np.testing.assert_allclose(sa["conic_opacity"][vis], sb["conic_opacity"][vis], rtol=1e-4, atol=1e-7)
+    err = (a[1] - b[1]).abs().amax(0).cpu().numpy()
+    assert (err > 1e-5).sum() <= max(2, int(1e-4 * err.size)), (err > 1e-5).sum()
+    assert float(err.max()) < 2e-2
