@@ -531,3 +531,65 @@ def test_cuda_cov3d_branch_matches_reference_covariance(golden, mod):
     err = (a[1] - b[1]).abs().amax(0).cpu().numpy()
     assert (err > 1e-5).sum() <= max(2, int(1e-4 * err.size)), (err > 1e-5).sum()
     assert float(err.max()) < 2e-2
+
+
+# ---------------------------------------------------------------- hand-checkable cases of SURVEY 8c, on the device
+def _hand_scene(mean, scale, opacity, rgb=(1.0, 0.5, 0.25), W=64, H=64, bg=(0.0, 0.0, 0.0)):
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32)
+    mean = np.asarray(mean, np.float32).reshape(-1, 3)
+    P = mean.shape[0]
+    scale = np.asarray(scale, np.float32).reshape(-1, 3)
+    cam = S.make_camera(W, H)
+    return dict(means3D=t(mean), opacities=torch.full((P, 1), float(opacity)), colors_precomp=t(np.tile(np.asarray(rgb, np.float32), (P, 1))),
+                scales=t(np.tile(scale, (P // scale.shape[0], 1))), rotations=t(np.tile(np.array([1, 0, 0, 0], np.float32), (P, 1))),
+                shs=torch.zeros(P, 1, 3), sh_degree=0, bg=t(bg), camera=cam, W=W, H=H, P=P, M=1)
+
+
+HAND_CASES = {
+    "single_isotropic": dict(mean=[0, 0, 4.0], scale=[0.05, 0.05, 0.05], opacity=0.8),
+    "behind_camera_and_near_plane": dict(mean=[[0, 0, -1.0], [0, 0, 0.2], [0, 0, 0.2001]], scale=[0.01, 0.01, 0.01], opacity=0.9),
+    "two_overlapping": dict(mean=[[0, 0, 6.0], [0, 0, 3.0]], scale=[0.3, 0.3, 0.3], opacity=0.6, rgb=(1, 1, 1), bg=(0, 0, 1)),
+    "opaque_layers_terminate": dict(mean=[[0, 0, 2.0], [0, 0, 3.0], [0, 0, 4.0], [0, 0, 5.0]], scale=[0.5, 0.5, 0.5], opacity=1.0),
+    "below_alpha_threshold": dict(mean=[0, 0, 4.0], scale=[0.3, 0.3, 0.3], opacity=1.0 / 256.0, bg=(0.2, 0.4, 0.6)),
+    "ragged_40x24": dict(mean=[[0.1, 0.05, 3.0], [-0.3, 0.1, 5.0]], scale=[0.2, 0.1, 0.3], opacity=0.7, W=40, H=24, bg=(0.1, 0.2, 0.3)),
+}
+
+
+@pytest.mark.parametrize("flags", [0, KEY64, PRECISE])
+@pytest.mark.parametrize("case", sorted(HAND_CASES))
+def test_hand_checkable_cases_on_the_device(oracle, case, flags):
+    """The cases tests/test_oracle_cpu.py pins analytically on the oracle (single Gaussian alpha map, culling at
+    z <= 0.2, order / transmittance of two Gaussians, the 0.99 clamp and T < 1e-4 termination, the 1/255 threshold,
+    partial tiles), through the C ABI: every intermediate bit-exact against the oracle, plus the analytic facts
+    themselves read from the device outputs (depth sentinel 15.0 of gen_seq.py:50, radii > 0 <=> visible)."""
+    sc = _hand_scene(**HAND_CASES[case])
+    f, out, d, camd, bgd = _check_forward(oracle, sc, flags, use_colors=True)
+    _check_backward(oracle, f, out, d, camd, bgd, sc, flags, 5, use_colors=True)
+    n, color, radii, geom, binning, img, depth = out
+    color, depth, radii = color.cpu().numpy(), depth.cpu().numpy(), radii.cpu().numpy()
+    st = _state(out, sc, camd, flags)
+    if case == "single_isotropic":
+        focal = 64 / (2 * camd.tanfovx)
+        var = (focal * 0.05 / 4.0) ** 2 + 0.3
+        assert radii[0] == int(np.ceil(3 * np.sqrt(var)))
+        ys, xs = np.mgrid[0:64, 0:64]
+        a = 0.8 * np.exp(-0.5 * ((xs - 31.5) ** 2 + (ys - 31.5) ** 2) / var)
+        a = np.where(a < 1 / 255, 0, np.minimum(a, 0.99))
+        inside = st["n_contrib"].view(np.uint32) > 0
+        np.testing.assert_allclose(color[0][inside], a[inside], atol=1e-5)
+        np.testing.assert_allclose(color[2][inside], 0.25 * a[inside], atol=1e-5)
+        assert depth[0, 31, 31] == np.float32(4.0) and (depth[0][a <= 0.5] == np.float32(15.0)).all()
+    elif case == "behind_camera_and_near_plane":
+        assert radii[0] == 0 and radii[1] == 0 and radii[2] > 0
+    elif case == "two_overlapping":
+        assert depth[0, 32, 32] == np.float32(3.0) and st["n_contrib"].view(np.uint32)[32, 32] == 2
+        assert abs(color[2, 32, 32] - (color[0, 32, 32] + st["final_T"][32, 32])) < 1e-5      # bg enters as T * bg
+    elif case == "opaque_layers_terminate":
+        assert st["n_contrib"].view(np.uint32)[32, 32] == 1 and abs(st["final_T"][32, 32] - 0.01) < 1e-6
+        assert depth[0, 32, 32] == np.float32(2.0)
+    elif case == "below_alpha_threshold":
+        assert radii[0] > 0 and (st["n_contrib"] == 0).all() and (st["final_T"] == 1).all()
+        np.testing.assert_array_equal(color[1], np.full((64, 64), 0.4, np.float32))
+        assert (depth == np.float32(15.0)).all()
+    elif case == "ragged_40x24":
+        assert color.shape == (3, 24, 40) and depth.shape == (1, 24, 40) and st["ranges"].shape == (6, 2)
