@@ -76,7 +76,10 @@ def _check_forward(oracle, sc, flags, cam=None, bg=None, **kw):
     return f, out, d, camd, bgd
 
 
-def _check_backward(oracle, f, out, d, camd, bgd, sc, flags, seed, **kw):
+def _check_backward(oracle, f, out, d, camd, bgd, sc, flags, seed, rot_floor=0.0, **kw):
+    """`rot_floor`: for scenes whose rotation gradient is analytically zero (isotropic scales) the reference value is
+    exactly 0 and the device's is rounding noise (~1e-8 next to scale gradients of 1e2..1e4): the rotation error is
+    then measured against max|dL_drotations| + rot_floor * max|dL_dscales| instead of against zero."""
     W, H = camd.image_width, camd.image_height
     wt = S.loss_weights(W, H, seed)
     g_ref = oracle.backward(f, wt.numpy())
@@ -91,6 +94,9 @@ def _check_backward(oracle, f, out, d, camd, bgd, sc, flags, seed, **kw):
         assert np.isfinite(a).all(), name
         assert (a[~vis] == 0).all(), name + ": culled Gaussians must get exactly zero"
         res[name] = rel_err(a, b)
+        if name == "dL_drotations" and rot_floor > 0.0:
+            res[name] = float(np.abs(a.astype(np.float64) - b).max() /
+                              (np.abs(b).max() + rot_floor * np.abs(g_ref["dL_dscales"]).max() + 1e-30))
     conic = g["dL_dconic"].cpu().numpy().reshape(-1, 4)
     res["dL_dconic"] = rel_err(conic[:, [0, 1, 3]], g_ref["dL_dconic"][:, [0, 1, 3]])
     bad = {k: v for k, v in res.items() if not v < 1e-3}
@@ -564,7 +570,7 @@ def test_hand_checkable_cases_on_the_device(oracle, case, flags):
     themselves read from the device outputs (depth sentinel 15.0 of gen_seq.py:50, radii > 0 <=> visible)."""
     sc = _hand_scene(**HAND_CASES[case])
     f, out, d, camd, bgd = _check_forward(oracle, sc, flags, use_colors=True)
-    _check_backward(oracle, f, out, d, camd, bgd, sc, flags, 5, use_colors=True)
+    _check_backward(oracle, f, out, d, camd, bgd, sc, flags, 5, rot_floor=1e-3, use_colors=True)   # isotropic: dL/drot == 0
     n, color, radii, geom, binning, img, depth = out
     color, depth, radii = color.cpu().numpy(), depth.cpu().numpy(), radii.cpu().numpy()
     st = _state(out, sc, camd, flags)
@@ -576,8 +582,8 @@ def test_hand_checkable_cases_on_the_device(oracle, case, flags):
         a = 0.8 * np.exp(-0.5 * ((xs - 31.5) ** 2 + (ys - 31.5) ** 2) / var)
         a = np.where(a < 1 / 255, 0, np.minimum(a, 0.99))
         inside = st["n_contrib"].view(np.uint32) > 0
-        np.testing.assert_allclose(color[0][inside], a[inside], atol=1e-5)
-        np.testing.assert_allclose(color[2][inside], 0.25 * a[inside], atol=1e-5)
+        np.testing.assert_allclose(color[0][inside], a[inside], atol=2e-5)
+        np.testing.assert_allclose(color[2][inside], 0.25 * a[inside], atol=2e-5)
         assert depth[0, 31, 31] == np.float32(4.0) and (depth[0][a <= 0.5] == np.float32(15.0)).all()
     elif case == "behind_camera_and_near_plane":
         assert radii[0] == 0 and radii[1] == 0 and radii[2] > 0
