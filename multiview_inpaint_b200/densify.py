@@ -154,6 +154,31 @@ class DensificationStats:
         return new
 
 
+def sync_rng(device, generator=None, group=None) -> bool:
+    """Every rank holds a replica of the model and the same all-reduced statistics, so every rank derives the same
+    clone / split / prune masks; the one thing that could differ is the random draw of densify_and_split
+    (gaussian_model.py:438).  Rank 0's generator state (the given generator, else the default generator of `device`)
+    is broadcast so that all replicas sample identical children.  Returns True if a broadcast happened."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return False
+    device = torch.device(device)
+    cuda = device.type == "cuda"
+    if generator is not None:
+        state = generator.get_state()
+    else:
+        state = torch.cuda.get_rng_state(device) if cuda else torch.get_rng_state()
+    state = state.to(device)
+    dist.broadcast(state, 0, group=group)
+    if generator is not None:
+        generator.set_state(state.cpu())
+    elif cuda:
+        torch.cuda.set_rng_state(state.cpu(), device)
+    else:
+        torch.set_rng_state(state.cpu())
+    return True
+
+
 def reset_opacity_values(opacity_raw: torch.Tensor) -> torch.Tensor:
     """`reset_opacity` (:263-266): inverse_sigmoid(min(sigmoid(o), 0.01)), utils/general_utils.py:18-19."""
     o = torch.sigmoid(opacity_raw)

@@ -145,23 +145,10 @@ class GaussianParamArena:
         statistics, which is what densification_postfix leaves, :423-425) and drops per-view workspaces / capacity
         hints sized for the old P.  Multi-rank: every rank holds the same model and the same all-reduced statistics;
         the split's random samples are made identical by broadcasting rank 0's generator state first (`sync_ranks`)."""
-        import torch.distributed as dist
         from . import densify
         assert stats.P == self.P
-        if sync_ranks and dist.is_available() and dist.is_initialized() and dist.get_world_size(stats.group) > 1:
-            cuda = self.device.type == "cuda"
-            if generator is not None:
-                state = generator.get_state()
-            else:
-                state = torch.cuda.get_rng_state(self.device) if cuda else torch.get_rng_state()
-            state = state.to(self.device)
-            dist.broadcast(state, 0, group=stats.group)
-            if generator is not None:
-                generator.set_state(state.cpu())
-            elif cuda:
-                torch.cuda.set_rng_state(state.cpu(), self.device)
-            else:
-                torch.set_rng_state(state.cpu())
+        if sync_ranks:
+            densify.sync_rng(self.device, generator, getattr(stats, "group", None))
         plan = densify.plan_densify_and_prune(self._xyz, self._scaling, self._rotation, self._opacity,
                                               stats.grad_norm_accum, stats.visible_count, max_grad, min_opacity, extent,
                                               max_screen_size, percent_dense=percent_dense, generator=generator)

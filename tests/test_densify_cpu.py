@@ -170,3 +170,52 @@ def test_densification_stats_accumulate_like_train_py():
     torch.manual_seed(int(nseed))
     _, ref = make_plan("a")
     assert torch.equal(plan.src_row, ref.src_row) and torch.equal(plan.child_xyz, ref.child_xyz)
+
+
+# ---------------------------------------------------------------- world 2 (gloo): replicas densify identically
+def _densify_rank(rank, world, port, out_dir):
+    import torch.distributed as dist
+    from multiview_inpaint_b200.multiview import GradArena
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = gold_model("a_in")
+    P = m["xyz"].shape[0]
+    max_grad, min_op, extent, mss, percent_dense, _ = GOLD["a_args"].tolist()
+    # each rank saw its own views: the statistics are partial until the step's all-reduce (SUM / SUM / MAX)
+    arena = GradArena(P, 4, "cpu")
+    share = (torch.arange(P) % world == rank)
+    arena.grad_norm_accum.copy_(m["xyz_gradient_accum"].reshape(-1) * share)
+    arena.visible_count.copy_((m["denom"].reshape(-1) * share).to(torch.int32))
+    arena.all_reduce()
+    stats = densify.DensificationStats(P, "cpu")
+    stats.add_step(arena)
+    torch.manual_seed(1000 + 17 * rank)                 # replicas whose default generators have drifted apart
+    unsynced = torch.rand(1).item()
+    synced = densify.sync_rng("cpu")
+    plan = densify.plan_densify_and_prune(m["xyz"], m["scaling"], m["rotation"], m["opacity"], stats.grad_norm_accum,
+                                          stats.visible_count, max_grad, min_op, extent, int(mss), percent_dense=percent_dense)
+    torch.save(dict(src_row=plan.src_row, child_xyz=plan.child_xyz, child_scaling=plan.child_scaling, n_keep=plan.n_keep_state,
+                    counts=plan.counts, synced=synced, unsynced=unsynced), os.path.join(out_dir, f"plan{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_replicas_densify_identically(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_densify_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "plan0.pt"), torch.load(tmp_path / "plan1.pt")
+    assert a["synced"] and b["synced"] and a["unsynced"] != b["unsynced"]
+    assert a["counts"] == b["counts"] and a["n_keep"] == b["n_keep"] and a["counts"]["split"] > 0
+    for k in ("src_row", "child_xyz", "child_scaling"):
+        assert torch.equal(a[k], b[k]), k
+    # and the all-reduced statistics gave the reference's masks: same rows as the single-process golden plan
+    _, ref = make_plan("a")
+    assert torch.equal(a["src_row"], ref.src_row)
+
+
+def test_sync_rng_is_a_no_op_without_a_process_group():
+    assert densify.sync_rng("cpu") is False
