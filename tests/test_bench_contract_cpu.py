@@ -1,0 +1,72 @@
+"""The measurement contract, checked without a GPU: bench.py's algorithmic-byte model is SURVEY.md section 8(d)'s, the
+roofline denominator is the driver-measured peak, and the bench line recorded on the B200 (profiles/r01_v6_bench.json)
+carries every key the driver reads."""
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_algorithmic_bytes_follow_survey_8d(bench):
+    # SURVEY 8(d) worked example: headline config with V = 0.8 P = 2.4 M, N = 6 V = 14.4 M
+    P, V, N, W, H, M = 3_000_000, 2_400_000, 14_400_000, 1600, 1008, 16
+    G = (W // 16) * (H // 16)
+    a = bench.algorithmic_bytes(P, V, N, G, W, H, M)
+    assert a["preprocess"] == P * (119 + 12 * M) == P * 311
+    assert a["scan"] == 8 * P and a["duplicate"] == 20 * P + 12 * N
+    assert a["tile_sort"] == N * (8 + 6 * 24)                       # 1 histogram read + 6 passes x (12 read + 12 write)
+    assert a["tile_ranges"] == 8 * N + 8 * G
+    assert a["blend_forward"] == 44 * N + 24 * W * H
+    assert a["blend_backward"] == 44 * N + 20 * W * H + 36 * N
+    assert a["geom_backward"] == P * 550
+    fwd = sum(a[k] for k in ("preprocess", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward"))
+    bwd = a["blend_backward"] + a["geom_backward"]
+    assert abs(fwd / 1e9 - 4.2) < 0.15 and abs(bwd / 1e9 - 2.8) < 0.15          # "~4.2 GB + ~2.8 GB = ~7 GB per view"
+    for M_, b in ((1, 190), (4, 260)):
+        assert bench.algorithmic_bytes(10, 10, 10, 1, 16, 16, M_)["geom_backward"] == 10 * b
+    assert set(a) <= set(bench.FWD_STAGES) | set(bench.BWD_STAGES)         # every modelled stage is a profiled stage
+
+
+def test_peak_is_the_measured_one(bench):
+    peak, kind = bench.peaks()
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        assert kind == "measured" and peak == float(json.load(open(mp))["hbm_gbs"])
+    else:
+        assert kind == "fallback" and 6000 < peak < 8000
+
+
+def test_recorded_bench_line_has_the_contract_keys():
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r01_v6_bench.json")).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in line, k
+    assert line["unit"] == "views/s" and line["higher_is_better"] is True and line["scaling"] == "weak"
+    assert line["vs_baseline"] is None and line["data"] == "synthetic" and line["dtype"] == "f32"
+    assert line["warmup"] >= 3 and line["steps"] >= 20 and line["gpu_launches"] > 0
+    assert "workload" in line["config"] and "model" not in line["config"]
+    assert {"P", "V", "N", "G"} <= set(line["config"])                           # so the roofline can be recomputed
+    e = line["e2e"]
+    assert e["unit"] == line["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert 0 < e["value"] < line["value"] * 1.02                                 # end to end is not a copy of `value`
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = line["cpu_baseline"]
+    assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["unit"] == line["unit"] and c["sample"]
+    k = line["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(k)
+    assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # value = views of the whole job / device time
+    assert abs(line["value"] - line["config"]["views_per_step"] / (line["ms_per_step"] / 1000.0)) < 1e-6 * line["value"]
