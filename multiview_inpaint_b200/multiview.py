@@ -119,14 +119,13 @@ class GradArena:
         self.storage.zero_()
 
     def add_view_stats(self, dL_dmeans2D: torch.Tensor, radii: torch.Tensor):
-        if radii.is_cuda:  # one fused kernel instead of six torch launches
-            from . import _C
-            _C.accumulate_view_stats(radii, dL_dmeans2D, self.grad_norm_accum, self.visible_count, self.max_radii)
-            return
-        vis = radii > 0
-        self.grad_norm_accum += torch.norm(dL_dmeans2D[:, :2], dim=-1) * vis   # gaussian_model.py:483
-        self.visible_count += vis.to(torch.int32)                               # gaussian_model.py:484
-        torch.maximum(self.max_radii, radii, out=self.max_radii)                # train.py:115
+        """Densification statistics of one view (gaussian_model.py:483-484, train.py:115) added into the arena by
+        one fused kernel (gsr_accumulate_view_stats) instead of six torch launches.  CUDA only: there is no CPU
+        path (the gloo tests of the sharding logic accumulate their oracle views themselves)."""
+        if not radii.is_cuda:
+            raise RuntimeError("GradArena.add_view_stats needs CUDA tensors: the statistics kernel has no CPU path")
+        from . import _C
+        _C.accumulate_view_stats(radii, dL_dmeans2D, self.grad_norm_accum, self.visible_count, self.max_radii)
 
     def all_reduce(self, group=None):
         group = group if group is not None else self.group

@@ -30,7 +30,12 @@ def _oracle_view(sc, cam, wt, arena):
     g = O.backward(f, wt.numpy())
     for name in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations"):
         arena.views[name] += torch.from_numpy(g[name]).view_as(arena.views[name])
-    arena.add_view_stats(torch.from_numpy(g["dL_dmeans2D"]), torch.from_numpy(f.radii))
+    # the densification statistics with the reference's per-view semantics, accumulated by the CHECKER here (on the
+    # device the product does this in gsr_accumulate_view_stats, tests/test_parity_gpu.py)
+    radii, vis = torch.from_numpy(f.radii), torch.from_numpy(f.radii > 0)
+    arena.grad_norm_accum += torch.norm(torch.from_numpy(g["dL_dmeans2D"])[:, :2], dim=-1) * vis   # gaussian_model.py:483
+    arena.visible_count += vis.to(torch.int32)                                                    # gaussian_model.py:484
+    torch.maximum(arena.max_radii, radii, out=arena.max_radii)                                    # train.py:115
 
 
 def _run_rank(rank, world, port, out_dir):
@@ -110,3 +115,9 @@ def test_async_views_bookkeeping():
     a.slots[2, 1] = 1                                           # prefiltered trap
     with pytest.raises(RuntimeError):
         a.check([2])
+
+
+def test_view_stats_have_no_cpu_path():
+    a = mv.GradArena(4, 1, "cpu")
+    with pytest.raises(RuntimeError):
+        a.add_view_stats(torch.zeros(4, 3), torch.ones(4, dtype=torch.int32))
