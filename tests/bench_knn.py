@@ -1,5 +1,6 @@
-"""distCUDA2 (csrc/knn.cu) timing on the GPU box: points/s at 100k / 1M / 3M / 10M points, against the
-brute-force oracle on a bounded query sample (CPU, all host threads).  python tools/exp_knn.py"""
+"""(Lives under tests/ because it checks against and times the brute-force oracle, which only test infrastructure may use.)
+distCUDA2 (csrc/knn.cu) timing on the GPU box: points/s at 100k / 1M / 3M / 10M points, against the
+brute-force oracle on a bounded query sample (CPU, all host threads).  python tests/bench_knn.py"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 nproc > gpurun_out/nproc.txt
 timeout 240 python -m pytest tests/test_knn_gpu.py -m gpu -x -q > gpurun_out/pytest_knn.log 2>&1; echo "pytest knn rc=$?" >> gpurun_out/pytest_knn.log
 tail -5 gpurun_out/pytest_knn.log
-timeout 200 python tools/exp_knn.py > gpurun_out/knn_bench.log 2>&1; tail -4 gpurun_out/knn_bench.log
+timeout 200 python tests/bench_knn.py > gpurun_out/knn_bench.log 2>&1; tail -4 gpurun_out/knn_bench.log
 timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_knn_gpu.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
