@@ -1,0 +1,80 @@
+"""Size-independent properties of the CPU oracle (the checker of the GPU parity tests), on seeded random scenes:
+what must hold for ANY correct implementation of SURVEY.md Appendix A, so a slip in the restatement shows up even
+where no golden vector exists ("parity unpinned")."""
+import numpy as np
+import pytest
+import torch
+
+from multiview_inpaint_b200 import scenes as S
+from tests.util import oracle_forward, small_scene
+
+
+def _permuted(sc, perm):
+    out = dict(sc)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        out[k] = sc[k][perm].contiguous()
+    return out
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_gaussian_order_does_not_matter(oracle, seed):
+    """The image depends on the SET of Gaussians: lists are ordered by (depth, index), so with distinct depths a
+    permutation of the inputs permutes radii / point ids and leaves every pixel bit-identical."""
+    sc = small_scene(1500, 96, 64, 1, seed, 7.0)
+    f = oracle_forward(oracle, sc)
+    d = f.depths[f.radii > 0]
+    assert len(np.unique(d.view(np.uint32))) == len(d), "scene has depth ties: pick another seed"
+    perm = torch.from_numpy(np.random.default_rng(seed).permutation(sc["P"]))
+    g = oracle_forward(oracle, _permuted(sc, perm))
+    np.testing.assert_array_equal(g.radii, f.radii[perm.numpy()])
+    assert g.num_rendered == f.num_rendered
+    np.testing.assert_array_equal(g.color.view(np.uint32), f.color.view(np.uint32))
+    np.testing.assert_array_equal(g.depth.view(np.uint32), f.depth.view(np.uint32))
+    np.testing.assert_array_equal(g.n_contrib, f.n_contrib)
+    np.testing.assert_array_equal(perm.numpy()[g.point_list], f.point_list)          # same Gaussians in the same list slots
+
+
+def test_background_enters_linearly_through_final_T(oracle):
+    sc = small_scene(1200, 80, 48, 0, 9, 6.0)
+    f0 = oracle_forward(oracle, sc, bg=np.zeros(3, np.float32))
+    bg = np.array([0.25, 0.5, 1.0], np.float32)
+    f1 = oracle_forward(oracle, sc, bg=bg)
+    np.testing.assert_array_equal(f1.final_T, f0.final_T)
+    np.testing.assert_array_equal(f1.n_contrib, f0.n_contrib)
+    np.testing.assert_allclose(f1.color, f0.color + f0.final_T[None] * bg[:, None, None], rtol=0, atol=1e-6)
+    assert ((f0.final_T >= 0) & (f0.final_T <= 1)).all()
+
+
+def test_invisible_gaussians_change_nothing(oracle):
+    """Gaussians behind the camera, beyond the frustum guard band or with alpha below 1/255 everywhere may be added
+    or removed freely: radii 0 (or no contribution), identical image."""
+    sc = small_scene(800, 64, 64, 1, 21, 6.0)
+    f = oracle_forward(oracle, sc)
+    extra = 50
+    g = torch.Generator().manual_seed(1)
+    add = dict(means3D=torch.cat([sc["means3D"], torch.tensor([[0.0, 0.0, -3.0]]).repeat(extra, 1) + torch.randn(extra, 3, generator=g) * 0.1]),
+               scales=torch.cat([sc["scales"], torch.full((extra, 3), 0.05)]),
+               rotations=torch.cat([sc["rotations"], torch.tensor([[1.0, 0, 0, 0]]).repeat(extra, 1)]),
+               opacities=torch.cat([sc["opacities"], torch.full((extra, 1), 0.9)]),
+               shs=torch.cat([sc["shs"], torch.zeros(extra, sc["shs"].shape[1], 3)]))
+    sc2 = dict(sc, **add, P=sc["P"] + extra)
+    f2 = oracle_forward(oracle, sc2)
+    assert (f2.radii[sc["P"]:] == 0).all() and f2.num_rendered == f.num_rendered
+    np.testing.assert_array_equal(f2.color.view(np.uint32), f.color.view(np.uint32))
+    np.testing.assert_array_equal(f2.point_list, f.point_list)
+
+
+def test_zero_loss_weights_give_zero_gradients_and_linearity(oracle):
+    """The backward is linear in dL/dcolor: g(a w1 + b w2) = a g(w1) + b g(w2) (up to fp32 summation), g(0) = 0."""
+    sc = small_scene(600, 64, 48, 1, 33, 6.0)
+    f = oracle_forward(oracle, sc)
+    w1 = S.loss_weights(64, 48, 1).numpy()
+    w2 = S.loss_weights(64, 48, 2).numpy()
+    g0 = oracle.backward(f, np.zeros_like(w1))
+    for k, v in g0.items():
+        assert not np.any(v), k
+    g1, g2, g12 = oracle.backward(f, w1), oracle.backward(f, w2), oracle.backward(f, (2.0 * w1 - 0.5 * w2).astype(np.float32))
+    for k in ("dL_dmeans3D", "dL_dsh", "dL_dopacity", "dL_dscales", "dL_drotations", "dL_dmeans2D"):
+        want = 2.0 * g1[k].astype(np.float64) - 0.5 * g2[k].astype(np.float64)
+        scale = np.abs(want).max() + 1e-30
+        assert np.abs(g12[k] - want).max() <= 2e-5 * scale, k
