@@ -209,7 +209,7 @@ def apply_plan(params, plan: DensifyPlan):
             rows = plan.child_rows.to(params.device)
             new._xyz[rows] = plan.child_xyz.to(params.device)
             new._scaling[rows] = plan.child_scaling.to(params.device)
-    step = params.step_count
+    step, active = params.step_count, getattr(params, "active_sh_degree", 0)
     params.__dict__.update(new.__dict__)
-    params.step_count = step
+    params.step_count, params.active_sh_degree = step, active
     return params

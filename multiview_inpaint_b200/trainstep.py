@@ -43,6 +43,34 @@ def _numel(shp):
     return n
 
 
+def expon_lr_func(lr_init: float, lr_final: float, lr_delay_steps: int = 0, lr_delay_mult: float = 1.0,
+                  max_steps: int = 1000000):
+    """The position learning-rate schedule of the reference (`get_expon_lr_func`, utils/general_utils.py:31-64, applied
+    every iteration by `update_learning_rate`, gaussian_model.py:169-175, train.py:68): log-linear interpolation from
+    lr_init (step 0) to lr_final (step max_steps), optionally eased in over lr_delay_steps.  Returns step -> lr; feed
+    it to `fused_train_step` as lrs["xyz"]."""
+    import numpy as np
+
+    def helper(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        if lr_delay_steps > 0:
+            delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
+        else:
+            delay_rate = 1.0
+        t = np.clip(step / max_steps, 0, 1)
+        return delay_rate * np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t)
+    return helper
+
+
+def learning_rates(iteration: int, xyz_schedule, feature_lr: float = 0.0025, opacity_lr: float = 0.05,
+                   scaling_lr: float = 0.005, rotation_lr: float = 0.001) -> dict:
+    """The six group learning rates of `training_setup` (gaussian_model.py:154-161; defaults arguments/__init__.py:83-86)
+    at `iteration`, in the form `fused_train_step` / `apply_gradients` take them."""
+    return dict(xyz=float(xyz_schedule(iteration)), f_dc=feature_lr, f_rest=feature_lr / 20.0, opacity=opacity_lr,
+                scaling=scaling_lr, rotation=rotation_lr)
+
+
 class GaussianParamArena:
     """Raw (pre-activation) Gaussian parameters in ONE flat fp32 allocation
         [ _xyz (P,3) | _features (P,M,3) | _opacity (P,1) | _scaling (P,3) | _rotation (P,4) ]
@@ -71,6 +99,8 @@ class GaussianParamArena:
             setattr(self, name, self._slice(self.param, name))
         self._features_dc = self._features[:, :1, :]      # views: gaussian_model.py:142-143 keeps them as two tensors
         self._features_rest = self._features[:, 1:, :]
+        self.max_sh_degree = int(round(self.M ** 0.5)) - 1   # M = (max_sh_degree + 1)^2
+        self.active_sh_degree = 0                            # gaussian_model.py:45; raised by oneupSHdegree()
 
     def _slice(self, flat: torch.Tensor, name: str) -> torch.Tensor:
         shp = self._shapes[name]
@@ -91,6 +121,12 @@ class GaussianParamArena:
             a._scaling.copy_(scaling)
             a._rotation.copy_(rotation)
         return a
+
+    def oneupSHdegree(self):
+        """gaussian_model.py:120-122 (train.py:71-72: every 1000 iterations): the degree handed to the rasterizer as
+        `sh_degree` grows up to max_sh_degree; the (P,M,3) tensor keeps its full size throughout."""
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
 
     # the getters of gaussian_model.py:95-115
     @property

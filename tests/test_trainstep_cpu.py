@@ -179,3 +179,31 @@ def test_save_image_quantisation_oracle_matches_torch_expression():
     g = torch.rand(1, 5, 9)
     ref1 = g.expand(3, -1, -1).clone().mul(255).add_(0.5).clamp_(0, 255).permute(1, 2, 0).to(torch.uint8).numpy()
     assert np.array_equal(T.save_image_u8(g.numpy()), ref1)
+
+
+# ------------------------------------------------------------------------------------------------ schedules (host side)
+def test_position_lr_schedule_matches_reference_get_expon_lr_func():
+    """tests/golden/lr_schedule.npz holds the REFERENCE's get_expon_lr_func (utils/general_utils.py:31-64) evaluated for
+    its two optimisation presets and a delayed variant (make_lr_golden.py): identical doubles."""
+    from multiview_inpaint_b200.trainstep import expon_lr_func, learning_rates
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lr_schedule.npz"))
+    steps = g["steps"]
+    for name in ("default_30k", "inpaint_300", "delayed", "disabled"):
+        a = g[f"{name}_args"]
+        f = expon_lr_func(lr_init=a[0], lr_final=a[1], lr_delay_steps=int(a[2]), lr_delay_mult=a[3], max_steps=int(a[4]))
+        got = np.array([float(f(int(s))) for s in steps])
+        np.testing.assert_array_equal(got, g[f"{name}_lr"], err_msg=name)
+    f = expon_lr_func(0.00016, 0.0000016, 0, 0.01, 30_000)
+    lrs = learning_rates(0, f)
+    assert lrs == dict(xyz=0.00016, f_dc=0.0025, f_rest=0.0025 / 20.0, opacity=0.05, scaling=0.005, rotation=0.001)
+    assert abs(learning_rates(30_000, f)["xyz"] - 0.0000016) < 1e-18
+
+
+def test_sh_degree_schedule_on_the_arena():
+    from multiview_inpaint_b200.trainstep import GaussianParamArena
+    pa = GaussianParamArena(5, 16, "cpu")
+    assert (pa.max_sh_degree, pa.active_sh_degree) == (3, 0)
+    for want in (1, 2, 3, 3, 3):                       # gaussian_model.py:120-122: saturates at max_sh_degree
+        pa.oneupSHdegree()
+        assert pa.active_sh_degree == want
+    assert GaussianParamArena(5, 1, "cpu").max_sh_degree == 0 and GaussianParamArena(5, 4, "cpu").max_sh_degree == 1
