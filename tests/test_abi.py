@@ -90,3 +90,31 @@ def test_argument_validation_raises_like_reference():
     # CPU tensors are refused loudly: there is no fallback path
     with pytest.raises(RuntimeError, match="CUDA"):
         r(means3D=x, means2D=x, opacities=x[:, :1], shs=x[:, None], scales=x, rotations=torch.zeros(4, 4))
+
+
+def test_ctypes_argument_counts_match_the_header(built):
+    """Every prototype of include/gsrast_b200.h against the ctypes signature multiview_inpaint_b200/_C.py declares for
+    it: same number of parameters (a drifted argtypes list corrupts the call silently), pointer vs scalar in the same
+    positions."""
+    import ctypes as C
+    from multiview_inpaint_b200 import _C
+    hdr = open(os.path.join(ROOT, "include", "gsrast_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)                      # comments mention function names too
+    protos = re.findall(r"\b(?:int|size_t|uint64_t|void|const char\*)\s+(gsr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 25
+    checked = 0
+    for name, params in protos:
+        fn = getattr(_C._lib, name)
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        if fn.argtypes is None:
+            assert len(plist) == 0 or name in ("gsr_last_error", "gsr_version", "gsr_kernel_launches", "gsr_debug_approx_units"), \
+                f"{name}: {len(plist)} parameters in the header, no argtypes in _C.py"
+            continue
+        assert len(fn.argtypes) == len(plist), f"{name}: header has {len(plist)} parameters, _C.py declares {len(fn.argtypes)}"
+        for k, (p, t) in enumerate(zip(plist, fn.argtypes)):
+            is_ptr_c = "*" in p or "gsr_alloc_fn" in p
+            is_ptr_py = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._CFuncPtr)
+            assert is_ptr_c == is_ptr_py, f"{name}: parameter {k} `{p}` vs {t}"
+        checked += 1
+    assert checked >= 25
