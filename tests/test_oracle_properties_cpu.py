@@ -78,3 +78,45 @@ def test_zero_loss_weights_give_zero_gradients_and_linearity(oracle):
         want = 2.0 * g1[k].astype(np.float64) - 0.5 * g2[k].astype(np.float64)
         scale = np.abs(want).max() + 1e-30
         assert np.abs(g12[k] - want).max() <= 2e-5 * scale, k
+
+
+def test_depth_ties_break_by_gaussian_index(oracle):
+    """The domain's collisions: Gaussians at exactly the same depth (clones made by densification sit on top of their
+    originals, gaussian_model.py:456-464) have equal sort keys; a stable sort keeps them in index order inside every
+    tile list, and the two-level scheme (depth sort, emission in that order, stable tile sort) must give the very
+    same lists as the single stable (tile | depth) sort."""
+    sc = small_scene(600, 64, 48, 1, 13, 8.0)
+    # every Gaussian three times: same position / shape, different colours and opacities
+    rep = lambda t: torch.cat([t, t, t]).contiguous()
+    g = torch.Generator().manual_seed(2)
+    sc3 = dict(sc, means3D=rep(sc["means3D"]), scales=rep(sc["scales"]), rotations=rep(sc["rotations"]),
+               opacities=torch.rand(3 * sc["P"], 1, generator=g) * 0.6 + 0.05,
+               shs=torch.randn(3 * sc["P"], sc["shs"].shape[1], 3, generator=g) * 0.3, P=3 * sc["P"])
+    f = oracle_forward(oracle, sc3)
+    P = sc["P"]
+    assert (f.depths[:P] == f.depths[P:2 * P]).all() and (f.radii[:P] == f.radii[2 * P:]).all()
+    depth_bits = f.depths.view(np.uint32)[f.point_list].astype(np.int64)
+    ids = f.point_list.astype(np.int64)
+    n_ties = 0
+    for t in range(f.ranges.shape[0]):
+        a, b = int(f.ranges[t, 0]), int(f.ranges[t, 1])
+        d, i = depth_bits[a:b], ids[a:b]
+        assert (np.diff(d) >= 0).all()
+        tie = np.diff(d) == 0
+        assert (np.diff(i)[tie] > 0).all(), f"tile {t}: equal depths not in index order"
+        n_ties += int(tie.sum())
+    assert n_ties >= 2 * (f.radii[:P] > 0).sum()                   # each visible triple ties twice in every tile it touches
+    # two-level == single sort (what DESIGN.md section 4 claims), with ties
+    dkeys = np.where(f.radii > 0, f.depths.view(np.uint32), np.uint32(0xFFFFFFFF))
+    order = np.argsort(dkeys, kind="stable")
+    tiles, vals = [], []
+    for gid in order:
+        if f.radii[gid] <= 0:
+            continue
+        sel = f.values_unsorted == gid
+        tiles.append((f.keys_unsorted[sel] >> 32).astype(np.int64))
+        vals.append(f.values_unsorted[sel])
+    tiles, vals = np.concatenate(tiles), np.concatenate(vals)
+    np.testing.assert_array_equal(vals[np.argsort(tiles, kind="stable")], f.point_list)
+    # the image only depends on the order through the blend: finite and bounded
+    assert np.isfinite(f.color).all() and (f.final_T >= 0).all()

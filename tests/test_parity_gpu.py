@@ -599,3 +599,20 @@ def test_hand_checkable_cases_on_the_device(oracle, case, flags):
         assert (depth == np.float32(15.0)).all()
     elif case == "ragged_40x24":
         assert color.shape == (3, 24, 40) and depth.shape == (1, 24, 40) and st["ranges"].shape == (6, 2)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("GSR_RUN_NEW_GPU_TESTS"),
+                    reason="written after the round's GPU budget was spent: not yet run on a device; set GSR_RUN_NEW_GPU_TESTS=1")
+@pytest.mark.parametrize("flags", [0, KEY64])
+def test_depth_ties_on_the_device(oracle, flags):
+    """Collisions: every Gaussian three times at the same position (what densification's clones look like), so every
+    tile list is full of equal depth keys that must come out in index order -- bit-exact lists, ranges and geometry
+    against the oracle in both binning modes (tests/test_oracle_properties_cpu.py pins the oracle's side)."""
+    sc = small_scene(600, 64, 48, 1, 13, 8.0)
+    rep = lambda t: torch.cat([t, t, t]).contiguous()
+    g = torch.Generator().manual_seed(2)
+    sc3 = dict(sc, means3D=rep(sc["means3D"]), scales=rep(sc["scales"]), rotations=rep(sc["rotations"]),
+               opacities=torch.rand(3 * sc["P"], 1, generator=g) * 0.6 + 0.05,
+               shs=torch.randn(3 * sc["P"], sc["shs"].shape[1], 3, generator=g) * 0.3, P=3 * sc["P"])
+    f, out, d, camd, bgd = _check_forward(oracle, sc3, flags)
+    _check_backward(oracle, f, out, d, camd, bgd, sc3, flags, 13)
