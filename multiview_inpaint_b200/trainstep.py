@@ -128,6 +128,36 @@ class GaussianParamArena:
         if self.active_sh_degree < self.max_sh_degree:
             self.active_sh_degree += 1
 
+    @classmethod
+    def create_from_pcd(cls, points, colors, sh_degree: int, device, dist2: torch.Tensor | None = None) -> "GaussianParamArena":
+        """`GaussianModel.create_from_pcd` (gaussian_model.py:124-147): the initial model from an SfM point cloud --
+        positions = points, DC coefficient = RGB2SH(colour) (utils/sh_utils.py:114-115), higher SH zero, isotropic
+        scale = log sqrt(mean squared distance to the three nearest neighbours) from `distCUDA2` (here
+        gsr_knn3_mean_dist2, csrc/knn.cu) clamped at 1e-7, identity rotations, opacity inverse_sigmoid(0.1).
+        `points` / `colors`: (N,3) arrays or tensors (pcd.points / pcd.colors, colours in 0..1).  `dist2` lets a caller
+        supply the neighbour distances (tests do, to run the host logic without a GPU); by default they come from the
+        CUDA kernel, which needs a CUDA `device`."""
+        import numpy as np
+        device = torch.device(device)
+        pts = torch.as_tensor(np.asarray(points)).float().to(device)
+        rgb = torch.as_tensor(np.asarray(colors)).float().to(device)
+        N, M = pts.shape[0], (sh_degree + 1) ** 2
+        C0 = 0.28209479177387814
+        fused_color = (rgb - 0.5) / C0                                                # RGB2SH
+        if dist2 is None:
+            dist2 = _C.dist_cuda2(pts.contiguous())                                   # raises on CPU tensors: no fallback
+        dist2 = torch.clamp_min(dist2.to(device), 0.0000001)
+        scales = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 3)
+        rots = torch.zeros((N, 4), device=device)
+        rots[:, 0] = 1
+        x = 0.1 * torch.ones((N, 1), dtype=torch.float, device=device)
+        opacities = torch.log(x / (1 - x))                                            # inverse_sigmoid
+        f_dc = fused_color.reshape(N, 1, 3)                                           # features[:, :3, 0] -> (N, 1, 3)
+        f_rest = torch.zeros((N, M - 1, 3), device=device)
+        a = cls.from_tensors(pts, f_dc, f_rest, opacities, scales, rots)
+        a.active_sh_degree = 0
+        return a
+
     # the getters of gaussian_model.py:95-115
     @property
     def get_xyz(self):

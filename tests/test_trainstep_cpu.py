@@ -6,6 +6,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import trainstep_oracle as T
 
@@ -207,3 +208,24 @@ def test_sh_degree_schedule_on_the_arena():
         pa.oneupSHdegree()
         assert pa.active_sh_degree == want
     assert GaussianParamArena(5, 1, "cpu").max_sh_degree == 0 and GaussianParamArena(5, 4, "cpu").max_sh_degree == 1
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_create_from_pcd_matches_reference(case):
+    """tests/golden/init_from_pcd.npz holds what the REFERENCE's GaussianModel.create_from_pcd (gaussian_model.py:124-147)
+    builds from a seeded point cloud (make_init_golden.py; its distCUDA2 call answered by the brute-force oracle the
+    CUDA kernel is bit-identical to).  Given the same neighbour distances the arena must hold the same six tensors."""
+    from multiview_inpaint_b200.trainstep import GaussianParamArena
+    g = np.load(os.path.join(ROOT, "tests", "golden", "init_from_pcd.npz"))
+    deg = int(g[f"{case}_deg"])
+    pa = GaussianParamArena.create_from_pcd(g[f"{case}_points"], g[f"{case}_colors"], deg, "cpu",
+                                            dist2=torch.from_numpy(g[f"{case}_dist2"].copy()))
+    assert pa.M == (deg + 1) ** 2 and pa.active_sh_degree == 0 and pa.max_sh_degree == deg
+    for name, got in (("_xyz", pa._xyz), ("_features_dc", pa._features_dc), ("_features_rest", pa._features_rest),
+                      ("_scaling", pa._scaling), ("_rotation", pa._rotation), ("_opacity", pa._opacity)):
+        want = torch.from_numpy(g[f"{case}{name}"].copy())
+        assert got.shape == want.shape, name
+        assert torch.equal(got.contiguous(), want), name
+    assert torch.equal(pa._scaling[0], pa._scaling[1])      # the coincident pair shares its neighbourhood (one distance is 0)
+    with pytest.raises(RuntimeError):
+        GaussianParamArena.create_from_pcd(g[f"{case}_points"], g[f"{case}_colors"], deg, "cpu")   # no CPU neighbour search
