@@ -120,3 +120,58 @@ def test_depth_ties_break_by_gaussian_index(oracle):
     np.testing.assert_array_equal(vals[np.argsort(tiles, kind="stable")], f.point_list)
     # the image only depends on the order through the blend: finite and bounded
     assert np.isfinite(f.color).all() and (f.final_T >= 0).all()
+
+
+@pytest.mark.parametrize("seed,W,H,rad", [(41, 96, 64, 7.0), (42, 200, 120, 25.0), (43, 40, 24, 4.0)])
+def test_radius_rect_and_keys_against_an_independent_numpy_restatement(oracle, seed, W, H, rad):
+    """SURVEY Appendix A.2 steps 6-9 and A.3 restated a second time in numpy from the oracle's OWN float64 torch twin
+    (oracle/torch_golden.py gives the 2-D covariance): radius = ceil(3 sqrt(lambda_max)) with the 0.1 floor, the tile
+    rect with C truncation and clamping, tiles_touched, and the (tile << 32 | depth bits) keys in row-major rect order.
+    Integers must agree exactly wherever the float32 / float64 radius does not sit on a ceil() boundary."""
+    from oracle import torch_golden as TG
+    sc = small_scene(1500, W, H, 1, seed, rad)
+    cam = sc["camera"]
+    f = oracle_forward(oracle, sc)
+    dd = torch.float64
+    P = sc["P"]
+    pix, conic, opac, rgb, tz = TG.preprocess(sc["means3D"].to(dd), torch.zeros(P, 3, dtype=dd), sc["opacities"].to(dd),
+                                              sc["scales"].to(dd), sc["rotations"].to(dd), sc["shs"].to(dd), 1,
+                                              cam.world_view_transform, cam.full_proj_transform, cam.camera_center, W, H,
+                                              cam.tanfovx, cam.tanfovy)
+    cn = conic.numpy()
+    det_c = cn[:, 0] * cn[:, 2] - cn[:, 1] ** 2                      # conic = cov^-1: cov = adj(conic) / det(conic)
+    a, c, b = cn[:, 2] / det_c, cn[:, 0] / det_c, -cn[:, 1] / det_c
+    mid = 0.5 * (a + c)
+    lam = mid + np.sqrt(np.maximum(0.1, mid * mid - (a * c - b * b)))
+    r64 = 3.0 * np.sqrt(lam)
+    radius = np.ceil(r64)
+    safe = (np.abs(r64 - np.round(r64)) > 1e-4) & (np.abs(tz.numpy() - 0.2) > 1e-6)   # away from ceil() and near-plane boundaries
+    safe |= tz.numpy() < 0.2 - 1e-6                                                  # culled: everything is 0 whatever the rest
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    px, py = pix.numpy()[:, 0], pix.numpy()[:, 1]
+    trunc = lambda v: np.trunc(v).astype(np.int64)
+    x0 = np.clip(trunc((px - radius) / 16), 0, gx)
+    x1 = np.clip(trunc((px + radius + 15) / 16), 0, gx)
+    y0 = np.clip(trunc((py - radius) / 16), 0, gy)
+    y1 = np.clip(trunc((py + radius + 15) / 16), 0, gy)
+    # pixel positions a hair away from a multiple of 16 could truncate differently in float32: exclude those too
+    frac = lambda v: np.abs(v / 16 - np.round(v / 16))
+    safe &= (frac(px - radius) > 1e-5) & (frac(px + radius + 15) > 1e-5) & (frac(py - radius) > 1e-5) & (frac(py + radius + 15) > 1e-5)
+    tiles = (x1 - x0) * (y1 - y0)
+    culled = tz.numpy() <= 0.2
+    want_tiles = np.where(culled, 0, tiles)
+    want_radii = np.where(culled | (tiles == 0), 0, radius).astype(np.int64)
+    assert safe.mean() > 0.95
+    np.testing.assert_array_equal(f.tiles_touched[safe].astype(np.int64), want_tiles[safe])
+    np.testing.assert_array_equal(f.radii[safe].astype(np.int64), want_radii[safe])
+    # keys: row-major over the rect, tile id in the high word, the float32 depth's bit pattern in the low word
+    offs = np.concatenate([[0], np.cumsum(f.tiles_touched.astype(np.int64))])
+    np.testing.assert_array_equal(f.point_offsets.astype(np.int64), offs[1:])
+    checked = 0
+    for i in np.nonzero(safe & (f.radii > 0))[0][:300]:
+        ks = f.keys_unsorted[offs[i]:offs[i + 1]]
+        want = [((y * gx + x) << 32) | int(f.depths[i:i + 1].view(np.uint32)[0]) for y in range(y0[i], y1[i]) for x in range(x0[i], x1[i])]
+        np.testing.assert_array_equal(ks.astype(np.uint64), np.array(want, dtype=np.uint64))
+        assert (f.values_unsorted[offs[i]:offs[i + 1]] == i).all()
+        checked += 1
+    assert checked > 100
