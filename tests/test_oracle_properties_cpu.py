@@ -175,3 +175,53 @@ def test_radius_rect_and_keys_against_an_independent_numpy_restatement(oracle, s
         assert (f.values_unsorted[offs[i]:offs[i + 1]] == i).all()
         checked += 1
     assert checked > 100
+
+
+@pytest.mark.parametrize("seed,W,H,rad,P", [(51, 64, 48, 9.0, 900), (52, 40, 24, 5.0, 40)])
+def test_blend_outputs_against_an_independent_per_pixel_restatement(oracle, seed, W, H, rad, P):
+    """SURVEY Appendix A.5 a second time, pixel by pixel in float64 numpy from the oracle's own geometry state and
+    lists: colour, final_T, n_contrib (index of the last contributor) and the w-depth fork's MEDIAN depth (depth of
+    the Gaussian whose blending takes T across 0.5; 15.0 where none does -- gen_seq.py:50).  The float32 oracle may
+    differ from float64 only where a threshold (1/255, 1e-4, 0.5) is hit within rounding: a handful of pixels."""
+    sc = small_scene(P, W, H, 1, seed, rad)
+    bg = np.array([0.3, 0.6, 0.9], np.float32)
+    f = oracle_forward(oracle, sc, bg=bg)
+    gx = (W + 15) // 16
+    xy, co, rgb, dep = f.means2D.astype(np.float64), f.conic_opacity.astype(np.float64), f.rgb.astype(np.float64), f.depths
+    color = np.zeros((3, H, W)); final_T = np.ones((H, W)); n_contrib = np.zeros((H, W), np.int64)
+    depth = np.full((H, W), 15.0, np.float32)
+    fragile = np.zeros((H, W), bool)                       # a threshold was closer than float32 rounding
+    for y in range(H):
+        for x in range(W):
+            t = (y // 16) * gx + x // 16
+            T, C, last = 1.0, np.zeros(3), 0
+            for k, j in enumerate(f.point_list[f.ranges[t, 0]:f.ranges[t, 1]], start=1):
+                dx, dy = xy[j, 0] - x, xy[j, 1] - y
+                power = -0.5 * (co[j, 0] * dx * dx + co[j, 2] * dy * dy) - co[j, 1] * dx * dy
+                if power > 0:
+                    continue
+                alpha = min(0.99, co[j, 3] * np.exp(power))
+                if abs(alpha - 1 / 255) < 1e-6:
+                    fragile[y, x] = True
+                if alpha < 1 / 255:
+                    continue
+                test_T = T * (1 - alpha)
+                if abs(test_T - 1e-4) < 1e-8 or abs(test_T - 0.5) < 1e-6:
+                    fragile[y, x] = True
+                if test_T < 1e-4:
+                    break
+                C += rgb[j] * alpha * T
+                if T > 0.5 and test_T < 0.5:
+                    depth[y, x] = dep[j]
+                T, last = test_T, k
+            color[:, y, x] = C + T * bg
+            final_T[y, x], n_contrib[y, x] = T, last
+    ok = ~fragile
+    assert ok.mean() > 0.98
+    assert np.abs(color - f.color)[:, ok].max() < 2e-6
+    assert np.abs(final_T - f.final_T)[ok].max() < 1e-6
+    np.testing.assert_array_equal(n_contrib[ok], f.n_contrib[ok])
+    np.testing.assert_array_equal(depth[ok], f.depth[0][ok])
+    assert (f.depth[0] != np.float32(15.0)).any()
+    if P < 100:
+        assert (f.depth[0] == np.float32(15.0)).any()        # the sparse scene leaves pixels no Gaussian takes across T = 0.5
