@@ -601,8 +601,6 @@ def test_hand_checkable_cases_on_the_device(oracle, case, flags):
         assert color.shape == (3, 24, 40) and depth.shape == (1, 24, 40) and st["ranges"].shape == (6, 2)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("GSR_RUN_NEW_GPU_TESTS"),
-                    reason="written after the round's GPU budget was spent: not yet run on a device; set GSR_RUN_NEW_GPU_TESTS=1")
 @pytest.mark.parametrize("flags", [0, KEY64])
 def test_depth_ties_on_the_device(oracle, flags):
     """Collisions: every Gaussian three times at the same position (what densification's clones look like), so every
@@ -618,13 +616,22 @@ def test_depth_ties_on_the_device(oracle, flags):
     _check_backward(oracle, f, out, d, camd, bgd, sc3, flags, 13)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("GSR_RUN_NEW_GPU_TESTS"),
-                    reason="written after the round's GPU budget was spent: not yet run on a device; set GSR_RUN_NEW_GPU_TESTS=1")
 @pytest.mark.parametrize("flags", [0, KEY64])
 def test_gaussian_order_does_not_matter_on_the_device(flags):
     """Size-independent property (no oracle involved): with distinct depths a permutation of the input Gaussians
     permutes radii and point ids and leaves every pixel of colour and depth bit-identical."""
     sc = small_scene(20000, 320, 176, 1, 61, 6.0)
+    # 13 600 visible depths in a few exponent ranges always hold a handful of equal fp32 keys (birthday): drop those
+    # Gaussians first -- the depth depends on the position and the camera alone -- so that the order is fully defined
+    a, d, cam, bg = cuda_forward(sc, flags=flags, capacity=0)
+    bits = _state(a, sc, cam, flags)["depths"].view(np.uint32)
+    vis = a[2].cpu().numpy() > 0
+    uniq, cnt = np.unique(bits[vis], return_counts=True)
+    keep = torch.from_numpy(~(vis & np.isin(bits, uniq[cnt > 1])))
+    assert 0 < int((~keep).sum()) < 100
+    sc = dict(sc, P=int(keep.sum()))
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        sc[k] = sc[k][keep].contiguous()
     a, d, cam, bg = cuda_forward(sc, flags=flags, capacity=0)
     perm = torch.from_numpy(np.random.default_rng(61).permutation(sc["P"]))
     sc_p = dict(sc)

@@ -344,12 +344,8 @@ def test_fused_step_equals_reference_structure_step(C, deg, n_views):
     np.testing.assert_allclose(pa._features.cpu().numpy(), p1, rtol=0, atol=2e-7 * max(1.0, np.abs(p1).max()))
 
 
-# ------------------------------------------------------------------------------------------------ written after the round's GPU budget
-_NEW = pytest.mark.skipif(not os.environ.get("GSR_RUN_NEW_GPU_TESTS"),
-                          reason="written after the round's GPU budget was spent: not yet run on a device; set GSR_RUN_NEW_GPU_TESTS=1")
 
 
-@_NEW
 @pytest.mark.parametrize("case", ["a", "b", "c"])
 def test_create_from_pcd_on_the_device_matches_reference(case):
     """The whole initialisation on the GPU -- neighbour distances from gsr_knn3_mean_dist2 (bit-identical to the
@@ -359,15 +355,15 @@ def test_create_from_pcd_on_the_device_matches_reference(case):
     g = np.load(os.path.join(ROOT, "tests", "golden", "init_from_pcd.npz"))
     deg = int(g[f"{case}_deg"])
     pa = GaussianParamArena.create_from_pcd(g[f"{case}_points"], g[f"{case}_colors"], deg, DEV)
-    for name, got in (("_xyz", pa._xyz), ("_features_dc", pa._features_dc), ("_features_rest", pa._features_rest),
-                      ("_rotation", pa._rotation)):
+    for name, got in (("_xyz", pa._xyz), ("_features_rest", pa._features_rest), ("_rotation", pa._rotation)):
         assert torch.equal(got.contiguous().cpu(), torch.from_numpy(g[f"{case}{name}"].copy())), name
-    for name, got in (("_scaling", pa._scaling), ("_opacity", pa._opacity)):
+    # RGB2SH = (c - 0.5) / C0: torch's CUDA kernel multiplies by the reciprocal of a scalar divisor, the golden's CPU
+    # kernel divides (first device run, r2c1_pytest.log: 1-ulp differences) -- same tolerance as log / sqrt below
+    for name, got in (("_features_dc", pa._features_dc.contiguous()), ("_scaling", pa._scaling), ("_opacity", pa._opacity)):
         want = torch.from_numpy(g[f"{case}{name}"].copy())
         assert float((got.cpu() - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max())), name
 
 
-@_NEW
 def test_ply_round_trip_from_the_device(tmp_path):
     from multiview_inpaint_b200 import plyio
     from multiview_inpaint_b200.trainstep import GaussianParamArena
