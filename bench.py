@@ -46,11 +46,14 @@ def parse():
     ap.add_argument("--views-per-rank", type=int, default=4)
     ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
     ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
-    ap.add_argument("--streams", type=int, default=2, help="views in flight per GPU (ViewPipeline depth; 1 = one stream)")
+    ap.add_argument("--streams", type=int, default=2, help="view groups in flight per GPU (ViewPipeline depth; 1 = one stream): with the batched "
+                    "front end the rank's views are split into this many groups, one stream each")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "nvls"],
                     help="arena collective: NCCL, the in-switch multimem kernel, or whichever is faster here")
     ap.add_argument("--ar-chunks", type=int, default=8, help="Gaussian-range chunks of the pipelined per-Gaussian backward + in-switch all-reduce (1 = sequential)")
     ap.add_argument("--per-view-backward", action="store_true", help="K8+K9 per view (accumulate) instead of one batched launch per step")
+    ap.add_argument("--no-batched", action="store_true", help="front end + blend view by view on the ViewPipeline's streams (round-1 structure) "
+                    "instead of ONE launch per stage for all views of the rank (gsr_forward_views / gsr_backward_blend_views)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")
     ap.add_argument("--no-train-step", action="store_true", help="skip the fused-optimisation-step leg (SURVEY 8f rows 1, 4)")
@@ -347,7 +350,7 @@ def run_ours(args):
             mv.cuda_views_fwd_bwd(gauss, [settings(cams_dev[v]) for v in mine], [lambda c, wt=wts_dev[v]: wt for v in mine],
                                   arena, flags=args.flags, capacities=[av.capacity(v) for v in mine],
                                   async_results=[av.slot(v) for v in mine], pipeline=pipe, all_reduce=True, chunks=args.ar_chunks,
-                                  workspaces=workspaces)
+                                  workspaces=workspaces, batched=not args.no_batched)
         if args.per_view_backward:
             arena.all_reduce()
         throttle.tick(dev)
@@ -401,7 +404,7 @@ def run_ours(args):
         else:
             mv.cuda_views_fwd_bwd(gauss, stages, grads, arena, flags=args.flags, capacities=[av.capacity(v) for v in mine],
                                   async_results=[av.slot(v) for v in mine], pipeline=pipe, all_reduce=True, chunks=args.ar_chunks,
-                                  workspaces=workspaces)
+                                  workspaces=workspaces, batched=not args.no_batched)
         if args.per_view_backward:
             arena.all_reduce()
         out = float(torch.stack(loss_parts).sum().item())                  # D2H: the step's result (syncs)
@@ -529,7 +532,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_geom_backward": not args.per_view_backward, "ar_chunks": args.ar_chunks, "P": P, "V": V, "N": N,
+        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_front_end": not args.no_batched, "batched_geom_backward": not args.per_view_backward, "ar_chunks": args.ar_chunks, "P": P, "V": V, "N": N,
                    "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce", "allreduce": comm,
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},

@@ -92,6 +92,36 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
                 float* out_color, float* out_depth, int32_t* radii, int64_t* num_rendered_host,
                 int64_t capacity_hint, uint32_t flags);
 
+/* ---- batched forward (extension; the reference renders one camera per call, gaussian_renderer/__init__.py:85-93) --
+ * The forward of `n_views` views of the SAME Gaussians with ONE launch per pipeline stage for all views (K1 with the
+ * views' CTAs interleaved so that the Gaussian parameters come from HBM once, the depth sort / expansion / tile sort as
+ * segmented kernels, one blend launch over every view's tiles).  Always asynchronous (the GSR_FLAG_ASYNC contract of
+ * gsr_forward): the caller owns every buffer -- sizes from gsr_get_layout(P, width, height, capacity, flags), 256-byte
+ * aligned -- and reads result_host (PINNED int64[2]: N, status bits) after synchronising the stream; a view whose
+ * N exceeds its capacity (or whose overflow bit is set) is invalid and must be redone with a larger capacity.
+ * Two-level binning only (no GSR_FLAG_BINNING_KEY64 / GSR_FLAG_REFERENCE).  Results are bit-identical to gsr_forward
+ * per view (same kernels: gsr_forward is the n_views == 1 case). */
+typedef struct {
+  const float* background;  /* (3,)                                                                       */
+  const float* viewmatrix;  /* (4,4)                                                                      */
+  const float* projmatrix;  /* (4,4)                                                                      */
+  const float* cam_pos;     /* (3,)                                                                       */
+  float tan_fovx, tan_fovy;
+  int width, height;
+  float* out_color;         /* (3,H,W)                                                                    */
+  float* out_depth;         /* (1,H,W)                                                                    */
+  int32_t* radii;           /* (P,)                                                                       */
+  char* geom_buffer;        /* gsr_layout.geom_bytes                                                      */
+  char* binning_buffer;     /* gsr_layout.binning_bytes for `capacity`                                    */
+  char* image_buffer;       /* gsr_layout.image_bytes                                                     */
+  int64_t capacity;         /* instances the binning buffer holds, 0 < capacity < GSR_MAX_INSTANCES       */
+  int64_t* result_host;     /* pinned: [0] = N, [1] = status bits (low word trap, high word overflow)     */
+} gsr_view_forward;
+int gsr_forward_views(void* stream, int P, int D, int M, const float* means3D, const float* shs,
+                      const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                      const float* rotations, const float* cov3D_precomp, int prefiltered,
+                      const gsr_view_forward* views_host, int n_views, uint32_t flags);
+
 /* Replaces CudaRasterizer::Rasterizer::backward (called by rasterize_gaussians_backward).
  * dL_dpix (3,H,W).  Every output is fully WRITTEN (zeros for culled Gaussians), callers need not
  * clear them:  dL_dmean2D (P,3) [.z = 0]  dL_dconic (P,4) [x,y,_,w]  dL_dopacity (P,)
@@ -139,6 +169,18 @@ typedef struct {
 int gsr_backward_blend(void* stream, int P, const float* background, int width, int height,
                        const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
                        const float* dL_dpix, char* scratch, size_t scratch_bytes, uint32_t flags);
+/* K7 of several views in one launch (one clear of all accumulators, one blend launch over every view's tiles). */
+typedef struct {
+  const float* background;
+  int width, height;
+  const char* geom_buffer;
+  const char* binning_buffer;
+  const char* image_buffer;
+  const float* dL_dpix;      /* (3,H,W) */
+  char* scratch;             /* gsr_backward_scratch_bytes(P), 16-byte aligned */
+  size_t scratch_bytes;
+} gsr_view_backward;
+int gsr_backward_blend_views(void* stream, int P, const gsr_view_backward* views_host, int n_views, uint32_t flags);
 int gsr_backward_geom_multi(void* stream, int P, int D, int M, const float* means3D, const float* shs,
                             const float* scales, float scale_modifier, const float* rotations,
                             const gsr_view_grad* views_host, int n_views, float* dL_dopacity,
@@ -337,6 +379,11 @@ int gsr_debug_approx_units(const float* x_dev, int n, float* out_dev, void* stre
 
 const char* gsr_last_error(void);
 int gsr_version(void);
+
+/* Experiment switches (tools/ only; the product path never calls this).  knob 0: warp ranking of the radix sort
+ * (0 match_any, 1 ballots = default, 2 shared-memory atomicOr); knob 1: 0 drops the per-instance tile_count atomics of
+ * the expansion (results are then WRONG: timing experiments only). */
+int gsr_debug_set(int knob, int value);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,21 @@ class GsrViewGrad(C.Structure):
                 ("cam_pos", _vp), ("dL_dmean2D", _vp), ("tan_fovx", _f), ("tan_fovy", _f), ("width", _i), ("height", _i)]
 
 
+class GsrViewForward(C.Structure):
+    _fields_ = [("background", _vp), ("viewmatrix", _vp), ("projmatrix", _vp), ("cam_pos", _vp), ("tan_fovx", _f), ("tan_fovy", _f),
+                ("width", _i), ("height", _i), ("out_color", _vp), ("out_depth", _vp), ("radii", _vp), ("geom_buffer", _vp),
+                ("binning_buffer", _vp), ("image_buffer", _vp), ("capacity", _i64), ("result_host", _vp)]
+
+
+class GsrViewBackward(C.Structure):
+    _fields_ = [("background", _vp), ("width", _i), ("height", _i), ("geom_buffer", _vp), ("binning_buffer", _vp),
+                ("image_buffer", _vp), ("dL_dpix", _vp), ("scratch", _vp), ("scratch_bytes", _sz)]
+
+
+_lib.gsr_forward_views.restype = _i
+_lib.gsr_forward_views.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, C.POINTER(GsrViewForward), _i, _u32]
+_lib.gsr_backward_blend_views.restype = _i
+_lib.gsr_backward_blend_views.argtypes = [_vp, _i, C.POINTER(GsrViewBackward), _i, _u32]
 _lib.gsr_backward_blend.restype = _i
 _lib.gsr_backward_blend.argtypes = [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _u32]
 _lib.gsr_backward_geom_multi.restype = _i
@@ -146,11 +161,11 @@ _lib.gsr_gather_rows.argtypes = [_vp, _i64, _i64, _i64, _vp, C.POINTER(GsrGather
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
                     "gsr_accumulate_view_stats", "gsr_loss_temp_bytes", "gsr_loss_l1_ssim_forward",
                     "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step", "gsr_quantize_rgb8", "gsr_gather_rows",
-                    "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
+                    "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_forward_views", "gsr_backward_blend_views", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches", "gsr_debug_approx_units",
-                    "gsr_last_error", "gsr_version")
+                    "gsr_last_error", "gsr_version", "gsr_debug_set")
 
 
 def _check(rc: int, what: str):
@@ -418,6 +433,87 @@ def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBu
     return scratch
 
 
+def forward_views(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, views, sh, degree,
+                  prefiltered, capacities, async_results, workspaces=None, flags=None):
+    """Batched forward (gsr_forward_views): every pipeline stage is ONE launch for all `views` of the same Gaussians.
+    views: list of dicts / settings objects with viewmatrix, projmatrix, campos, tanfovx, tanfovy, image_height,
+    image_width (and optionally bg).  capacities[k] > 0 and async_results[k] (pinned int64[2]) per view; nothing
+    blocks the host.  -> list of (-1, color, radii, geom, binning, img, depth) like rasterize_gaussians."""
+    flags = DEFAULT_FLAGS if flags is None else int(flags)
+    P = means3D.shape[0]
+    dev = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor (this rasterizer has no CPU path)")
+    M = sh.shape[1] if sh.numel() != 0 else 0
+    nv = len(views)
+    get = lambda v, k: v[k] if isinstance(v, dict) else getattr(v, k)
+    keep, out = [], []
+    with torch.cuda.device(dev):
+        background = _f32c(background, "background")
+        means3D = _f32c(means3D, "means3D")
+        colors, opacity = _f32c(colors, "colors_precomp"), _f32c(opacity, "opacities")
+        scales, rotations = _f32c(scales, "scales"), _f32c(rotations, "rotations")
+        cov3D_precomp, sh = _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(sh, "shs")
+        arr = (GsrViewForward * max(nv, 1))()
+        for k, v in enumerate(views):
+            H, W = int(get(v, "image_height")), int(get(v, "image_width"))
+            cap = int(capacities[k])
+            res = async_results[k]
+            assert res.is_pinned() and res.dtype == torch.int64 and res.numel() >= 2 and cap > 0
+            lay = get_layout(P, W, H, cap, flags)
+            ws = workspaces[k] if workspaces is not None else None
+            if ws is not None:
+                color, depth = ws.tensor("color", (3, H, W), torch.float32), ws.tensor("depth", (1, H, W), torch.float32)
+                radii = ws.tensor("radii", (P,), torch.int32)
+                geom, binning, img = ws.bytes("geom", lay.geom_bytes), ws.bytes("binning", lay.binning_bytes), ws.bytes("image", lay.image_bytes)
+            else:
+                color, depth = torch.empty(3, H, W, device=dev), torch.empty(1, H, W, device=dev)
+                radii = torch.empty(P, dtype=torch.int32, device=dev)
+                geom, binning, img = (torch.empty(int(n), dtype=torch.uint8, device=dev)
+                                      for n in (lay.geom_bytes, lay.binning_bytes, lay.image_bytes))
+            vm, pm, cp = _f32c(get(v, "viewmatrix"), "viewmatrix"), _f32c(get(v, "projmatrix"), "projmatrix"), _f32c(get(v, "campos"), "campos")
+            bgk = background
+            keep.append((vm, pm, cp, bgk))
+            g = arr[k]
+            g.background, g.viewmatrix, g.projmatrix, g.cam_pos = _ptr(bgk), _ptr(vm), _ptr(pm), _ptr(cp)
+            g.tan_fovx, g.tan_fovy, g.width, g.height = float(get(v, "tanfovx")), float(get(v, "tanfovy")), W, H
+            g.out_color, g.out_depth, g.radii = color.data_ptr(), depth.data_ptr(), (radii.data_ptr() if P else None)
+            g.geom_buffer, g.binning_buffer, g.image_buffer = geom.data_ptr(), binning.data_ptr(), img.data_ptr()
+            g.capacity, g.result_host = cap, res.data_ptr()
+            out.append((-1, color, radii, geom, binning, img, depth))
+        if nv:
+            _check(_lib.gsr_forward_views(_stream(dev), P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
+                                          _ptr(scales), float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp),
+                                          int(bool(prefiltered)), arr, nv, flags), "forward_views")
+    return out
+
+
+def backward_blend_views(background, dL_dout_colors, geoms, binnings, imgs, P, flags=None, workspaces=None):
+    """K7 of several views in one launch (gsr_backward_blend_views) -> list of packed accumulators (uint8 scratch)."""
+    flags = DEFAULT_FLAGS if flags is None else int(flags)
+    nv = len(dL_dout_colors)
+    if nv == 0:
+        return []
+    dev = dL_dout_colors[0].device
+    with torch.cuda.device(dev):
+        nscratch = int(_lib.gsr_backward_scratch_bytes(P))
+        background = _f32c(background, "background")
+        arr = (GsrViewBackward * nv)()
+        keep, scratches = [], []
+        for k in range(nv):
+            dL = _f32c(dL_dout_colors[k], "dL_dout_color")
+            keep.append(dL)
+            sc = workspaces[k].bytes("scratch", nscratch) if workspaces is not None else torch.empty(nscratch, dtype=torch.uint8, device=dev)
+            scratches.append(sc)
+            g = arr[k]
+            g.background, g.width, g.height = _ptr(background), int(dL.shape[2]), int(dL.shape[1])
+            g.geom_buffer, g.binning_buffer, g.image_buffer = _ptr(geoms[k]), _ptr(binnings[k]), _ptr(imgs[k])
+            g.dL_dpix, g.scratch, g.scratch_bytes = dL.data_ptr(), sc.data_ptr(), nscratch
+        if P != 0:
+            _check(_lib.gsr_backward_blend_views(_stream(dev), P, arr, nv, flags), "backward_blend_views")
+    return scratches
+
+
 def backward_geom_multi_supported(M: int) -> bool:
     return M in (1, 4, 16)
 
@@ -511,6 +607,13 @@ def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_coun
 
 
 # ---- measurement hooks ---------------------------------------------------------------------------
+
+def debug_set(knob: int, value: int):
+    """Experiment switches of the library (gsr_debug_set); never used by the product path."""
+    _lib.gsr_debug_set.restype = _i
+    _lib.gsr_debug_set.argtypes = [_i, _i]
+    _check(_lib.gsr_debug_set(int(knob), int(value)), "gsr_debug_set")
+
 
 def kernel_launches() -> int:
     return int(_lib.gsr_kernel_launches())

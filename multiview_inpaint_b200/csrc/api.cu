@@ -75,19 +75,21 @@ GeomLayout geom_layout(int P, uint32_t flags) {
   L.tiles_touched = take(n * 4);
   L.point_offsets = take(n * 4);
   L.status = take(32);
-  L.temp_bytes = scan_temp_bytes(P);
+  L.scan_temp_bytes = scan_temp_bytes(P);
+  L.scan_temp = take(L.scan_temp_bytes);  // adjacent to status: one region to clear
   if (!key64(flags)) {
     L.depth_keys = take(n * 4);
     L.order = take(n * 4);
     L.depth_keys_alt = take(n * 4);
     L.order_alt = take(n * 4);
     L.rects = take(n * 8);
-    const size_t st = sort_temp_bytes(P, 4, 32);
-    if (st > L.temp_bytes) L.temp_bytes = st;
+    L.temp_bytes = sort_temp_bytes(P, 4, 32);
+    L.temp = take(L.temp_bytes);          // depth-sort temp (its own region: cleared up front with everything else)
   } else {
     L.depth_keys = L.order = L.depth_keys_alt = L.order_alt = L.rects = (size_t)-1;
+    L.temp_bytes = 0;
+    L.temp = (size_t)-1;
   }
-  L.temp = take(L.temp_bytes);
   L.bytes = off;
   return L;
 }
@@ -201,6 +203,14 @@ int gsr_profile_collect(double* ms_host, int64_t* counts_host) {
   return 0;
 }
 int gsr_version(void) { return GSR_VERSION; }
+
+int gsr_debug_set(int knob, int value) {
+  switch (knob) {
+    case 0: if (value < 0 || value > 2) return fail(GSR_E_INVALID, "gsr_debug_set: rank mode 0..2"); g_rs_rank_mode = value; return 0;
+    case 1: g_bin_count_atomics = value != 0; return 0;
+    default: return fail(GSR_E_INVALID, "gsr_debug_set: unknown knob");
+  }
+}
 
 int gsr_debug_approx_units(const float* x_dev, int n, float* out_dev, void* stream) {
   if (n <= 0) return 0;
@@ -343,6 +353,293 @@ int gsr_get_layout(int P, int width, int height, int64_t num_rendered, uint32_t 
   return 0;
 }
 
+}  // extern "C" (reopened below)
+
+// ---- the forward pipeline over a batch of views (one launch per stage for all of them) ------------------------
+namespace gsr {
+struct FwdView {   // host-side working set of one view
+  Camera cam;
+  const float* bg;
+  float* out_color;
+  float* out_depth;
+  int32_t* radii;
+  char* geom;
+  char* img;
+  char* bin;       // set once the capacity is known
+  int64_t cap;
+  int G, end_bit;
+};
+static int32_t* status_of(const FwdView& v, const GeomLayout& gl) { return reinterpret_cast<int32_t*>(v.geom + gl.status); }
+
+// K1 (+ depth sort in the two-level scheme, + scan in the literal one) for `nv` views.  `also_binning`: the binning
+// buffers are already there (speculative / asynchronous path), so their counters are cleared by the same launch.
+static int front_end(cudaStream_t s, FwdView* v, int nv, int P, int D, int M, const float* means3D, const float* shs,
+                     const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                     const float* rotations, const float* cov3D_precomp, int prefiltered, uint32_t flags, bool also_binning);
+static int bin_and_blend(cudaStream_t s, FwdView* v, int nv, int P, uint32_t flags, bool clear);
+
+static void binning_zero_regions(const FwdView& w, const GeomLayout& gl, const ImageLayout& il, int P, uint32_t flags,
+                                 std::vector<ZeroRegion>& z) {
+  const BinningLayout bl = binning_layout(w.cap, w.cam.W, w.cam.H, flags);
+  z.push_back({w.geom + gl.scan_temp, gl.scan_temp_bytes});
+  z.push_back({w.img + il.tile_count, (size_t)w.G * 4});
+  z.push_back({w.bin + bl.temp, bl.temp_bytes});
+  (void)P;
+}
+
+static int front_end(cudaStream_t s, FwdView* v, int nv, int P, int D, int M, const float* means3D, const float* shs,
+                          const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                          const float* rotations, const float* cov3D_precomp, int prefiltered, uint32_t flags,
+                          bool also_binning) {
+  if (P <= 0 || nv <= 0) return 0;
+  const bool k64 = key64(flags);
+  const GeomLayout gl = geom_layout(P, flags);
+  std::vector<ZeroRegion> z;
+  std::vector<PreView> pv((size_t)nv);
+  for (int k = 0; k < nv; k++) {
+    const FwdView& w = v[k];
+    const ImageLayout il = image_layout(w.cam.W, w.cam.H);
+    if (!k64) z.push_back({w.geom + gl.temp, gl.temp_bytes});
+    if (also_binning && !k64) {   // status block + the adjacent scan temp as one region
+      z.push_back({w.geom + gl.status, gl.scan_temp + gl.scan_temp_bytes - gl.status});
+      const BinningLayout bl = binning_layout(w.cap, w.cam.W, w.cam.H, flags);
+      z.push_back({w.img + il.tile_count, (size_t)w.G * 4});
+      z.push_back({w.bin + bl.temp, bl.temp_bytes});
+    } else {
+      z.push_back({w.geom + gl.status, 32});
+    }
+    PreView& q = pv[(size_t)k];
+    q.cam = w.cam;
+    q.radii = w.radii;
+    q.rec = reinterpret_cast<float4*>(w.geom + gl.rec);
+    q.depths = reinterpret_cast<float*>(w.geom + gl.depths);
+    q.clamped = reinterpret_cast<uint8_t*>(w.geom + gl.clamped);
+    q.tiles_touched = reinterpret_cast<uint32_t*>(w.geom + gl.tiles_touched);
+    q.depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(w.geom + gl.depth_keys);
+    q.rects = k64 ? nullptr : reinterpret_cast<ushort4*>(w.geom + gl.rects);
+    q.status = status_of(w, gl);
+  }
+  GSR_CUDA(launch_zero_regions(s, z.data(), (int)z.size()), "clear counters");
+  PROF(0);
+  GSR_CUDA(launch_preprocess(s, P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                             scale_modifier, prefiltered, pv.data(), nv), "preprocess");
+  if (k64) {
+    PROF(2);
+    for (int k = 0; k < nv; k++)
+      GSR_CUDA(launch_inclusive_scan(s, P, pv[(size_t)k].tiles_touched, nullptr,
+                                     reinterpret_cast<uint32_t*>(v[k].geom + gl.point_offsets), v[k].geom + gl.scan_temp), "scan");
+  } else {
+    PROF(1);
+    // Stable sort of (depth bits, index); culled Gaussians (key 0xFFFFFFFF) are DROPPED by the first pass, so the
+    // sorted pairs are the V = status[5] visible ones.  32 bits = 4 passes (even): a -> b -> a -> b -> a, the result
+    // lands back in (depth_keys, order); pass 0 takes the element index as the value.
+    std::vector<SortSeg<uint32_t>> segs((size_t)nv);
+    for (int k = 0; k < nv; k++) {
+      char* g = v[k].geom;
+      SortSeg<uint32_t>& q = segs[(size_t)k];
+      q.n = P;
+      q.n_dev = nullptr;
+      q.n_dev_compact = reinterpret_cast<const uint32_t*>(status_of(v[k], gl) + 5);
+      q.keys_in = reinterpret_cast<uint32_t*>(g + gl.depth_keys);
+      q.vals_in = nullptr;
+      q.keys_out = reinterpret_cast<uint32_t*>(g + gl.depth_keys);
+      q.vals_out = reinterpret_cast<uint32_t*>(g + gl.order);
+      q.keys_alt = reinterpret_cast<uint32_t*>(g + gl.depth_keys_alt);
+      q.vals_alt = reinterpret_cast<uint32_t*>(g + gl.order_alt);
+      q.temp = g + gl.temp;
+    }
+    GSR_CUDA(launch_sort_pairs_u32_batched(s, segs.data(), nv, 32, false, true, true), "depth sort");
+  }
+  PROF(-1);
+  return 0;
+}
+
+// Binning + blend of `nv` views for the capacities in v[k].cap (v[k].bin allocated for them); every kernel reads the
+// true N / V on the device.  `clear`: the binning counters were not cleared by front_end (exact-size path, re-binning).
+static int bin_and_blend(cudaStream_t s, FwdView* v, int nv, int P, uint32_t flags, bool clear) {
+  const bool k64 = key64(flags), ref = refstruct(flags);
+  const GeomLayout gl = geom_layout(P > 0 ? P : 0, flags);
+  std::vector<BlendFwdView> bv((size_t)nv);
+  bool any = false;
+  for (int k = 0; k < nv; k++) any = any || (P > 0 && v[k].cap > 0);
+  if (any && !k64) {
+    std::vector<ZeroRegion> z;
+    std::vector<BinView> bins;
+    std::vector<PrepView> preps;
+    std::vector<SortSeg<uint32_t>> segs;
+    int end_bit = 0;
+    bool same_bits = true;
+    for (int k = 0; k < nv; k++) {
+      FwdView& w = v[k];
+      const ImageLayout il = image_layout(w.cam.W, w.cam.H);
+      if (w.cap <= 0) {
+        GSR_CUDA(cudaMemsetAsync(w.img + il.ranges, 0, (size_t)w.G * sizeof(uint2), s), "memset ranges");
+        continue;
+      }
+      const BinningLayout bl = binning_layout(w.cap, w.cam.W, w.cam.H, flags);
+      if (clear) {
+        binning_zero_regions(w, gl, il, P, flags, z);
+        z.push_back({status_of(w, gl) + 4, 4});   // work-list length
+      }
+      uint32_t* point_list = reinterpret_cast<uint32_t*>(w.bin + bl.point_list);
+      uint32_t* vals_alt = reinterpret_cast<uint32_t*>(w.bin + bl.vals_alt);
+      uint32_t* ka = reinterpret_cast<uint32_t*>(w.bin + bl.keys_a);
+      uint32_t* kb = reinterpret_cast<uint32_t*>(w.bin + bl.keys_b);
+      const int passes = (w.end_bit + 7) / 8;
+      // emit into "a"; with an even pass count the sorted result lands back in "a", with an odd one in "b" -- pick
+      // a so that the result is always point_list (offset 0)
+      uint32_t* va = (passes & 1) ? vals_alt : point_list;
+      uint32_t* valt = (passes & 1) ? va : vals_alt;
+      uint32_t* kout = (passes & 1) ? kb : ka;
+      uint32_t* kalt = (passes & 1) ? ka : kb;
+      BinView b{};
+      b.order = reinterpret_cast<const uint32_t*>(w.geom + gl.order);
+      b.rects = reinterpret_cast<const ushort4*>(w.geom + gl.rects);
+      b.offsets = reinterpret_cast<uint32_t*>(w.geom + gl.point_offsets);
+      b.tile_keys = ka;
+      b.vals = va;
+      b.cap = (uint32_t)w.cap;
+      b.tile_count = reinterpret_cast<uint32_t*>(w.img + il.tile_count);
+      b.gx = w.cam.grid_x;
+      b.ticket = reinterpret_cast<uint32_t*>(w.geom + gl.scan_temp);
+      b.lb_status = reinterpret_cast<unsigned long long*>(w.geom + gl.scan_temp + align_up(16));
+      b.status = status_of(w, gl);
+      b.big_items = reinterpret_cast<uint4*>(w.bin + bl.big_items);
+      b.big_cap = (uint32_t)bin_big_capacity(w.cap);
+      b.P = P;
+      bins.push_back(b);
+      PrepView pr{};
+      pr.G = w.G;
+      pr.tile_count = b.tile_count;
+      pr.ranges = reinterpret_cast<uint2*>(w.img + il.ranges);
+      pr.end_bit = w.end_bit;
+      pr.hist = sort_hist_ptr(w.bin + bl.temp);
+      preps.push_back(pr);
+      SortSeg<uint32_t> q{};
+      q.n = w.cap;
+      q.n_dev = reinterpret_cast<const uint32_t*>(status_of(w, gl) + 2);   // N (low word), written by K1
+      q.n_dev_compact = nullptr;
+      q.keys_in = ka;
+      q.vals_in = va;
+      q.keys_out = kout;
+      q.vals_out = point_list;
+      q.keys_alt = kalt;
+      q.vals_alt = valt;
+      q.temp = w.bin + bl.temp;
+      segs.push_back(q);
+      if (end_bit == 0) end_bit = w.end_bit;
+      same_bits = same_bits && end_bit == w.end_bit;
+    }
+    if (!z.empty()) GSR_CUDA(launch_zero_regions(s, z.data(), (int)z.size()), "clear binning counters");
+    PROF(3);
+    GSR_CUDA(launch_bin_expand(s, bins.data(), (int)bins.size()), "scan + duplicate (depth order)");
+    PROF(5);
+    GSR_CUDA(launch_tile_prepare(s, preps.data(), (int)preps.size()), "tile ranges + digit bases");
+    PROF(4);
+    if (same_bits) {
+      GSR_CUDA(launch_sort_pairs_u32_batched(s, segs.data(), (int)segs.size(), end_bit, true, false, true), "tile sort");
+    } else {  // views with different tile-id widths: one sort per view
+      for (size_t k = 0; k < segs.size(); k++)
+        GSR_CUDA(launch_sort_pairs_u32_batched(s, &segs[k], 1, preps[k].end_bit, true, false, true), "tile sort");
+    }
+  } else if (any) {  // the literal 64-bit key paths: one view at a time
+    for (int k = 0; k < nv; k++) {
+      FwdView& w = v[k];
+      const ImageLayout il = image_layout(w.cam.W, w.cam.H);
+      uint2* ranges = reinterpret_cast<uint2*>(w.img + il.ranges);
+      if (w.cap <= 0) {
+        GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)w.G * sizeof(uint2), s), "memset ranges");
+        continue;
+      }
+      const BinningLayout bl = binning_layout(w.cap, w.cam.W, w.cam.H, flags);
+      const int end_bit = key64_end_bit(w.cam.W, w.cam.H);
+      const int passes = (end_bit + 7) / 8;
+      int32_t* status = status_of(w, gl);
+      const uint32_t* n_dev = reinterpret_cast<const uint32_t*>(status + 2);
+      uint32_t* point_list = reinterpret_cast<uint32_t*>(w.bin + bl.point_list);
+      uint32_t* vals_alt = reinterpret_cast<uint32_t*>(w.bin + bl.vals_alt);
+      uint32_t* va = (passes & 1) ? vals_alt : point_list;
+      uint32_t* valt = (passes & 1) ? va : vals_alt;
+      uint64_t* ka = reinterpret_cast<uint64_t*>(w.bin + bl.keys_a);
+      uint64_t* kb = reinterpret_cast<uint64_t*>(w.bin + bl.keys_b);
+      const float4* rec = reinterpret_cast<const float4*>(w.geom + gl.rec);
+      const float* depths = reinterpret_cast<const float*>(w.geom + gl.depths);
+      const uint32_t* offsets = reinterpret_cast<const uint32_t*>(w.geom + gl.point_offsets);
+      if (ref) {  // reference structure: duplicateWithKeys -> cub SortPairs (unsorted -> sorted arrays) -> identifyTileRanges
+        PROF(3);
+        GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, w.radii, w.cam.grid_x, w.cam.grid_y, ka, vals_alt, w.cap, status), "duplicateWithKeys");
+        PROF(4);
+        GSR_CUDA(launch_ref_sort_pairs(s, w.cap, ka, vals_alt, kb, point_list, end_bit, w.bin + bl.temp, bl.temp_bytes), "cub sort");
+        PROF(5);
+        GSR_CUDA(launch_tile_ranges_u64(s, w.cap, n_dev, kb, w.G, ranges), "identifyTileRanges");
+      } else {
+        PROF(3);
+        GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, w.radii, w.cam.grid_x, w.cam.grid_y, ka, va, w.cap, status), "duplicateWithKeys");
+        uint64_t* kout = (passes & 1) ? kb : ka;
+        uint64_t* kalt = (passes & 1) ? ka : kb;
+        PROF(4);
+        GSR_CUDA(launch_sort_pairs_u64(s, w.cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, w.bin + bl.temp), "sort");
+        PROF(5);
+        GSR_CUDA(launch_tile_ranges_u64(s, w.cap, n_dev, kout, w.G, ranges), "identifyTileRanges");
+      }
+    }
+  } else {
+    for (int k = 0; k < nv; k++) {
+      const ImageLayout il = image_layout(v[k].cam.W, v[k].cam.H);
+      GSR_CUDA(cudaMemsetAsync(v[k].img + il.ranges, 0, (size_t)v[k].G * sizeof(uint2), s), "memset ranges");
+    }
+  }
+  PROF(6);
+  for (int k = 0; k < nv; k++) {
+    const FwdView& w = v[k];
+    const ImageLayout il = image_layout(w.cam.W, w.cam.H);
+    BlendFwdView& q = bv[(size_t)k];
+    q.W = w.cam.W;
+    q.H = w.cam.H;
+    q.ranges = reinterpret_cast<const uint2*>(w.img + il.ranges);
+    q.point_list = reinterpret_cast<const uint32_t*>(w.bin);   // offset 0 for any capacity
+    q.rec = reinterpret_cast<const float4*>(w.geom + gl.rec);
+    q.depths = reinterpret_cast<const float*>(w.geom + gl.depths);
+    q.bg = w.bg;
+    q.out_color = w.out_color;
+    q.out_depth = w.out_depth;
+    q.final_T = reinterpret_cast<float*>(w.img + il.final_T);
+    q.n_contrib = reinterpret_cast<uint32_t*>(w.img + il.n_contrib);
+  }
+  if (ref) {
+    for (int k = 0; k < nv; k++)
+      GSR_CUDA(launch_ref_blend_forward(s, bv[(size_t)k].W, bv[(size_t)k].H, bv[(size_t)k].ranges, bv[(size_t)k].point_list,
+                                        bv[(size_t)k].rec, bv[(size_t)k].depths, bv[(size_t)k].bg, bv[(size_t)k].out_color,
+                                        bv[(size_t)k].out_depth, bv[(size_t)k].final_T, bv[(size_t)k].n_contrib),
+               "blend forward (reference structure)");
+  } else {
+    GSR_CUDA(launch_blend_forward(s, bv.data(), nv, (flags & GSR_FLAG_PRECISE) != 0), "blend forward");
+  }
+  PROF(-1);
+  return 0;
+}
+
+static FwdView make_fwd_view(int W, int H, const float* view_d, const float* proj_d, const float* campos_d, float tan_fovx,
+                             float tan_fovy, float scale_modifier, const float* bg, float* out_color, float* out_depth,
+                             int32_t* radii, char* geom, char* img) {
+  FwdView w{};
+  w.cam = make_camera(W, H, view_d, proj_d, campos_d, tan_fovx, tan_fovy, scale_modifier);
+  w.bg = bg;
+  w.out_color = out_color;
+  w.out_depth = out_depth;
+  w.radii = radii;
+  w.geom = geom;
+  w.img = img;
+  w.bin = nullptr;
+  w.cap = 0;
+  w.G = w.cam.grid_x * w.cam.grid_y;
+  w.end_bit = tile_bits(W, H);
+  return w;
+}
+}  // namespace gsr
+
+extern "C" {
+
 int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_alloc_fn binning_alloc,
                 void* binning_user, gsr_alloc_fn image_alloc, void* image_user, int P, int D, int M,
                 const float* background, int width, int height, const float* means3D,
@@ -369,27 +666,18 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   *num_rendered_host = 0;
   Pinned& pin = pinned();
   if (!pin.result) return fail(GSR_E_ALLOC, "gsr_forward: cudaMallocHost failed");
-  const Camera cam = make_camera(width, height, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, scale_modifier);
-  const int G = cam.grid_x * cam.grid_y;
 
   const GeomLayout gl = geom_layout(P, flags);
   const ImageLayout il = image_layout(width, height);
   char* geom = geom_alloc(geom_user, gl.bytes);
   char* img = image_alloc(image_user, il.bytes);
   if (!geom || !img) return fail(GSR_E_ALLOC, "gsr_forward: geometry/image buffer allocation failed");
-  float4* rec = reinterpret_cast<float4*>(geom + gl.rec);
-  float* depths = reinterpret_cast<float*>(geom + gl.depths);
-  uint8_t* clamped = reinterpret_cast<uint8_t*>(geom + gl.clamped);
-  uint32_t* tiles_touched = reinterpret_cast<uint32_t*>(geom + gl.tiles_touched);
-  uint32_t* offsets = reinterpret_cast<uint32_t*>(geom + gl.point_offsets);
+  FwdView w = make_fwd_view(width, height, viewmatrix, projmatrix, cam_pos, tan_fovx, tan_fovy, scale_modifier, background,
+                            out_color, out_depth, radii, geom, img);
   int32_t* status = reinterpret_cast<int32_t*>(geom + gl.status);
-  float* final_T = reinterpret_cast<float*>(img + il.final_T);
-  uint32_t* n_contrib = reinterpret_cast<uint32_t*>(img + il.n_contrib);
-  uint2* ranges = reinterpret_cast<uint2*>(img + il.ranges);
   const bool k64 = key64(flags);
 
   int64_t N = 0;
-  const uint32_t* order = nullptr;
   const bool async = (flags & GSR_FLAG_ASYNC) != 0;
   const bool ref = refstruct(flags);
   if (ref) {  // the reference learns N on the host mid-pipeline and sizes everything exactly
@@ -398,97 +686,25 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
   }
   int64_t* result = async ? num_rendered_host : pin.result;  // [0] = N, [1] = status bits
   if (async && capacity_hint <= 0) return fail(GSR_E_INVALID, "gsr_forward: GSR_FLAG_ASYNC needs a capacity_hint");
-  if (P > 0) {
-    GSR_CUDA(cudaMemsetAsync(status, 0, 32, s), "memset status");
-    uint32_t* depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(geom + gl.depth_keys);
-    ushort4* rects = k64 ? nullptr : reinterpret_cast<ushort4*>(geom + gl.rects);
-    PROF(0);
-    GSR_CUDA(launch_preprocess(s, P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
-                               colors_precomp, cam, prefiltered, radii, rec, depths, clamped,
-                               tiles_touched, depth_keys, rects, status), "preprocess");
-    if (k64) {
-      PROF(2);
-      GSR_CUDA(launch_inclusive_scan(s, P, tiles_touched, nullptr, offsets, geom + gl.temp), "scan");
-    } else {
-      PROF(1);
-      // stable sort of (depth bits, index) over all P Gaussians; culled ones carry 0xFFFFFFFF and
-      // end up last.  32 bits = 4 passes (even): a -> b -> a -> b -> a, the sorted pairs land back
-      // in (depth_keys, order); pass 0 takes the element index as the value.
-      uint32_t* ka = depth_keys;
-      uint32_t* va = reinterpret_cast<uint32_t*>(geom + gl.order);
-      uint32_t* kb = reinterpret_cast<uint32_t*>(geom + gl.depth_keys_alt);
-      uint32_t* vb = reinterpret_cast<uint32_t*>(geom + gl.order_alt);
-      GSR_CUDA(launch_sort_pairs_u32(s, P, nullptr, ka, nullptr, ka, va, kb, vb, 32, geom + gl.temp), "depth sort");
-      order = va;  // the scan runs fused with the expansion (launch_bin_expand), once the capacity is known
-    }
-    PROF(-1);
-  }
-  // N lives in status[2..3] (uint64, written by K1); the kernels read its low word
-  const uint32_t* n_dev = P > 0 ? reinterpret_cast<const uint32_t*>(status + 2) : nullptr;
+  // Instance limit: uint32 positions (the reference's point_offsets are uint32 as well) for the default two-level
+  // binning; the literal 64-bit-key paths (GSR_FLAG_BINNING_KEY64 / REFERENCE) keep index arithmetic validated to 2^30.
+  const int64_t n_limit = k64 ? (1ll << 30) : GSR_MAX_INSTANCES;
+  const bool speculate = capacity_hint > 0 && capacity_hint < n_limit;
 
-  // ---- binning + blend for a given capacity; every kernel reads the true N on the device ----
-  char* bin = nullptr;
-  auto bin_and_blend = [&](int64_t cap) -> int {
+  auto alloc_binning = [&](int64_t cap) -> int {
     const BinningLayout bl = binning_layout(cap, width, height, flags);
-    bin = binning_alloc(binning_user, bl.bytes);
-    if (!bin) return fail(GSR_E_ALLOC, "gsr_forward: binning buffer allocation failed");
-    uint32_t* point_list = reinterpret_cast<uint32_t*>(bin + bl.point_list);
-    uint32_t* vals_alt = reinterpret_cast<uint32_t*>(bin + bl.vals_alt);
-    if (P > 0 && cap > 0) {
-      const int end_bit = k64 ? key64_end_bit(width, height) : tile_bits(width, height);
-      const int passes = (end_bit + 7) / 8;
-      // emit into "a"; with an even pass count the sorted result lands back in "a", with an odd
-      // one in "b" -- pick a so that the result is always point_list (offset 0)
-      uint32_t* va = (passes & 1) ? vals_alt : point_list;
-      uint32_t* valt = (passes & 1) ? va : vals_alt;
-      if (ref) {  // reference structure: duplicateWithKeys -> cub SortPairs (unsorted -> sorted arrays) -> identifyTileRanges
-        uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
-        uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
-        PROF(3);
-        GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, vals_alt, cap, status), "duplicateWithKeys");
-        PROF(4);
-        GSR_CUDA(launch_ref_sort_pairs(s, cap, ka, vals_alt, kb, point_list, end_bit, bin + bl.temp, bl.temp_bytes), "cub sort");
-        PROF(5);
-        GSR_CUDA(launch_tile_ranges_u64(s, cap, n_dev, kb, G, ranges), "identifyTileRanges");
-      } else if (k64) {
-        uint64_t* ka = reinterpret_cast<uint64_t*>(bin + bl.keys_a);
-        uint64_t* kb = reinterpret_cast<uint64_t*>(bin + bl.keys_b);
-        PROF(3);
-        GSR_CUDA(launch_duplicate_key64(s, P, rec, depths, offsets, radii, cam.grid_x, cam.grid_y, ka, va, cap, status), "duplicateWithKeys");
-        uint64_t* kout = (passes & 1) ? kb : ka;
-        uint64_t* kalt = (passes & 1) ? ka : kb;
-        PROF(4);
-        GSR_CUDA(launch_sort_pairs_u64(s, cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, bin + bl.temp), "sort");
-        PROF(5);
-        GSR_CUDA(launch_tile_ranges_u64(s, cap, n_dev, kout, G, ranges), "identifyTileRanges");
-      } else {
-        uint32_t* ka = reinterpret_cast<uint32_t*>(bin + bl.keys_a);
-        uint32_t* kb = reinterpret_cast<uint32_t*>(bin + bl.keys_b);
-        uint32_t* tile_count = reinterpret_cast<uint32_t*>(img + il.tile_count);
-        PROF(3);
-        GSR_CUDA(launch_bin_expand(s, P, order, reinterpret_cast<const ushort4*>(geom + gl.rects), offsets, ka, va, cap,
-                                   tile_count, G, cam.grid_x, geom + gl.temp, status,
-                                   reinterpret_cast<uint4*>(bin + bl.big_items), bin_big_capacity(cap)), "scan + duplicate (depth order)");
-        PROF(5);
-        GSR_CUDA(launch_tile_prepare(s, G, tile_count, ranges, end_bit, sort_hist_ptr(bin + bl.temp)), "tile ranges + digit bases");
-        uint32_t* kout = (passes & 1) ? kb : ka;
-        uint32_t* kalt = (passes & 1) ? ka : kb;
-        PROF(4);
-        GSR_CUDA(launch_sort_pairs_u32(s, cap, n_dev, ka, va, kout, point_list, kalt, valt, end_bit, bin + bl.temp, true), "tile sort");
-      }
-    } else {
-      GSR_CUDA(cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s), "memset ranges");
-    }
-    PROF(6);
-    if (ref)
-      GSR_CUDA(launch_ref_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
-                                        out_depth, final_T, n_contrib), "blend forward (reference structure)");
-    else
-      GSR_CUDA(launch_blend_forward(s, width, height, ranges, point_list, rec, depths, background, out_color,
-                                    out_depth, final_T, n_contrib, (flags & GSR_FLAG_PRECISE) != 0), "blend forward");
-    PROF(-1);
+    w.bin = binning_alloc(binning_user, bl.bytes);
+    w.cap = cap;
+    if (!w.bin) return fail(GSR_E_ALLOC, "gsr_forward: binning buffer allocation failed");
     return 0;
   };
+  if (speculate)
+    if (int rc = alloc_binning(capacity_hint)) return rc;
+  if (int rc = front_end(s, &w, 1, P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+                         cov3D_precomp, prefiltered, flags, speculate))
+    return rc;
+  // N lives in status[2..3] (uint64, written by K1); the kernels read its low word
+  const uint32_t* n_dev = P > 0 ? reinterpret_cast<const uint32_t*>(status + 2) : nullptr;
   auto fetch_result = [&]() -> int {  // N and the status word to (pinned) host memory, asynchronously
     result[0] = 0;
     result[1] = 0;
@@ -499,32 +715,29 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
     return 0;
   };
 
-  // Instance limit: uint32 positions (the reference's point_offsets are uint32 as well) for the default two-level
-  // binning; the literal 64-bit-key paths (GSR_FLAG_BINNING_KEY64 / REFERENCE) keep index arithmetic validated to 2^30.
-  const int64_t n_limit = k64 ? (1ll << 30) : GSR_MAX_INSTANCES;
-  if (capacity_hint > 0 && capacity_hint < n_limit) {
+  if (speculate) {
     // Speculative path: queue binning + blend for the hinted capacity BEFORE learning N, so the
-    // GPU never idles on the host.  The host then waits for N only (copied right after the scan,
+    // GPU never idles on the host.  The host then waits for N only (copied right after the depth sort,
     // early in the queue) while the GPU keeps working, or does not wait at all (GSR_FLAG_ASYNC).
-    cudaEvent_t ev = nullptr;
+    static thread_local cudaEvent_t ev = nullptr;   // one event per host thread, reused (no create / destroy per view)
     if (!async) {
       if (int rc = fetch_result()) return rc;
-      GSR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create");
+      if (!ev) GSR_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event create");
       GSR_CUDA(cudaEventRecord(ev, s), "event record");
     }
-    if (int rc = bin_and_blend(capacity_hint)) { if (ev) cudaEventDestroy(ev); return rc; }
+    if (int rc = bin_and_blend(s, &w, 1, P, flags, false)) return rc;
     if (async) {
       if (int rc = fetch_result()) return rc;   // includes the overflow bit set by the duplicate kernel
       return 0;                                 // caller checks result[0] <= capacity_hint && result[1] == 0 after a sync
     }
     GSR_CUDA(cudaEventSynchronize(ev), "sync num_rendered");
-    cudaEventDestroy(ev);
     N = result[0];  // full 64-bit sum: beyond the limit is rejected below
     if ((int32_t)(result[1] & 0xffffffff) != 0) return fail(GSR_E_PREFILTERED, "gsr_forward: point filtered by culling but 'prefiltered' was set");
     if (N >= n_limit) return fail(GSR_E_OVERFLOW, "gsr_forward: too many (tile, Gaussian) instances (limit 2^32 - 65536; 2^30 with GSR_FLAG_BINNING_KEY64 / GSR_FLAG_REFERENCE)");
     if (N > capacity_hint) {  // rare: the hint was too small, redo binning + blend at the exact size
       GSR_CUDA(cudaMemsetAsync(status + 1, 0, 4, s), "clear overflow");
-      if (int rc = bin_and_blend(N)) return rc;
+      if (int rc = alloc_binning(N)) return rc;
+      if (int rc = bin_and_blend(s, &w, 1, P, flags, true)) return rc;
     }
     *num_rendered_host = N;
     return 0;
@@ -539,7 +752,62 @@ int gsr_forward(void* stream, gsr_alloc_fn geom_alloc, void* geom_user, gsr_allo
     if (N >= n_limit) return fail(GSR_E_OVERFLOW, "gsr_forward: too many (tile, Gaussian) instances (limit 2^32 - 65536; 2^30 with GSR_FLAG_BINNING_KEY64 / GSR_FLAG_REFERENCE)");
   }
   *num_rendered_host = N;
-  return bin_and_blend(N);
+  if (int rc = alloc_binning(N)) return rc;
+  return bin_and_blend(s, &w, 1, P, flags, true);
+}
+
+int gsr_forward_views(void* stream, int P, int D, int M, const float* means3D, const float* shs,
+                      const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,
+                      const float* rotations, const float* cov3D_precomp, int prefiltered,
+                      const gsr_view_forward* views_host, int n_views, uint32_t flags) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (P < 0 || D < 0 || D > 3 || n_views < 0) return fail(GSR_E_INVALID, "gsr_forward_views: bad P/degree/n_views");
+  if (n_views == 0) return 0;
+  if (!views_host) return fail(GSR_E_INVALID, "gsr_forward_views: null views");
+  if (flags & (GSR_FLAG_BINNING_KEY64 | GSR_FLAG_REFERENCE))
+    return fail(GSR_E_INVALID, "gsr_forward_views: the batched forward uses the two-level binning (no GSR_FLAG_BINNING_KEY64 / GSR_FLAG_REFERENCE)");
+  if (P > 0) {
+    if (!means3D || !opacities) return fail(GSR_E_INVALID, "gsr_forward_views: null means3D/opacities");
+    if ((shs == nullptr) == (colors_precomp == nullptr))
+      return fail(GSR_E_INVALID, "gsr_forward_views: provide exactly one of shs / colors_precomp");
+    if (((scales == nullptr) || (rotations == nullptr)) == (cov3D_precomp == nullptr))
+      return fail(GSR_E_INVALID, "gsr_forward_views: provide exactly one of (scales, rotations) / cov3D_precomp");
+    if (shs && (D + 1) * (D + 1) > M) return fail(GSR_E_INVALID, "gsr_forward_views: sh degree needs more coefficients than M");
+    if (rotations && (reinterpret_cast<uintptr_t>(rotations) & 15)) return fail(GSR_E_INVALID, "gsr_forward_views: rotations must be 16-byte aligned");
+  }
+  const GeomLayout gl = geom_layout(P, flags);
+  std::vector<FwdView> vs((size_t)n_views);
+  for (int k = 0; k < n_views; k++) {
+    const gsr_view_forward& in = views_host[k];
+    if (in.width <= 0 || in.height <= 0 || !in.background || !in.viewmatrix || !in.projmatrix || !in.cam_pos ||
+        !in.out_color || !in.out_depth || !in.geom_buffer || !in.binning_buffer || !in.image_buffer || !in.result_host ||
+        (P > 0 && !in.radii) || in.capacity <= 0 || in.capacity >= GSR_MAX_INSTANCES)
+      return fail(GSR_E_INVALID, "gsr_forward_views: bad view descriptor (null pointer, size, or capacity outside (0, GSR_MAX_INSTANCES))");
+    if ((reinterpret_cast<uintptr_t>(in.geom_buffer) | reinterpret_cast<uintptr_t>(in.binning_buffer) |
+         reinterpret_cast<uintptr_t>(in.image_buffer)) & 255)
+      return fail(GSR_E_INVALID, "gsr_forward_views: buffers must be 256-byte aligned");
+    vs[(size_t)k] = make_fwd_view(in.width, in.height, in.viewmatrix, in.projmatrix, in.cam_pos, in.tan_fovx, in.tan_fovy,
+                                  scale_modifier, in.background, in.out_color, in.out_depth, in.radii, in.geom_buffer,
+                                  in.image_buffer);
+    vs[(size_t)k].bin = in.binning_buffer;
+    vs[(size_t)k].cap = in.capacity;
+    in.result_host[0] = 0;
+    in.result_host[1] = 0;
+  }
+  for (int k0 = 0; k0 < n_views; k0 += GSR_MAX_BATCH) {
+    const int nv = std::min(GSR_MAX_BATCH, n_views - k0);
+    if (int rc = front_end(s, vs.data() + k0, nv, P, D, M, means3D, shs, colors_precomp, opacities, scales, scale_modifier,
+                           rotations, cov3D_precomp, prefiltered, flags, true))
+      return rc;
+    if (int rc = bin_and_blend(s, vs.data() + k0, nv, P, flags, false)) return rc;
+  }
+  if (P > 0)
+    for (int k = 0; k < n_views; k++) {   // N and the status words (trap, overflow) of every view, asynchronously
+      const int32_t* status = status_of(vs[(size_t)k], gl);
+      GSR_CUDA(cudaMemcpyAsync(views_host[k].result_host, status + 2, 8, cudaMemcpyDeviceToHost, s), "memcpy num_rendered");
+      GSR_CUDA(cudaMemcpyAsync(views_host[k].result_host + 1, status, 8, cudaMemcpyDeviceToHost, s), "memcpy status");
+    }
+  return 0;
 }
 
 int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const float* background,
@@ -583,12 +851,15 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
   PROF(8);
   // always launched: the tile ranges, not num_rendered, bound the work (num_rendered may be unknown
   // to the host after an asynchronous forward)
-  if (refstruct(flags))
+  if (refstruct(flags)) {
     GSR_CUDA(launch_ref_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
                                        dL_dpix, gacc), "blend backward (reference structure)");
-  else
-    GSR_CUDA(launch_blend_backward(s, width, height, ranges, point_list, rec, background, final_T, n_contrib,
-                                   dL_dpix, gacc, (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
+  } else {
+    BlendBwdView bv{};
+    bv.W = width; bv.H = height; bv.ranges = ranges; bv.point_list = point_list; bv.rec = rec; bv.bg = background;
+    bv.final_T = final_T; bv.n_contrib = n_contrib; bv.dL_dpix = dL_dpix; bv.gacc = gacc;
+    GSR_CUDA(launch_blend_backward(s, &bv, 1, (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
+  }
   PROF(9);
   GSR_CUDA(launch_geom_backward(s, P, D, M, means3D, radii, shs, clamped, scales, rotations, cov3D_precomp,
                                 colors_precomp, cam, rec, gacc, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
@@ -601,33 +872,58 @@ int gsr_backward(void* stream, int P, int D, int M, int64_t num_rendered, const 
 int gsr_backward_blend(void* stream, int P, const float* background, int width, int height,
                        const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
                        const float* dL_dpix, char* scratch, size_t scratch_bytes, uint32_t flags) {
+  gsr_view_backward v{};
+  v.background = background; v.width = width; v.height = height; v.geom_buffer = geom_buffer;
+  v.binning_buffer = binning_buffer; v.image_buffer = image_buffer; v.dL_dpix = dL_dpix; v.scratch = scratch;
+  v.scratch_bytes = scratch_bytes;
+  return gsr_backward_blend_views(stream, P, &v, 1, flags);
+}
+
+int gsr_backward_blend_views(void* stream, int P, const gsr_view_backward* views_host, int n_views, uint32_t flags) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (P < 0 || width <= 0 || height <= 0) return fail(GSR_E_INVALID, "gsr_backward_blend: bad P/width/height");
-  if (P == 0) return 0;
-  if (!background || !geom_buffer || !binning_buffer || !image_buffer || !dL_dpix || !scratch)
-    return fail(GSR_E_INVALID, "gsr_backward_blend: null argument");
-  if (scratch_bytes < gsr_backward_scratch_bytes(P) || (reinterpret_cast<uintptr_t>(scratch) & 15))
-    return fail(GSR_E_INVALID, "gsr_backward_blend: scratch too small or misaligned");
+  if (P < 0 || n_views < 0) return fail(GSR_E_INVALID, "gsr_backward_blend: bad P/n_views");
+  if (P == 0 || n_views == 0) return 0;
+  if (!views_host) return fail(GSR_E_INVALID, "gsr_backward_blend: null views");
   const GeomLayout gl = geom_layout(P, flags);
-  const ImageLayout il = image_layout(width, height);
-  const BinningLayout bl = binning_layout(0, width, height, flags);  // point_list sits at offset 0 for any capacity
+  std::vector<BlendBwdView> bv((size_t)n_views);
+  std::vector<ZeroRegion> z((size_t)n_views);
+  for (int k = 0; k < n_views; k++) {
+    const gsr_view_backward& in = views_host[k];
+    if (in.width <= 0 || in.height <= 0) return fail(GSR_E_INVALID, "gsr_backward_blend: bad width/height");
+    if (!in.background || !in.geom_buffer || !in.binning_buffer || !in.image_buffer || !in.dL_dpix || !in.scratch)
+      return fail(GSR_E_INVALID, "gsr_backward_blend: null argument");
+    if (in.scratch_bytes < gsr_backward_scratch_bytes(P) || (reinterpret_cast<uintptr_t>(in.scratch) & 15))
+      return fail(GSR_E_INVALID, "gsr_backward_blend: scratch too small or misaligned");
+    const ImageLayout il = image_layout(in.width, in.height);
+    BlendBwdView& q = bv[(size_t)k];
+    q.W = in.width;
+    q.H = in.height;
+    q.ranges = reinterpret_cast<const uint2*>(in.image_buffer + il.ranges);
+    q.point_list = reinterpret_cast<const uint32_t*>(in.binning_buffer);   // point_list sits at offset 0 for any capacity
+    q.rec = reinterpret_cast<const float4*>(in.geom_buffer + gl.rec);
+    q.bg = in.background;
+    q.final_T = reinterpret_cast<const float*>(in.image_buffer + il.final_T);
+    q.n_contrib = reinterpret_cast<const uint32_t*>(in.image_buffer + il.n_contrib);
+    q.dL_dpix = in.dL_dpix;
+    q.gacc = reinterpret_cast<float*>(in.scratch);
+    z[(size_t)k] = {in.scratch, (size_t)P * 48};
+  }
   PROF(7);
-  GSR_CUDA(cudaMemsetAsync(scratch, 0, (size_t)P * 48, s), "memset accumulator");
-  PROF(8);
-  if (refstruct(flags))
-    GSR_CUDA(launch_ref_blend_backward(s, width, height, reinterpret_cast<const uint2*>(image_buffer + il.ranges),
-                                       reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list),
-                                       reinterpret_cast<const float4*>(geom_buffer + gl.rec), background,
-                                       reinterpret_cast<const float*>(image_buffer + il.final_T),
-                                       reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib), dL_dpix,
-                                       reinterpret_cast<float*>(scratch)), "blend backward (reference structure)");
+  if (n_views == 1)
+    GSR_CUDA(cudaMemsetAsync(z[0].ptr, 0, z[0].bytes, s), "memset accumulator");
   else
-    GSR_CUDA(launch_blend_backward(s, width, height, reinterpret_cast<const uint2*>(image_buffer + il.ranges),
-                                   reinterpret_cast<const uint32_t*>(binning_buffer + bl.point_list),
-                                   reinterpret_cast<const float4*>(geom_buffer + gl.rec), background,
-                                   reinterpret_cast<const float*>(image_buffer + il.final_T),
-                                   reinterpret_cast<const uint32_t*>(image_buffer + il.n_contrib), dL_dpix,
-                                   reinterpret_cast<float*>(scratch), (flags & GSR_FLAG_PRECISE) != 0), "blend backward");
+    GSR_CUDA(launch_zero_regions(s, z.data(), n_views), "clear accumulators");
+  PROF(8);
+  if (refstruct(flags)) {
+    for (int k = 0; k < n_views; k++)
+      GSR_CUDA(launch_ref_blend_backward(s, bv[(size_t)k].W, bv[(size_t)k].H, bv[(size_t)k].ranges, bv[(size_t)k].point_list,
+                                         bv[(size_t)k].rec, bv[(size_t)k].bg, bv[(size_t)k].final_T, bv[(size_t)k].n_contrib,
+                                         bv[(size_t)k].dL_dpix, bv[(size_t)k].gacc), "blend backward (reference structure)");
+  } else {
+    for (int k0 = 0; k0 < n_views; k0 += GSR_MAX_BATCH)
+      GSR_CUDA(launch_blend_backward(s, bv.data() + k0, std::min(GSR_MAX_BATCH, n_views - k0), (flags & GSR_FLAG_PRECISE) != 0),
+               "blend backward");
+  }
   PROF(-1);
   return 0;
 }

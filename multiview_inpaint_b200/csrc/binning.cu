@@ -95,17 +95,36 @@ __device__ __forceinline__ uint32_t tile_of_slot(uint32_t q, uint32_t xy0, uint3
   return ((xy0 >> 16) + row) * gx + (xy0 & 0xffffu) + (q - row * w);
 }
 
+bool g_bin_count_atomics = true;
+struct BinArgs {
+  BinView v[GSR_MAX_BATCH];
+  bool count;
+};
+
+// blockIdx.y = view.  Walks the V = status[5] visible Gaussians of `order` (depth order, culled ones were dropped by
+// the depth sort's compacting first pass); the grid is sized for P and surplus CTAs retire before taking a ticket.
 __global__ void __launch_bounds__(BE_THREADS)
-bin_expand_kernel(int P, const uint32_t* __restrict__ order, const ushort4* __restrict__ rects,
-                  uint32_t* __restrict__ offsets, uint32_t* __restrict__ tile_keys,
-                  uint32_t* __restrict__ vals, uint32_t cap, uint32_t* __restrict__ tile_count, int gx,
-                  volatile unsigned long long* lb_status, uint32_t* ticket, int32_t* __restrict__ status,
-                  uint4* __restrict__ big_items, uint32_t big_cap) {
+bin_expand_kernel(const __grid_constant__ BinArgs args) {
+  const BinView& a = args.v[blockIdx.y];
+  const int P = (int)min((uint32_t)a.status[5], (uint32_t)a.P);
+  if ((int64_t)blockIdx.x * BE_TILE >= P) return;
+  const uint32_t* __restrict__ order = a.order;
+  const ushort4* __restrict__ rects = a.rects;
+  uint32_t* __restrict__ offsets = a.offsets;
+  uint32_t* __restrict__ tile_keys = a.tile_keys;
+  uint32_t* __restrict__ vals = a.vals;
+  const uint32_t cap = a.cap;
+  uint32_t* __restrict__ tile_count = a.tile_count;
+  const int gx = a.gx;
+  volatile unsigned long long* lb_status = a.lb_status;
+  int32_t* __restrict__ status = a.status;
+  uint4* __restrict__ big_items = a.big_items;
+  const uint32_t big_cap = a.big_cap;
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_warp[BE_THREADS / 32];
   __shared__ uint32_t s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
   const int64_t kbase = (int64_t)tile * BE_TILE + warp * (32 * BE_ROUNDS) + lane;
@@ -233,7 +252,7 @@ bin_expand_kernel(int P, const uint32_t* __restrict__ order, const ushort4* __re
         const uint32_t t = tile_of_slot(q, o_xy, o_w, o_magic, (uint32_t)gx);
         tile_keys[off] = t;
         vals[off] = o_id;
-        atomicAdd(tile_count + t, 1u);
+        if (args.count) atomicAdd(tile_count + t, 1u);
       }
     }
     base += total;
@@ -242,10 +261,15 @@ bin_expand_kernel(int P, const uint32_t* __restrict__ order, const ushort4* __re
 
 // Work-list items {id, x0 | y0 << 16, w | h << 16, first output slot}: one warp per item, coalesced.
 __global__ void __launch_bounds__(256)
-bin_expand_big_kernel(const uint4* __restrict__ big_items, const int32_t* __restrict__ status, uint32_t big_cap,
-                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ vals, uint32_t cap,
-                      uint32_t* __restrict__ tile_count, int gx) {
-  const uint32_t n_items = min((uint32_t)status[4], big_cap);
+bin_expand_big_kernel(const __grid_constant__ BinArgs args) {
+  const BinView& a = args.v[blockIdx.y];
+  const uint4* __restrict__ big_items = a.big_items;
+  uint32_t* __restrict__ tile_keys = a.tile_keys;
+  uint32_t* __restrict__ vals = a.vals;
+  uint32_t* __restrict__ tile_count = a.tile_count;
+  const uint32_t cap = a.cap;
+  const int gx = a.gx;
+  const uint32_t n_items = min((uint32_t)a.status[4], a.big_cap);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
   for (uint32_t it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n_items; it += n_warps) {
@@ -267,9 +291,16 @@ bin_expand_big_kernel(const uint4* __restrict__ big_items, const int32_t* __rest
 // One CTA: ranges = exclusive scan of the per-tile counts ((0,0) for untouched tiles, as the
 // reference's memset leaves them), and the tile sort's per-digit exclusive bases (what the onesweep
 // histogram + scan kernels would produce from the keys).
+struct PrepArgs {
+  PrepView v[GSR_MAX_BATCH];
+};
 __global__ void __launch_bounds__(1024)
-tile_prepare_kernel(int G, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
-                    int passes, int end_bit, uint32_t* __restrict__ hist) {
+tile_prepare_kernel(const __grid_constant__ PrepArgs args) {
+  const PrepView& a = args.v[blockIdx.x];
+  const int G = a.G, passes = a.passes, end_bit = a.end_bit;
+  const uint32_t* __restrict__ tile_count = a.tile_count;
+  uint2* __restrict__ ranges = a.ranges;
+  uint32_t* __restrict__ hist = a.hist;
   __shared__ uint32_t s_h[4 * 256];
   __shared__ uint32_t s_w[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -371,36 +402,83 @@ cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order,
   count_launch();
   return cudaGetLastError();
 }
-cudaError_t launch_bin_expand(cudaStream_t s, int P, const uint32_t* order, const ushort4* rects, uint32_t* offsets,
-                              uint32_t* tile_keys, uint32_t* vals, int64_t cap, uint32_t* tile_count, int G,
-                              int grid_x, char* scan_temp, int32_t* status, uint4* big_items, int64_t big_cap) {
-  if (P == 0) return cudaSuccess;
-  const int64_t tiles = ((int64_t)P + BE_TILE - 1) / BE_TILE;
-  uint32_t* ticket = reinterpret_cast<uint32_t*>(scan_temp);
-  auto* lb = reinterpret_cast<unsigned long long*>(scan_temp + align_up(16));
-  cudaError_t e = cudaMemsetAsync(scan_temp, 0, scan_temp_bytes(P), s);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(tile_count, 0, (size_t)G * 4, s);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(status + 4, 0, 4, s);  // work-list length
-  if (e != cudaSuccess) return e;
-  bin_expand_kernel<<<(unsigned)tiles, BE_THREADS, 0, s>>>(P, order, rects, offsets, tile_keys, vals, (uint32_t)cap,
-                                                           tile_count, grid_x, lb, ticket, status, big_items,
-                                                           (uint32_t)big_cap);
-  bin_expand_big_kernel<<<148 * 4, 256, 0, s>>>(big_items, status, (uint32_t)big_cap, tile_keys, vals, (uint32_t)cap,
-                                                tile_count, grid_x);
+// capacity of the work list for `cap` instances: every queued rect has more than BE_BIG tiles
+int64_t bin_big_capacity(int64_t cap) { return cap / (BE_BIG + 1) + 1; }
+
+// The caller has zeroed every view's scan temp (ticket + look-back words), tile_count and status[4].
+cudaError_t launch_bin_expand(cudaStream_t s, const BinView* views, int nv) {
+  if (nv <= 0) return cudaSuccess;
+  if (nv > GSR_MAX_BATCH) return cudaErrorInvalidValue;
+  BinArgs args{};
+  args.count = g_bin_count_atomics;
+  int max_p = 0;
+  for (int k = 0; k < nv; k++) {
+    args.v[k] = views[k];
+    max_p = views[k].P > max_p ? views[k].P : max_p;
+  }
+  if (max_p == 0) return cudaSuccess;
+  const int64_t tiles = ((int64_t)max_p + BE_TILE - 1) / BE_TILE;
+  bin_expand_kernel<<<dim3((unsigned)tiles, (unsigned)nv), BE_THREADS, 0, s>>>(args);
+  const int big_blocks = nv >= 4 ? 148 : 148 * 4 / nv;
+  bin_expand_big_kernel<<<dim3(big_blocks, (unsigned)nv), 256, 0, s>>>(args);
   count_launch(2);
   return cudaGetLastError();
 }
-// capacity of the work list for `cap` instances: every queued rect has more than BE_BIG tiles
-int64_t bin_big_capacity(int64_t cap) { return cap / (BE_BIG + 1) + 1; }
-cudaError_t launch_tile_prepare(cudaStream_t s, int G, const uint32_t* tile_count, uint2* ranges, int end_bit,
-                                uint32_t* hist) {
-  const int passes = (end_bit + 7) / 8;
-  if (passes > 4) return cudaErrorInvalidValue;
-  tile_prepare_kernel<<<1, 1024, 0, s>>>(G, tile_count, ranges, passes, end_bit, hist);
+cudaError_t launch_tile_prepare(cudaStream_t s, const PrepView* views, int nv) {
+  if (nv <= 0) return cudaSuccess;
+  if (nv > GSR_MAX_BATCH) return cudaErrorInvalidValue;
+  PrepArgs args{};
+  for (int k = 0; k < nv; k++) {
+    args.v[k] = views[k];
+    args.v[k].passes = (views[k].end_bit + 7) / 8;
+    if (args.v[k].passes > 4) return cudaErrorInvalidValue;
+  }
+  tile_prepare_kernel<<<nv, 1024, 0, s>>>(args);
   count_launch();
   return cudaGetLastError();
+}
+
+// ---- one launch that zeroes every counter / look-back array / histogram a batched forward needs --------------------
+constexpr int ZERO_MAX_REGIONS = 4 * GSR_MAX_BATCH;
+struct ZeroArgs {
+  uint32_t* ptr[ZERO_MAX_REGIONS];
+  unsigned long long words[ZERO_MAX_REGIONS];
+};
+__global__ void __launch_bounds__(256) zero_regions_kernel(const __grid_constant__ ZeroArgs args) {
+  uint32_t* __restrict__ p = args.ptr[blockIdx.y];
+  const unsigned long long words = args.words[blockIdx.y];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const unsigned long long quads = words >> 2;
+    for (unsigned long long i = t; i < quads; i += stride) reinterpret_cast<uint4*>(p)[i] = make_uint4(0, 0, 0, 0);
+    for (unsigned long long i = (quads << 2) + t; i < words; i += stride) p[i] = 0;
+  } else {
+    for (unsigned long long i = t; i < words; i += stride) p[i] = 0;
+  }
+}
+cudaError_t launch_zero_regions(cudaStream_t s, const ZeroRegion* regions, int n) {
+  for (int base = 0; base < n; base += ZERO_MAX_REGIONS) {
+    ZeroArgs args{};
+    int m = 0;
+    unsigned long long max_words = 0;
+    for (int k = base; k < n && m < ZERO_MAX_REGIONS; k++) {
+      if (!regions[k].ptr || regions[k].bytes == 0) continue;
+      args.ptr[m] = reinterpret_cast<uint32_t*>(regions[k].ptr);
+      args.words[m] = regions[k].bytes / 4;
+      max_words = args.words[m] > max_words ? args.words[m] : max_words;
+      m++;
+    }
+    if (m == 0) continue;
+    unsigned long long blocks = (max_words / 4 + 255) / 256;
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
+    zero_regions_kernel<<<dim3((unsigned)blocks, (unsigned)m), 256, 0, s>>>(args);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t N, const uint32_t* n_dev, const uint64_t* keys, int G, uint2* ranges) {
   cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)G * sizeof(uint2), s);

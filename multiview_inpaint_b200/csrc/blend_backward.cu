@@ -58,13 +58,25 @@ __device__ __forceinline__ float warp_transpose_reduce9(float v0, float v1, floa
   return k;
 }
 
+struct BlendBwdArgs {
+  BlendBwdView v[GSR_MAX_BATCH];
+};
+
+// blockIdx.y = view of a batched step
 template <bool PRECISE>
 __global__ void __launch_bounds__(256)
-blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
-                      const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
-                      const float* __restrict__ bg, const float* __restrict__ final_T,
-                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
-                      float* __restrict__ gacc) {
+blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
+  const BlendBwdView& a = args.v[blockIdx.y];
+  const int W = a.W, H = a.H, grid_x = a.grid_x;
+  if ((int)blockIdx.x >= a.G) return;
+  const uint2* __restrict__ ranges = a.ranges;
+  const uint32_t* __restrict__ point_list = a.point_list;
+  const float4* __restrict__ rec = a.rec;
+  const float* __restrict__ bg = a.bg;
+  const float* __restrict__ final_T = a.final_T;
+  const uint32_t* __restrict__ n_contrib = a.n_contrib;
+  const float* __restrict__ dL_dpix = a.dL_dpix;
+  float* __restrict__ gacc = a.gacc;
   __shared__ __align__(16) unsigned char s_entries[BLEND_BATCH * ENTRY_BYTES];
   __shared__ uint32_t s_mask_arr[64];
   __shared__ uint32_t s_wmax[8];
@@ -196,18 +208,22 @@ blend_backward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges
   }
 }
 
-cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ranges,
-                                  const uint32_t* point_list, const float4* rec, const float* bg,
-                                  const float* final_T, const uint32_t* n_contrib,
-                                  const float* dL_dpix, float* gacc, bool precise) {
-  const int gx = cdiv(W, TILE_X), gy = cdiv(H, TILE_Y);
-  if (gx * gy == 0) return cudaSuccess;
+cudaError_t launch_blend_backward(cudaStream_t s, const BlendBwdView* views, int nv, bool precise) {
+  if (nv <= 0) return cudaSuccess;
+  if (nv > GSR_MAX_BATCH) return cudaErrorInvalidValue;
+  BlendBwdArgs args{};
+  int max_g = 0;
+  for (int k = 0; k < nv; k++) {
+    args.v[k] = views[k];
+    args.v[k].grid_x = cdiv(views[k].W, TILE_X);
+    args.v[k].G = args.v[k].grid_x * cdiv(views[k].H, TILE_Y);
+    max_g = args.v[k].G > max_g ? args.v[k].G : max_g;
+  }
+  if (max_g == 0) return cudaSuccess;
   if (precise)
-    blend_backward_kernel<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
-                                                        n_contrib, dL_dpix, gacc);
+    blend_backward_kernel<true><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
   else
-    blend_backward_kernel<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, bg, final_T,
-                                                         n_contrib, dL_dpix, gacc);
+    blend_backward_kernel<false><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
   count_launch();
   return cudaGetLastError();
 }

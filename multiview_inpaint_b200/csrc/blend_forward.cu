@@ -23,13 +23,26 @@
 
 namespace gsr {
 
+struct BlendFwdArgs {
+  BlendFwdView v[GSR_MAX_BATCH];
+};
+
+// blockIdx.y = view of a batched step (one launch blends every view's tiles: no launch gaps, one tail)
 template <bool PRECISE>
 __global__ void __launch_bounds__(256)
-blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
-                     const uint32_t* __restrict__ point_list, const float4* __restrict__ rec,
-                     const float* __restrict__ depths, const float* __restrict__ bg,
-                     float* __restrict__ out_color, float* __restrict__ out_depth,
-                     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib) {
+blend_forward_kernel(const __grid_constant__ BlendFwdArgs args) {
+  const BlendFwdView& a = args.v[blockIdx.y];
+  const int W = a.W, H = a.H, grid_x = a.grid_x;
+  if ((int)blockIdx.x >= a.G) return;  // views of different sizes share the grid
+  const uint2* __restrict__ ranges = a.ranges;
+  const uint32_t* __restrict__ point_list = a.point_list;
+  const float4* __restrict__ rec = a.rec;
+  const float* __restrict__ depths = a.depths;
+  const float* __restrict__ bg = a.bg;
+  float* __restrict__ out_color = a.out_color;
+  float* __restrict__ out_depth = a.out_depth;
+  float* __restrict__ final_T = a.final_T;
+  uint32_t* __restrict__ n_contrib = a.n_contrib;
   __shared__ __align__(16) unsigned char s_entries[BLEND_BATCH * ENTRY_BYTES];
   __shared__ uint32_t s_mask_arr[64];  // [target warp][staging warp]
   const uint32_t s_ent = pin_reg((uint32_t)__cvta_generic_to_shared(s_entries));
@@ -119,18 +132,22 @@ blend_forward_kernel(int W, int H, int grid_x, const uint2* __restrict__ ranges,
   }
 }
 
-cudaError_t launch_blend_forward(cudaStream_t s, int W, int H, const uint2* ranges,
-                                 const uint32_t* point_list, const float4* rec, const float* depths,
-                                 const float* bg, float* out_color, float* out_depth,
-                                 float* final_T, uint32_t* n_contrib, bool precise) {
-  const int gx = cdiv(W, TILE_X), gy = cdiv(H, TILE_Y);
-  if (gx * gy == 0) return cudaSuccess;
+cudaError_t launch_blend_forward(cudaStream_t s, const BlendFwdView* views, int nv, bool precise) {
+  if (nv <= 0) return cudaSuccess;
+  if (nv > GSR_MAX_BATCH) return cudaErrorInvalidValue;
+  BlendFwdArgs args{};
+  int max_g = 0;
+  for (int k = 0; k < nv; k++) {
+    args.v[k] = views[k];
+    args.v[k].grid_x = cdiv(views[k].W, TILE_X);
+    args.v[k].G = args.v[k].grid_x * cdiv(views[k].H, TILE_Y);
+    max_g = args.v[k].G > max_g ? args.v[k].G : max_g;
+  }
+  if (max_g == 0) return cudaSuccess;
   if (precise)
-    blend_forward_kernel<true><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, depths, bg,
-                                                       out_color, out_depth, final_T, n_contrib);
+    blend_forward_kernel<true><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
   else
-    blend_forward_kernel<false><<<gx * gy, 256, 0, s>>>(W, H, gx, ranges, point_list, rec, depths, bg,
-                                                        out_color, out_depth, final_T, n_contrib);
+    blend_forward_kernel<false><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
   count_launch();
   return cudaGetLastError();
 }

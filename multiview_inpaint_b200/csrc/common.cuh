@@ -93,14 +93,19 @@ inline int ceil_log2(uint32_t n) {
   return b;
 }
 
+// Views (independent segments) one batched launch covers: every front-end stage of a multi-view step is ONE launch
+// over all views of the rank (blockIdx.y = view, or view-interleaved CTAs where the views share inputs).
+constexpr int GSR_MAX_BATCH = 8;
+
 // ---- private layout of the opaque scratch buffers (public view: gsr_layout) -------------------
 struct GeomLayout {
   size_t rec, depths, clamped, tiles_touched, point_offsets;
   size_t depth_keys, order, depth_keys_alt, order_alt;    // two-level binning only (sorted result
                                                           // lands back in depth_keys / order)
   size_t rects;                                           // two-level only: ushort4[P] tile rects
-  size_t status;                                          // int32[8]: trap, overflow, N (u64), work-list length
-  size_t temp, temp_bytes;                                // scan + depth-sort temp
+  size_t status;                                          // int32[8]: trap, overflow, N (u64), work-list length, V
+  size_t scan_temp, scan_temp_bytes;                      // ticket + look-back words of the scans (right after status)
+  size_t temp, temp_bytes;                                // depth-sort temp (two-level binning only)
   size_t bytes;
 };
 struct ImageLayout {
@@ -118,16 +123,34 @@ GeomLayout geom_layout(int P, uint32_t flags);
 ImageLayout image_layout(int W, int H);
 BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags);
 
+// experiment switches behind gsr_debug_set (never changed by the product path)
+extern int g_rs_rank_mode;         // scan_sort.cu: 0 match_any, 1 ballots (default), 2 shared atomicOr
+extern bool g_bin_count_atomics;   // binning.cu: false drops the per-instance tile_count atomics (WRONG results: timing only)
+
 // ---- host launchers (one per translation unit) --------------------------------------------------
 void set_error(const char* msg);
 void count_launch(int n = 1);  // bumps the counter behind gsr_kernel_launches()
 
+// K1 outputs of one view.  status: int32[8] = {trap, overflow, N lo, N hi, work-list length, V (visible), -, -}
+struct PreView {
+  Camera cam;
+  int32_t* radii;
+  float4* rec;
+  float* depths;
+  uint8_t* clamped;
+  uint32_t* tiles_touched;
+  uint32_t* depth_keys;  // two-level binning only (else NULL)
+  ushort4* rects;        // two-level binning only (else NULL)
+  int32_t* status;
+};
+// One launch for all views: CTA b works on view b % nv, Gaussians [256 (b / nv), +256) -- the CTAs of the views
+// of one Gaussian chunk are co-resident, so the (P,M,3) SH rows and the other parameters come from HBM once and
+// from L2 for the other views.
 cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* means3D,
                               const float* scales, const float* rotations, const float* opacities,
                               const float* shs, const float* cov3D_precomp,
-                              const float* colors_precomp, const Camera& cam, int prefiltered,
-                              int32_t* radii, float4* rec, float* depths, uint8_t* clamped,
-                              uint32_t* tiles_touched, uint32_t* depth_keys, ushort4* rects, int32_t* status);
+                              const float* colors_precomp, float scale_modifier, int prefiltered,
+                              const PreView* views, int nv);
 cudaError_t launch_mark_visible(cudaStream_t s, int P, const float* means3D, const float* view,
                                 uint8_t* present);
 
@@ -144,6 +167,24 @@ cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_d
                                   uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp,
                                   bool have_bases = false);
 inline uint32_t* sort_hist_ptr(char* temp) { return reinterpret_cast<uint32_t*>(temp); }
+// One independent array of a batched (segmented) sort: blockIdx.y = segment.
+template <typename KeyT>
+struct SortSeg {
+  int64_t n;                      // capacity (sizes the grid and the temp storage); element count if n_dev == NULL
+  const uint32_t* n_dev;          // element count on the device: min(*n_dev, n)
+  const uint32_t* n_dev_compact;  // compact sorts: the number of keys != ~0, read by the passes after the first
+  const KeyT* keys_in;
+  const uint32_t* vals_in;        // NULL: values are the element indices
+  KeyT* keys_out;
+  uint32_t* vals_out;
+  KeyT* keys_alt;
+  uint32_t* vals_alt;
+  char* temp;                     // sort_temp_bytes(n, sizeof(KeyT), end_bit)
+};
+// compact: the first pass drops keys equal to 0xFFFFFFFF (culled Gaussians) -- the output holds *n_dev_compact pairs
+// temp_zeroed: the caller has already cleared every segment's temp (launch_zero_regions) -- no memsets here
+cudaError_t launch_sort_pairs_u32_batched(cudaStream_t s, const SortSeg<uint32_t>* segs, int nseg, int end_bit,
+                                          bool have_bases, bool compact, bool temp_zeroed);
 cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
@@ -156,26 +197,67 @@ cudaError_t launch_duplicate_key64(cudaStream_t s, int P, const float4* rec, con
 cudaError_t launch_duplicate_tiles(cudaStream_t s, int P, const uint32_t* order, const float4* rec,
                                    const uint32_t* offsets, const int32_t* radii, int grid_x,
                                    int grid_y, uint32_t* tile_keys, uint32_t* vals, int64_t cap, int32_t* status);
-// Two-level scheme: fused scan (offsets in depth order) + load-balanced expansion + per-tile counts;
-// `scan_temp` is the scan's temp (scan_temp_bytes(P)).  Then ranges + the tile sort's digit bases.
-cudaError_t launch_bin_expand(cudaStream_t s, int P, const uint32_t* order, const ushort4* rects, uint32_t* offsets,
-                              uint32_t* tile_keys, uint32_t* vals, int64_t cap, uint32_t* tile_count, int G,
-                              int grid_x, char* scan_temp, int32_t* status, uint4* big_items, int64_t big_cap);
+// Two-level scheme: fused scan (offsets in depth order) + load-balanced expansion + per-tile counts, one launch for
+// all views (blockIdx.y = view).  Then ranges + the tile sort's digit bases.
+struct BinView {
+  const uint32_t* order;           // Gaussian ids in depth order, V = status[5] entries
+  const ushort4* rects;            // [P] tile rects by Gaussian id
+  uint32_t* offsets;               // [P] out: inclusive instance offsets in depth order (first V entries)
+  uint32_t* tile_keys;             // [cap] out
+  uint32_t* vals;                  // [cap] out
+  uint32_t cap;
+  uint32_t* tile_count;            // [G], zeroed by the caller
+  int gx;
+  unsigned long long* lb_status;   // look-back words, zeroed by the caller (scan_temp + 256)
+  uint32_t* ticket;                // zeroed by the caller (scan_temp)
+  int32_t* status;                 // the view's status block; status[4] (work-list length) zeroed by the caller
+  uint4* big_items;
+  uint32_t big_cap;
+  int P;                           // capacity of `order`
+};
+struct PrepView {
+  int G;
+  const uint32_t* tile_count;
+  uint2* ranges;
+  int passes, end_bit;
+  uint32_t* hist;
+};
+cudaError_t launch_bin_expand(cudaStream_t s, const BinView* views, int nv);
 int64_t bin_big_capacity(int64_t cap);
-cudaError_t launch_tile_prepare(cudaStream_t s, int G, const uint32_t* tile_count, uint2* ranges, int end_bit,
-                                uint32_t* hist);
+cudaError_t launch_tile_prepare(cudaStream_t s, const PrepView* views, int nv);
+// Zeroes up to 4 * GSR_MAX_BATCH regions (4-byte aligned, sizes multiples of 4) with ONE launch.
+struct ZeroRegion { void* ptr; size_t bytes; };
+cudaError_t launch_zero_regions(cudaStream_t s, const ZeroRegion* regions, int n);
 // N = min(*n_dev, cap) when n_dev is given, else cap
 cudaError_t launch_tile_ranges_u64(cudaStream_t s, int64_t cap, const uint32_t* n_dev, const uint64_t* keys, int G, uint2* ranges);
 cudaError_t launch_tile_ranges_u32(cudaStream_t s, int64_t cap, const uint32_t* n_dev, const uint32_t* keys, int G, uint2* ranges);
 
-cudaError_t launch_blend_forward(cudaStream_t s, int W, int H, const uint2* ranges,
-                                 const uint32_t* point_list, const float4* rec, const float* depths,
-                                 const float* bg, float* out_color, float* out_depth,
-                                 float* final_T, uint32_t* n_contrib, bool precise);
-cudaError_t launch_blend_backward(cudaStream_t s, int W, int H, const uint2* ranges,
-                                  const uint32_t* point_list, const float4* rec, const float* bg,
-                                  const float* final_T, const uint32_t* n_contrib,
-                                  const float* dL_dpix, float* gacc /*[P][12]*/, bool precise);
+// K6 / K7 of all views of a batched step in one launch (blockIdx.y = view)
+struct BlendFwdView {
+  int W, H, grid_x, G;   // grid_x / G are filled in by the launcher
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const float4* rec;
+  const float* depths;
+  const float* bg;
+  float* out_color;
+  float* out_depth;
+  float* final_T;
+  uint32_t* n_contrib;
+};
+struct BlendBwdView {
+  int W, H, grid_x, G;
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const float4* rec;
+  const float* bg;
+  const float* final_T;
+  const uint32_t* n_contrib;
+  const float* dL_dpix;
+  float* gacc;  // [P][12]
+};
+cudaError_t launch_blend_forward(cudaStream_t s, const BlendFwdView* views, int nv, bool precise);
+cudaError_t launch_blend_backward(cudaStream_t s, const BlendBwdView* views, int nv, bool precise);
 cudaError_t launch_debug_approx_units(cudaStream_t s, const float* x, int n, float* out /*[n][2]*/);
 cudaError_t launch_geom_backward(cudaStream_t s, int P, int D, int M, const float* means3D,
                                  const int32_t* radii, const float* shs, const uint8_t* clamped,

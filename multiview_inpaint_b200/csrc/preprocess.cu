@@ -112,23 +112,40 @@ __device__ __forceinline__ void eval_sh_vec(const float4* __restrict__ row4, con
   }
 }
 
+struct PreArgs {
+  PreView v[GSR_MAX_BATCH];
+  int nv;
+};
+
 __global__ void __launch_bounds__(256)
 preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
                   const float* __restrict__ scales, const float* __restrict__ rotations,
                   const float* __restrict__ opacities, const float* __restrict__ shs,
                   const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
-                  const Camera cam, int prefiltered, int32_t* __restrict__ radii,
-                  float4* __restrict__ rec, float* __restrict__ depths,
-                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ tiles_touched,
-                  uint32_t* __restrict__ depth_keys, ushort4* __restrict__ rects,
-                  int32_t* __restrict__ status) {
+                  int prefiltered, const __grid_constant__ PreArgs args) {
   __shared__ float s_cam[35];
+  __shared__ unsigned long long s_sum_tiles;
+  __shared__ uint32_t s_sum_vis;
+  if (threadIdx.x == 0) { s_sum_tiles = 0; s_sum_vis = 0; }   // published by the barrier inside load_camera
+  // view-interleaved CTAs: the nv CTAs of one 256-Gaussian chunk are neighbours in launch order
+  const int vw = (int)(blockIdx.x % (unsigned)args.nv);
+  const PreView& pv_ = args.v[vw];
+  const Camera& cam = pv_.cam;
+  int32_t* __restrict__ radii = pv_.radii;
+  float4* __restrict__ rec = pv_.rec;
+  float* __restrict__ depths = pv_.depths;
+  uint8_t* __restrict__ clamped = pv_.clamped;
+  uint32_t* __restrict__ tiles_touched = pv_.tiles_touched;
+  uint32_t* __restrict__ depth_keys = pv_.depth_keys;
+  ushort4* __restrict__ rects = pv_.rects;
+  int32_t* __restrict__ status = pv_.status;
   load_camera(cam, s_cam);
   const float* view = s_cam;
   const float* proj = s_cam + 16;
   const float* campos = s_cam + 32;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
+  const int i_raw = (int)(blockIdx.x / (unsigned)args.nv) * blockDim.x + threadIdx.x;
+  const bool in_range = i_raw < P;   // threads past the end run on the last Gaussian and write nothing (no early
+  const int i = in_range ? i_raw : P - 1;  // return: the whole CTA takes part in the reduction at the end)
 
   // defaults for culled Gaussians
   int32_t out_radius = 0;
@@ -140,8 +157,8 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
                       __ldg(means3D + 3 * (size_t)i + 2)};
   float pv[3];
   xform4x3(p, view, pv);
-  bool alive = pv[2] > 0.2f;  // A.2 step 2 (the x/y frustum test is disabled upstream)
-  if (!alive && prefiltered) atomicExch(status, 1);
+  bool alive = in_range && pv[2] > 0.2f;  // A.2 step 2 (the x/y frustum test is disabled upstream)
+  if (in_range && !alive && prefiltered) atomicExch(status, 1);
 
   if (alive) {
     float ph[4];
@@ -279,17 +296,29 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
       }
     }
   }
-  radii[i] = out_radius;
-  tiles_touched[i] = out_tiles;
-  if (depth_keys != nullptr) depth_keys[i] = out_key;
-  if (rects != nullptr) rects[i] = out_rect;  // two-level binning: the fused scan + expansion reads this
-  // N = sum of tiles_touched, known as soon as K1 ends (status[2..3] as one uint64): the host sizes
-  // the binning buffer from it without waiting for the scan.  Any converged subset of the warp
-  // reduces among itself, so divergence above only changes how many partial sums are added.
-  const unsigned am = __activemask();
-  const uint32_t part = __reduce_add_sync(am, out_tiles);
-  if ((threadIdx.x & 31) == __ffs(am) - 1 && part != 0)
-    atomicAdd(reinterpret_cast<unsigned long long*>(status + 2), (unsigned long long)part);
+  if (in_range) {
+    radii[i] = out_radius;
+    tiles_touched[i] = out_tiles;
+    if (depth_keys != nullptr) depth_keys[i] = out_key;
+    if (rects != nullptr) rects[i] = out_rect;  // two-level binning: the fused scan + expansion reads this
+  }
+  // N = sum of tiles_touched (status[2..3] as one uint64), known as soon as K1 ends: the host sizes the binning buffer
+  // from it without waiting for the scan.  V = number of visible Gaussians (status[5]): the depth sort drops the culled
+  // ones in its first pass and every later stage walks V entries.  Reduced per warp, then per CTA in shared memory:
+  // two global atomics per CTA (one per warp on one address serialised in the L2: 94 k same-address atomics per view
+  // cost K1 a quarter of its time once the second counter was added).
+  __syncwarp();
+  const uint32_t part = __reduce_add_sync(0xffffffffu, out_tiles);
+  const uint32_t nvis = __popc(__ballot_sync(0xffffffffu, out_tiles != 0));
+  if ((threadIdx.x & 31) == 0 && part != 0) {
+    atomicAdd(&s_sum_tiles, (unsigned long long)part);
+    atomicAdd(&s_sum_vis, nvis);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_sum_tiles != 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(status + 2), s_sum_tiles);
+    atomicAdd(reinterpret_cast<uint32_t*>(status + 5), s_sum_vis);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -310,14 +339,18 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
 cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* means3D,
                               const float* scales, const float* rotations, const float* opacities,
                               const float* shs, const float* cov3D_precomp,
-                              const float* colors_precomp, const Camera& cam, int prefiltered,
-                              int32_t* radii, float4* rec, float* depths, uint8_t* clamped,
-                              uint32_t* tiles_touched, uint32_t* depth_keys, ushort4* rects, int32_t* status) {
-  if (P == 0) return cudaSuccess;
-  preprocess_kernel<<<cdiv(P, 256), 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs,
-                                                 cov3D_precomp, colors_precomp, cam, prefiltered,
-                                                 radii, rec, depths, clamped, tiles_touched,
-                                                 depth_keys, rects, status);
+                              const float* colors_precomp, float scale_modifier, int prefiltered,
+                              const PreView* views, int nv) {
+  if (P == 0 || nv <= 0) return cudaSuccess;
+  if (nv > GSR_MAX_BATCH) return cudaErrorInvalidValue;
+  PreArgs args{};
+  args.nv = nv;
+  for (int k = 0; k < nv; k++) {
+    args.v[k] = views[k];
+    args.v[k].cam.scale_modifier = scale_modifier;
+  }
+  preprocess_kernel<<<(unsigned)cdiv(P, 256) * (unsigned)nv, 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs,
+                                                                        cov3D_precomp, colors_precomp, prefiltered, args);
   count_launch();
   return cudaGetLastError();
 }

@@ -118,12 +118,21 @@ cudaError_t launch_inclusive_scan(cudaStream_t s, int64_t n, const uint32_t* in,
 }
 
 // =================================================================================================
-// Onesweep radix sort
+// Onesweep radix sort -- segmented: one launch sorts up to GSR_MAX_BATCH independent arrays (the views
+// of a multi-view step), blockIdx.y = segment.  Per 8-bit digit ONE read + ONE write of every pair.
+//   * COMPACT first pass: elements whose key is 0xFFFFFFFF (culled Gaussians) are dropped while they
+//     are read -- they are not counted, ranked or written -- so the remaining passes and everything
+//     downstream walk the V visible entries instead of all P (the count V lives on the device);
+//   * stable ranking per warp with match_any; the per-item ranks are kept as packed 16-bit pairs
+//     (<= 64 registers: four CTAs per SM);
+//   * decoupled look-back eight predecessors at a time (eight independent L2 loads in flight per
+//     digit thread instead of one dependent load per predecessor).
 // =================================================================================================
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_RADIX = 256;
 constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_LOOKBACK = 8;
 // Look-back status word of one (tile, digit): 2 flag bits + the count / inclusive prefix.  32-bit words (30-bit
 // prefix) below 2^30 elements; 64-bit words (62-bit prefix) from there up to the 2^32 - 1 elements that uint32
 // positions can address -- the reference's own limit (its point_offsets are uint32).
@@ -148,7 +157,7 @@ static int rs_tile(int key_bytes) {
 }
 static int rs_passes(int end_bit) { return (end_bit + 7) / 8; }
 
-// temp layout: [hist: passes*256 u32][tickets: 8 u32 (padded)][status: passes * tiles * 256 u32]
+// temp layout: [hist: 8*256 u32][tickets: 8 u32 (padded)][status: passes * tiles * 256 words]
 size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
   const int passes = rs_passes(end_bit);
   const int64_t tiles = (n + rs_tile(key_bytes) - 1) / rs_tile(key_bytes);
@@ -157,39 +166,59 @@ size_t sort_temp_bytes(int64_t n, int key_bytes, int end_bit) {
 }
 
 template <typename KeyT>
+struct RsHistArgs {
+  const KeyT* keys[GSR_MAX_BATCH];
+  const uint32_t* n_dev[GSR_MAX_BATCH];
+  int64_t n_cap[GSR_MAX_BATCH];
+  uint32_t* hist[GSR_MAX_BATCH];
+};
+
+// COMPACT: keys equal to ~0 are not counted (they are dropped by the first onesweep pass).
+// The low digits of a key are close to uniform: plain shared-memory atomics (no two lanes of a warp meet often).
+// The most significant digit is highly repetitive (exponent byte of the depth, high bits of a tile id): its lanes
+// aggregate with match_any first -- cheap there, because MATCH.ANY's cost grows with the number of DISTINCT values in
+// the warp (it was the whole cost of this kernel, 316 us per 12 M keys, when every digit went through it).
+template <typename KeyT, bool COMPACT>
 __global__ void __launch_bounds__(256)
-rs_histogram_kernel(const KeyT* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ n_dev,
-                    int end_bit, uint32_t* __restrict__ hist) {
+rs_histogram_kernel(const __grid_constant__ RsHistArgs<KeyT> args, int end_bit) {
   __shared__ uint32_t s_h[RS_MAX_PASSES * RS_RADIX];
-  const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+  const int seg = blockIdx.y;
+  const KeyT* __restrict__ keys = args.keys[seg];
+  const int64_t n_cap = args.n_cap[seg];
+  const int64_t n = args.n_dev[seg] ? min((int64_t)*args.n_dev[seg], n_cap) : n_cap;
   const int passes = (end_bit + 7) / 8;
   for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x) s_h[i] = 0;
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
+  const int top = passes - 1;
+  const int top_bits = end_bit - 8 * top;
   // warp-uniform trip count so that the full-mask match below is legal
   for (int64_t b = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); b < n; b += stride) {
     const int64_t i = b + lane;
-    const bool valid = i < n;
+    bool valid = i < n;
     const KeyT k = valid ? keys[i] : (KeyT)0;
-    for (int p = 0; p < passes; p++) {
-      const int bits = min(8, end_bit - 8 * p);
-      // invalid lanes get a private pseudo-digit so they never pair up
-      const uint32_t d = valid ? ((uint32_t)(k >> (8 * p)) & ((1u << bits) - 1)) : (0x100u | lane);
-      // warp-aggregate equal digits (tile-id keys are highly repetitive)
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
-      if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_h[p * RS_RADIX + d], __popc(peers));
-    }
+    if (COMPACT) valid = valid && k != ~(KeyT)0;
+    if (valid)
+      for (int p = 0; p < top; p++) atomicAdd(&s_h[p * RS_RADIX + ((uint32_t)(k >> (8 * p)) & 0xffu)], 1u);
+    // invalid lanes get a private pseudo-digit so they never pair up
+    const uint32_t d = valid ? ((uint32_t)(k >> (8 * top)) & ((1u << top_bits) - 1)) : (0x100u | lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_h[top * RS_RADIX + d], __popc(peers));
   }
   __syncthreads();
+  uint32_t* __restrict__ hist = args.hist[seg];
   for (int i = threadIdx.x; i < passes * RS_RADIX; i += blockDim.x)
     if (s_h[i]) atomicAdd(&hist[i], s_h[i]);
 }
 
-// exclusive scan of each pass' 256-bin histogram, in place; one block of 256 threads per pass
-__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(uint32_t* __restrict__ hist) {
+struct RsScanArgs {
+  uint32_t* hist[GSR_MAX_BATCH];
+};
+// exclusive scan of each pass' 256-bin histogram, in place; one block of 256 threads per (pass, segment)
+__global__ void __launch_bounds__(RS_RADIX) rs_scan_hist_kernel(const __grid_constant__ RsScanArgs args) {
   __shared__ uint32_t s_w[RS_RADIX / 32];
-  uint32_t* h = hist + blockIdx.x * RS_RADIX;
+  uint32_t* h = args.hist[blockIdx.y] + blockIdx.x * RS_RADIX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t c = h[tid];
   uint32_t x = c;
@@ -210,19 +239,45 @@ __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift, uint32_t mask) {
   return (uint32_t)(k >> shift) & mask;
 }
 
-template <typename KeyT, int ITEMS, typename StatusT>
-__global__ void __launch_bounds__(RS_THREADS)
-rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                   KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n_cap,
-                   const uint32_t* __restrict__ n_dev, int shift, int nbits,
-                   const uint32_t* __restrict__ global_base, volatile StatusT* status,
-                   uint32_t* ticket) {
+template <typename KeyT>
+struct RsPassSeg {
+  const KeyT* keys_in;
+  const uint32_t* vals_in;       // NULL: the element index is the value
+  KeyT* keys_out;
+  uint32_t* vals_out;
+  const uint32_t* n_dev;         // element count on the device (NULL: n_cap)
+  int64_t n_cap;                 // capacity: sizes the grid; surplus CTAs retire before taking a ticket
+  const uint32_t* global_base;   // [256] exclusive digit bases of this pass
+  void* status;                  // [tiles][256] look-back words (zeroed)
+  uint32_t* ticket;              // zeroed
+};
+template <typename KeyT>
+struct RsPassArgs {
+  RsPassSeg<KeyT> seg[GSR_MAX_BATCH];
+};
+
+template <typename StatusT>
+__device__ __forceinline__ StatusT ld_status(const volatile StatusT* p) { return *p; }
+
+// RANK: how the lanes of a warp find their equal-digit peers.
+//   0  match_any         one instruction, but MATCH.ANY iterates over the DISTINCT values of the warp: ~30 of them with
+//                        uniform 8-bit digits -- it was most of this kernel's time
+//   1  eight ballots     fixed cost: one VOTE + one select per digit bit (what cub's onesweep does)
+//   2  shared atomicOr   each lane ORs its lane bit into a per-(warp, digit) word and reads the word back
+template <typename KeyT, int ITEMS, typename StatusT, bool COMPACT, int RANK>
+__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? 4 : 2)
+rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int nbits) {
   using ST = RsStatus<StatusT>;
   constexpr int TILE = RS_THREADS * ITEMS;
+  static_assert(ITEMS % 2 == 0 && TILE < 65535, "packed 16-bit ranks");
+  const RsPassSeg<KeyT>& sg = args.seg[blockIdx.y];
   // the element count may live on the device (no host round trip): grid is sized by capacity and
   // surplus CTAs retire before taking a ticket
-  const int64_t n = n_dev ? min((int64_t)*n_dev, n_cap) : n_cap;
+  const int64_t n = sg.n_dev ? min((int64_t)*sg.n_dev, sg.n_cap) : sg.n_cap;
   if ((int64_t)blockIdx.x * TILE >= n) return;
+  const KeyT* __restrict__ keys_in = sg.keys_in;
+  const uint32_t* __restrict__ vals_in = sg.vals_in;
+  volatile StatusT* status = reinterpret_cast<volatile StatusT*>(sg.status);
   extern __shared__ __align__(16) unsigned char rs_smem[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                  // [TILE]
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * TILE);    // [TILE]
@@ -230,11 +285,15 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
   uint32_t* s_digit_off = s_warp_cnt + RS_WARPS * RS_RADIX;                         // [256]
   uint32_t* s_global_off = s_digit_off + RS_RADIX;                                  // [256]
   uint32_t* s_misc = s_global_off + RS_RADIX;                                       // [16]
+  uint32_t* s_match = s_misc + 16;                                                  // [WARPS][256], RANK == 2 only
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t mask = (1u << nbits) - 1;
-  if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
-  for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) s_warp_cnt[i] = 0;
+  if (tid == 0) s_misc[0] = atomicAdd(sg.ticket, 1u);
+  for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) {
+    s_warp_cnt[i] = 0;
+    if (RANK == 2) s_match[i] = 0;
+  }
   __syncthreads();
   const uint32_t tile = s_misc[0];
   const int64_t base = (int64_t)tile * TILE;
@@ -242,33 +301,56 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
 
   KeyT key[ITEMS];
   uint32_t val[ITEMS];
+  uint32_t live = 0;  // bit r: item r takes part (inside the array and, in a COMPACT pass, not a culled sentinel)
 #pragma unroll
   for (int r = 0; r < ITEMS; r++) {
     const int64_t idx = wbase + r * 32;
+    key[r] = ~(KeyT)0;
+    val[r] = (uint32_t)idx;
     if (idx < n) {
       key[r] = keys_in[idx];
-      val[r] = vals_in ? vals_in[idx] : (uint32_t)idx;
-    } else {
-      key[r] = ~(KeyT)0;  // pads take the largest digit and sit at the very end of the tile
-      val[r] = 0;
+      if (vals_in) val[r] = vals_in[idx];
+      if (!COMPACT || key[r] != ~(KeyT)0) live |= 1u << r;
     }
   }
 
   // ---- stable ranking: per-warp digit counters + match_any multi-split ----
-  uint32_t rank[ITEMS];
+  uint32_t rank2[ITEMS / 2];  // two 16-bit ranks per register
   const uint32_t lt_mask = (1u << lane) - 1;
 #pragma unroll
   for (int r = 0; r < ITEMS; r++) {
-    const uint32_t d = rs_digit(key[r], shift, mask);
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const bool ok = (live >> r) & 1u;
+    // items that do not take part get a private pseudo-digit: they never pair up and touch no counter
+    const uint32_t d = ok ? rs_digit(key[r], shift, mask) : (0x100u | (uint32_t)lane);
+    unsigned peers;
+    if (RANK == 0) {
+      peers = __match_any_sync(0xffffffffu, d);
+    } else if (RANK == 1) {
+      peers = __ballot_sync(0xffffffffu, ok);   // items that take part
+#pragma unroll
+      for (int bit = 0; bit < 8; bit++) {
+        const bool one = (d >> bit) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, one);
+        peers &= one ? m : ~m;
+      }
+      if (!ok) peers = 1u << lane;
+    } else {
+      uint32_t* slot = s_match + warp * RS_RADIX + (d & 0xffu);
+      if (ok) atomicOr(slot, 1u << lane);
+      __syncwarp();
+      peers = ok ? *slot : (1u << lane);
+      __syncwarp();
+      if (ok && lane == __ffs(peers) - 1) *slot = 0;   // ready for the next item (ordered by the __syncwarp below)
+    }
     const int leader = __ffs(peers) - 1;
     uint32_t old = 0;
-    if (lane == leader) {
+    if (ok && lane == leader) {
       old = s_warp_cnt[warp * RS_RADIX + d];
       s_warp_cnt[warp * RS_RADIX + d] = old + __popc(peers);
     }
     old = __shfl_sync(0xffffffffu, old, leader);
-    rank[r] = old + __popc(peers & lt_mask);
+    const uint32_t rk = old + __popc(peers & lt_mask);
+    if (r & 1) rank2[r >> 1] |= rk << 16; else rank2[r >> 1] = rk;
     __syncwarp();
   }
   __syncthreads();
@@ -297,6 +379,7 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
     for (int w = 0; w < warp; w++) wp += s_misc[1 + w];
     const uint32_t digit_off = wp + x - count;
     s_digit_off[d] = digit_off;
+    if (d == RS_RADIX - 1) s_misc[10] = digit_off + count;  // elements of this tile that take part
 
     StatusT excl = 0;
     volatile StatusT* my = status + (size_t)tile * RS_RADIX + d;
@@ -305,30 +388,44 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
     } else {
       *my = ST::AGG | (StatusT)count;
       int64_t t = (int64_t)tile - 1;
-      while (true) {
-        StatusT st;
-        do { st = status[(size_t)t * RS_RADIX + d]; } while ((st >> ST::SHIFT) == 0);
-        excl += st & ST::MASK;
-        if (st & ST::INC) break;
-        t--;
+      bool found = false;
+      while (!found) {
+        StatusT st[RS_LOOKBACK];
+#pragma unroll
+        for (int j = 0; j < RS_LOOKBACK; j++)
+          st[j] = (t - j >= 0) ? ld_status<StatusT>(status + (size_t)(t - j) * RS_RADIX + d) : ST::INC;  // before tile 0: "inclusive 0"
+#pragma unroll
+        for (int j = 0; j < RS_LOOKBACK; j++) {
+          if (!found) {
+            StatusT s = st[j];
+            while ((s >> ST::SHIFT) == 0) s = ld_status<StatusT>(status + (size_t)(t - j) * RS_RADIX + d);
+            excl += s & ST::MASK;
+            found = (s & ST::INC) != 0;
+          }
+        }
+        t -= RS_LOOKBACK;
       }
       *my = ST::INC | ((excl + (StatusT)count) & ST::MASK);
     }
-    s_global_off[d] = global_base[d] + (uint32_t)excl - digit_off;   // positions are < 2^32: mod-2^32 arithmetic
+    s_global_off[d] = sg.global_base[d] + (uint32_t)excl - digit_off;   // positions are < 2^32: mod-2^32 arithmetic
   }
   __syncthreads();
 
   // ---- reorder through shared memory so that the global scatter is run-wise contiguous ----
 #pragma unroll
   for (int r = 0; r < ITEMS; r++) {
-    const uint32_t d = rs_digit(key[r], shift, mask);
-    const uint32_t pos = s_digit_off[d] + s_warp_cnt[warp * RS_RADIX + d] + rank[r];
-    s_keys[pos] = key[r];
-    s_vals[pos] = val[r];
+    if ((live >> r) & 1u) {
+      const uint32_t d = rs_digit(key[r], shift, mask);
+      const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
+      const uint32_t pos = s_digit_off[d] + s_warp_cnt[warp * RS_RADIX + d] + rk;
+      s_keys[pos] = key[r];
+      s_vals[pos] = val[r];
+    }
   }
   __syncthreads();
-  const int64_t remain = n - base;
-  const int n_valid = remain < TILE ? (int)remain : TILE;
+  const int n_valid = (int)s_misc[10];
+  KeyT* __restrict__ keys_out = sg.keys_out;
+  uint32_t* __restrict__ vals_out = sg.vals_out;
 #pragma unroll 4
   for (int i = tid; i < n_valid; i += RS_THREADS) {
     const KeyT k = s_keys[i];
@@ -339,81 +436,142 @@ rs_onesweep_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict_
   }
 }
 
+int g_rs_rank_mode = 1;   // see rs_onesweep_kernel; gsr_debug_set(0, mode) switches it for experiments
+
+template <typename KeyT, typename StatusT, bool COMPACT, int RANK>
+static cudaError_t rs_launch_pass_r(cudaStream_t s, const RsPassArgs<KeyT>& pa, int nseg, int64_t max_tiles, int shift, int bits) {
+  constexpr int ITEMS = RsCfg<KeyT>::ITEMS;
+  constexpr int TILE = RS_THREADS * ITEMS;
+  const size_t smem = sizeof(KeyT) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 16) +
+                      (RANK == 2 ? 4 * RS_WARPS * RS_RADIX : 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, ITEMS, StatusT, COMPACT, RANK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  rs_onesweep_kernel<KeyT, ITEMS, StatusT, COMPACT, RANK><<<dim3((unsigned)max_tiles, (unsigned)nseg), RS_THREADS, smem, s>>>(pa, shift, bits);
+  return cudaGetLastError();
+}
+template <typename KeyT, typename StatusT, bool COMPACT>
+static cudaError_t rs_launch_pass(cudaStream_t s, const RsPassArgs<KeyT>& pa, int nseg, int64_t max_tiles, int shift, int bits) {
+  switch (g_rs_rank_mode) {
+    case 0: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 0>(s, pa, nseg, max_tiles, shift, bits);
+    case 2: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 2>(s, pa, nseg, max_tiles, shift, bits);
+    default: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 1>(s, pa, nseg, max_tiles, shift, bits);
+  }
+}
+
+// Sorts `nseg` independent arrays with one launch per pass.  In a `compact` sort the first pass drops keys equal
+// to ~0 and the later passes read their element count from seg.n_dev_compact (the number of surviving keys).
 template <typename KeyT>
-static cudaError_t sort_pairs_impl(cudaStream_t s, int64_t n, const uint32_t* n_dev, const KeyT* keys_in,
-                                   const uint32_t* vals_in, KeyT* keys_out, uint32_t* vals_out,
-                                   KeyT* keys_alt, uint32_t* vals_alt, int end_bit, char* temp,
-                                   bool have_bases = false) {
-  if (n <= 0) return cudaSuccess;
+static cudaError_t sort_pairs_batched(cudaStream_t s, const SortSeg<KeyT>* segs, int nseg, int end_bit,
+                                      bool have_bases, bool compact, bool temp_zeroed = false) {
+  if (nseg <= 0) return cudaSuccess;
+  if (nseg > GSR_MAX_BATCH) return cudaErrorInvalidValue;
   constexpr int ITEMS = RsCfg<KeyT>::ITEMS;
   constexpr int TILE = RS_THREADS * ITEMS;
   const int passes = rs_passes(end_bit);
   if (passes < 1 || passes > RS_MAX_PASSES) return cudaErrorInvalidValue;
-  const int64_t tiles = (n + TILE - 1) / TILE;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(temp);
-  uint32_t* tickets = reinterpret_cast<uint32_t*>(temp + align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4));
-  uint32_t* status = reinterpret_cast<uint32_t*>(temp + align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4) + align_up(64));
+  int64_t max_n = 0;
+  for (int k = 0; k < nseg; k++) max_n = segs[k].n > max_n ? segs[k].n : max_n;
+  if (max_n <= 0) return cudaSuccess;
+  const bool wide = max_n >= RS_WIDE_FROM;
+  for (int k = 0; k < nseg && nseg > 1; k++)
+    if ((segs[k].n >= RS_WIDE_FROM) != wide) {  // mixed look-back word widths: sort the arrays one by one
+      for (int j = 0; j < nseg; j++) {
+        cudaError_t ej = sort_pairs_batched<KeyT>(s, segs + j, 1, end_bit, have_bases, compact, temp_zeroed);
+        if (ej != cudaSuccess) return ej;
+      }
+      return cudaSuccess;
+    }
+  const size_t hist_bytes = align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4);
   cudaError_t e;
-  if (have_bases) {  // the caller has filled `hist` with exclusive digit bases: clear tickets + status only
-    const size_t skip = align_up((size_t)RS_MAX_PASSES * RS_RADIX * 4);
-    e = cudaMemsetAsync(temp + skip, 0, sort_temp_bytes(n, sizeof(KeyT), end_bit) - skip, s);
-    if (e != cudaSuccess) return e;
-    count_launch(passes);
-  } else {
-    e = cudaMemsetAsync(temp, 0, sort_temp_bytes(n, sizeof(KeyT), end_bit), s);
-    if (e != cudaSuccess) return e;
-    int hist_blocks = (int)((n + 256 * 16 - 1) / (256 * 16));
-    if (hist_blocks > 148 * 8) hist_blocks = 148 * 8;
-    rs_histogram_kernel<KeyT><<<hist_blocks, 256, 0, s>>>(keys_in, n, n_dev, end_bit, hist);
-    rs_scan_hist_kernel<<<passes, RS_RADIX, 0, s>>>(hist);
-    count_launch(2 + passes);
+  RsHistArgs<KeyT> ha{};
+  RsScanArgs sa{};
+  for (int k = 0; k < nseg; k++) {
+    const SortSeg<KeyT>& g = segs[k];
+    const size_t total = sort_temp_bytes(g.n > 0 ? g.n : 1, sizeof(KeyT), end_bit);
+    // the caller has filled `hist` with exclusive digit bases when have_bases: clear tickets + status only
+    if (!temp_zeroed) {
+      e = have_bases ? cudaMemsetAsync(g.temp + hist_bytes, 0, total - hist_bytes, s) : cudaMemsetAsync(g.temp, 0, total, s);
+      if (e != cudaSuccess) return e;
+    }
+    ha.keys[k] = g.keys_in;
+    ha.n_dev[k] = g.n_dev;
+    ha.n_cap[k] = g.n;
+    ha.hist[k] = reinterpret_cast<uint32_t*>(g.temp);
+    sa.hist[k] = ha.hist[k];
   }
+  if (!have_bases) {
+    int hist_blocks = (int)((max_n + 256 * 8 - 1) / (256 * 8));
+    const int cap_blocks = 148 * 8 / nseg > 148 ? 148 * 8 / nseg : 148;   // ~8 resident CTAs per SM over all segments
+    if (hist_blocks > cap_blocks) hist_blocks = cap_blocks;
+    if (compact)
+      rs_histogram_kernel<KeyT, true><<<dim3(hist_blocks, nseg), 256, 0, s>>>(ha, end_bit);
+    else
+      rs_histogram_kernel<KeyT, false><<<dim3(hist_blocks, nseg), 256, 0, s>>>(ha, end_bit);
+    rs_scan_hist_kernel<<<dim3(passes, nseg), RS_RADIX, 0, s>>>(sa);
+    count_launch(2);
+  }
+  count_launch(passes);
 
-  const size_t smem = sizeof(KeyT) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 16);
-  const bool wide = n >= RS_WIDE_FROM;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[wide]) {
-    e = wide ? cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, ITEMS, unsigned long long>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-             : cudaFuncSetAttribute(rs_onesweep_kernel<KeyT, ITEMS, uint32_t>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set[wide] = true;
-  }
   // ping-pong so that the LAST pass lands in (keys_out, vals_out); inputs are never written
-  const KeyT* kin = keys_in;
-  const uint32_t* vin = vals_in;
   for (int p = 0; p < passes; p++) {
     const bool to_out = ((passes - 1 - p) % 2) == 0;
-    KeyT* kout = to_out ? keys_out : keys_alt;
-    uint32_t* vout = to_out ? vals_out : vals_alt;
+    const bool from_out = !to_out;  // for p > 0 the previous pass wrote the other pair
+    RsPassArgs<KeyT> pa{};
+    int64_t max_tiles = 1;
+    for (int k = 0; k < nseg; k++) {
+      const SortSeg<KeyT>& g = segs[k];
+      const int64_t tiles = ((g.n > 0 ? g.n : 1) + TILE - 1) / TILE;
+      max_tiles = tiles > max_tiles ? tiles : max_tiles;
+      RsPassSeg<KeyT>& q = pa.seg[k];
+      q.keys_in = p == 0 ? g.keys_in : (from_out ? g.keys_out : g.keys_alt);
+      q.vals_in = p == 0 ? g.vals_in : (from_out ? g.vals_out : g.vals_alt);
+      q.keys_out = to_out ? g.keys_out : g.keys_alt;
+      q.vals_out = to_out ? g.vals_out : g.vals_alt;
+      q.n_dev = (compact && p > 0) ? g.n_dev_compact : g.n_dev;
+      q.n_cap = g.n;
+      q.global_base = reinterpret_cast<uint32_t*>(g.temp) + p * RS_RADIX;
+      uint32_t* tickets = reinterpret_cast<uint32_t*>(g.temp + hist_bytes);
+      char* status = g.temp + hist_bytes + align_up(64);
+      q.ticket = tickets + p;
+      q.status = status + (size_t)p * (size_t)tiles * RS_RADIX * rs_status_bytes(g.n);
+      if (g.n <= 0) q.n_cap = 0;
+    }
     const int bits = (end_bit - 8 * p) < 8 ? (end_bit - 8 * p) : 8;
+    const bool cpass = compact && p == 0;
     if (wide)
-      rs_onesweep_kernel<KeyT, ITEMS, unsigned long long><<<(unsigned)tiles, RS_THREADS, smem, s>>>(
-          kin, vin, kout, vout, n, n_dev, 8 * p, bits, hist + p * RS_RADIX,
-          reinterpret_cast<unsigned long long*>(status) + (size_t)p * tiles * RS_RADIX, tickets + p);
+      e = cpass ? rs_launch_pass<KeyT, unsigned long long, true>(s, pa, nseg, max_tiles, 8 * p, bits)
+                : rs_launch_pass<KeyT, unsigned long long, false>(s, pa, nseg, max_tiles, 8 * p, bits);
     else
-      rs_onesweep_kernel<KeyT, ITEMS, uint32_t><<<(unsigned)tiles, RS_THREADS, smem, s>>>(
-          kin, vin, kout, vout, n, n_dev, 8 * p, bits, hist + p * RS_RADIX,
-          status + (size_t)p * tiles * RS_RADIX, tickets + p);
-    e = cudaGetLastError();
+      e = cpass ? rs_launch_pass<KeyT, uint32_t, true>(s, pa, nseg, max_tiles, 8 * p, bits)
+                : rs_launch_pass<KeyT, uint32_t, false>(s, pa, nseg, max_tiles, 8 * p, bits);
     if (e != cudaSuccess) return e;
-    kin = kout;
-    vin = vout;
   }
   return cudaSuccess;
+}
+
+cudaError_t launch_sort_pairs_u32_batched(cudaStream_t s, const SortSeg<uint32_t>* segs, int nseg, int end_bit,
+                                          bool have_bases, bool compact, bool temp_zeroed) {
+  return sort_pairs_batched<uint32_t>(s, segs, nseg, end_bit, have_bases, compact, temp_zeroed);
 }
 
 cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint32_t* keys_in,
                                   const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
                                   uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp, bool have_bases) {
-  return sort_pairs_impl<uint32_t>(s, n, n_dev, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp,
-                                   have_bases);
+  if (n <= 0) return cudaSuccess;
+  SortSeg<uint32_t> g{n, n_dev, nullptr, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, temp};
+  return sort_pairs_batched<uint32_t>(s, &g, 1, end_bit, have_bases, false);
 }
 cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
-  return sort_pairs_impl<uint64_t>(s, n, n_dev, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, end_bit, temp);
+  if (n <= 0) return cudaSuccess;
+  SortSeg<uint64_t> g{n, n_dev, nullptr, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, temp};
+  return sort_pairs_batched<uint64_t>(s, &g, 1, end_bit, false, false);
 }
 
 }  // namespace gsr

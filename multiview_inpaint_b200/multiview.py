@@ -352,6 +352,29 @@ def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch
     return ViewState(color, depth, radii, n, geom, scratch, rs)
 
 
+def cuda_views_fwd_blend_batched(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: Sequence[Callable], flags: int,
+                                 capacities: Sequence[int], async_results: Sequence, workspaces: Sequence | None = None
+                                 ) -> list[ViewState]:
+    """Forward (K1..K6) of ALL views with one launch per stage (gsr_forward_views), the loss gradients, then the blend
+    backward (K7) of all views in one launch (gsr_backward_blend_views).  The views share the Gaussians, so K1's
+    parameter reads come from HBM once; the sorts and the expansion run as segmented kernels that fill the machine
+    where a single view's grids (1.7 waves per sort pass at 3 M Gaussians) left it latency-bound.  Asynchronous only:
+    needs capacities + pinned async_results (AsyncViews)."""
+    from . import _C
+    rss = [s() if callable(s) else s for s in settings_list]
+    if not rss:
+        return []
+    rs0 = rss[0]
+    e = torch.empty(0, device=gaussians["means3D"].device)
+    outs = _C.forward_views(rs0.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
+                            rs0.scale_modifier, e, rss, gaussians["shs"], rs0.sh_degree, rs0.prefiltered, capacities,
+                            async_results, workspaces=workspaces, flags=flags)
+    dLs = [fn(o[1]) for fn, o in zip(dL_dcolor_fns, outs)]
+    scratches = _C.backward_blend_views(rs0.bg, dLs, [o[3] for o in outs], [o[4] for o in outs], [o[5] for o in outs],
+                                        gaussians["means3D"].shape[0], flags=flags, workspaces=workspaces)
+    return [ViewState(o[1], o[6], o[2], -1, o[3], sc, rs) for o, sc, rs in zip(outs, scratches, rss)]
+
+
 def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena: GradArena, accumulate: bool = False,
                              flags: int = 0, want_means2D: bool = False):
     """Batched K8+K9 over `states` (one launch per four views): parameter gradients and densification
@@ -415,7 +438,7 @@ def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewSta
 def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: Sequence[Callable], arena: GradArena,
                        flags: int = 0, capacities: Sequence[int] | None = None, async_results: Sequence | None = None,
                        pipeline: ViewPipeline | None = None, accumulate: bool = False, all_reduce: bool = False,
-                       chunks: int = 4, workspaces: Sequence | None = None) -> list[ViewState]:
+                       chunks: int = 4, workspaces: Sequence | None = None, batched: bool = False) -> list[ViewState]:
     """A rank's share of a multi-view step: every view's forward + blend backward (two views in flight
     with `pipeline`), then ONE batched per-Gaussian backward that writes the arena.  Falls back to the
     per-view accumulate path when the batched kernel does not cover the configuration (M not in 1/4/16).
@@ -439,6 +462,21 @@ def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: 
             arena.all_reduce()
         return out
     states = []
+    if batched and capacities and async_results and all(c > 0 for c in capacities) and not (flags & (_C.FLAG_BINNING_KEY64 | _C.FLAG_REFERENCE)):
+        # one launch per stage for all views of a group (`batched`): every launch fills the machine.  With a pipeline the
+        # views are split into one group per stream, so that the memory- / latency-bound front end of one group runs
+        # under the issue-bound blend kernels of the other.
+        n = len(settings_list)
+        n_groups = min(len(pipeline.streams), n) if pipeline is not None else 1
+        bounds = [n * g // n_groups for g in range(n_groups + 1)]
+        states = []
+        with (pipeline.step() if pipeline else contextlib.nullcontext()):
+            for g in range(n_groups):
+                sl = slice(bounds[g], bounds[g + 1])
+                with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
+                    states += cuda_views_fwd_blend_batched(gaussians, settings_list[sl], dL_dcolor_fns[sl], flags, capacities[sl],
+                                                           async_results[sl], workspaces[sl] if workspaces else None)
+        settings_list = []
     with (pipeline.step() if pipeline else contextlib.nullcontext()):
         for k, rs in enumerate(settings_list):
             states.append(cuda_view_fwd_blend(gaussians, rs, dL_dcolor_fns[k], flags=flags,

@@ -45,10 +45,12 @@ def _check_forward(oracle, sc, flags, cam=None, bg=None, **kw):
     if flags & (KEY64 | REFERENCE):
         np.testing.assert_array_equal(st["point_offsets"].view(np.uint32), f.point_offsets)
     else:
+        # the depth sort drops culled Gaussians in its first pass: `order` holds the V visible ones, by (depth, index)
         dkeys = np.where(vis, f.depths.view(np.uint32), np.uint32(0xFFFFFFFF))
-        order = np.argsort(dkeys, kind="stable").astype(np.uint32)
-        np.testing.assert_array_equal(st["order"].view(np.uint32), order)
-        np.testing.assert_array_equal(st["point_offsets"].view(np.uint32),
+        V = int(vis.sum())
+        order = np.argsort(dkeys, kind="stable").astype(np.uint32)[:V]
+        np.testing.assert_array_equal(st["order"].view(np.uint32)[:V], order)
+        np.testing.assert_array_equal(st["point_offsets"].view(np.uint32)[:V],
                                       np.cumsum(f.tiles_touched[order], dtype=np.uint64).astype(np.uint32))
     np.testing.assert_array_equal(st["point_list"].view(np.uint32), f.point_list)
     np.testing.assert_array_equal(st["ranges"].view(np.uint32), f.ranges)
