@@ -36,7 +36,7 @@ UNIT = "views/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
@@ -44,9 +44,13 @@ def parse():
                     help="train: fwd+bwd views/s (the BASELINE metric, default); infer: forward-only colour+depth views/s "
                          "(BASELINE config 4, render.py / render_depth.py), no collective")
     ap.add_argument("--views-per-rank", type=int, default=4)
+    ap.add_argument("--total-views", type=int, default=0, help="STRONG scaling: a fixed batch of this many views per step, sharded over "
+                    "the ranks (BASELINE configs 3 / 4: the 25-frame orbit, the 200-view render set); 0 = weak scaling, views-per-rank each")
+    ap.add_argument("--no-balance", action="store_true", help="strong scaling: keep the round-robin view -> rank map instead of "
+                    "balancing the ranks' instance counts (longest-processing-time assignment on the learnt num_rendered)")
     ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
     ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
-    ap.add_argument("--streams", type=int, default=2, help="view groups in flight per GPU (ViewPipeline depth; 1 = one stream): with the batched "
+    ap.add_argument("--streams", type=int, default=1, help="view groups in flight per GPU (ViewPipeline depth; 1 = one stream): with the batched "
                     "front end the rank's views are split into this many groups, one stream each")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "nvls"],
                     help="arena collective: NCCL, the in-switch multimem kernel, or whichever is faster here")
@@ -56,6 +60,7 @@ def parse():
                     "instead of ONE launch per stage for all views of the rank (gsr_forward_views / gsr_backward_blend_views)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-structure", action="store_true", help="skip the GSR_FLAG_REFERENCE ablation leg")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in leg (GaussianRasterizer + loss.backward(), one view at a time)")
     ap.add_argument("--no-train-step", action="store_true", help="skip the fused-optimisation-step leg (SURVEY 8f rows 1, 4)")
     ap.add_argument("--files", type=int, default=0, help="infer mode: also time views/s all the way to PNG files with N writer threads "
                     "(AsyncImageWriter) against the reference's blocking save_image structure")
@@ -73,8 +78,9 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def algorithmic_bytes(P, V, N, G, W, H, M):
-    """SURVEY.md section 8(d) per-view figures, per stage (bytes per launch-bracket)."""
+def survey_bytes(P, V, N, G, W, H, M):
+    """SURVEY.md section 8(d) per-view figures, per stage: the traffic of the REFERENCE's structure (one 64-bit key sort
+    of six passes, a scan, AoS reads).  Kept beside the design model below; not used for any printed GB/s."""
     pre_b = {1: 190, 4: 260, 16: 550}.get(M, 119 + 27 * M)
     return {
         "preprocess": P * (119 + 12 * M),
@@ -86,6 +92,46 @@ def algorithmic_bytes(P, V, N, G, W, H, M):
         "blend_backward": 44 * N + 20 * W * H + 36 * N,
         "geom_backward": P * pre_b,
     }
+
+
+def algorithmic_bytes(P, V, N, G, W, H, M, nv=1):
+    """Bytes per view THIS design must move, per stage, for `nv` views sharing one batched launch
+    (the per-Gaussian inputs are then read once for all of them):
+      preprocess     reads 44 B of mean / scale / rotation / opacity per Gaussian and the 12 M-byte SH row of the V visible
+                     ones (once per batch); writes the 48-byte blend record + depth + clamp bits per visible Gaussian and
+                     radius, tiles_touched, depth key and tile rect (20 B) per Gaussian
+      depth_sort     histogram read (4 P) + compacting first pass (4 P in, 8 V out) + three more passes of 16 V
+      duplicate      order + rect in, offsets out (16 V), 8 N of (tile, id) pairs out; the tile_count reductions stay in L2
+      tile_sort      16 N per 8-bit pass of the tile id
+      tile_ranges    per-tile counts in, ranges out
+      blend_forward  list + records (44 N) and the per-pixel outputs (24 WH): an upper bound, the walk stops at saturation
+      accum_clear    the packed 48-byte accumulator per Gaussian
+      blend_backward 80 N + 20 WH (as SURVEY: records in, nine reductions out per instance)
+      geom_backward  batched K8+K9: parameters + SH rows once per batch, per view the record + accumulator of the visible
+                     Gaussians (96 V) and radius + clamp bits (5 P); the gradient row (4 (11 + 3 M) B per Gaussian) and the
+                     three statistics written once per batch"""
+    tile_passes = (max(1, math.ceil(math.log2(max(G, 2)))) + 7) // 8
+    grad_row = 4 * (3 + 3 * M + 1 + 3 + 4)
+    return {
+        "preprocess": (44 * P + 12 * M * V) / nv + 53 * V + 20 * P,
+        "depth_sort": 8 * P + 56 * V,
+        "duplicate": 16 * V + 8 * N,
+        "tile_sort": 16 * N * tile_passes,
+        "tile_ranges": 12 * G,
+        "blend_forward": 44 * N + 24 * W * H,
+        "accum_clear": 48 * P,
+        "blend_backward": 80 * N + 20 * W * H,
+        "geom_backward": (44 * P + 12 * M * V + (grad_row + 12) * P) / nv + 96 * V + 5 * P,
+    }
+
+
+def issue_counters():
+    """ncu counters of the issue-bound blend kernels (profiles/roofline_counters.json, written from the committed
+    `ncu --set full` captures by tools/make_profiles.py): issue-slot utilisation is their roof, not HBM."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_counters.json")))
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -131,7 +177,7 @@ class ClockSampler(threading.Thread):
 # -------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the CPU oracle on the host cores
 # -------------------------------------------------------------------------------------------------
-def cpu_view_seconds(sc, cam, wt, tile_step):
+def cpu_view_seconds(sc, cam, wt, tile_step, keep=None):
     """One fwd+bwd view on the CPU: full preprocess + binning, blend fwd/bwd on every
     `tile_step`-th tile; returns (estimated seconds for the full view, measured seconds, parts)."""
     import numpy as np
@@ -145,7 +191,7 @@ def cpu_view_seconds(sc, cam, wt, tile_step):
     f = O.bin_and_sort(O.preprocess(**kw))
     t1 = time.perf_counter()
     O.blend(f, np.zeros(3, np.float32), 0, tile_step)
-    O.backward(f, wt, 0, tile_step)          # blend backward on the sample + full per-Gaussian backward
+    g_full = O.backward(f, wt, 0, tile_step)          # blend backward on the sample + full per-Gaussian backward
     t2 = time.perf_counter()
     # the per-Gaussian backward inside O.backward is not strided: time it alone to avoid scaling it
     t3 = time.perf_counter()
@@ -154,8 +200,71 @@ def cpu_view_seconds(sc, cam, wt, tile_step):
     geom_bwd = t4 - t3
     blend_sample = max((t2 - t1) - geom_bwd, 0.0)
     est = (t1 - t0) + blend_sample * tile_step + geom_bwd
+    if keep is not None:
+        keep["f"], keep["g"] = f, g_full
     return est, (t2 - t0), dict(preprocess_bin_s=t1 - t0, blend_sample_s=blend_sample, geom_bwd_s=geom_bwd,
                                 N=int(f.num_rendered), V=int((f.radii > 0).sum()))
+
+
+def run_reference_install(args):
+    """SURVEY 0.1 / 8d baseline B0: if the driver (or a maintainer) has put an install of the reference's rasterizer
+    -- the third-party `diff_gaussian_rasterization` wheel the reference imports at gaussian_renderer/__init__.py:14 --
+    under baseline/_ref/, time THAT through its own public API on this config and return its JSON line.  Returns None
+    when there is no such install (the case in this repository: the package is neither in /root/reference nor in the
+    offline wheelhouse), and the caller falls back to the CPU oracle port."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    pkg = os.path.join(ref_dir, "diff_gaussian_rasterization")
+    if not os.path.isdir(pkg) or not any(f.startswith("_C") and f.endswith(".so") for f in os.listdir(pkg)):
+        return None
+    try:
+        import importlib.util
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        spec = importlib.util.spec_from_file_location("_ref_dgr", os.path.join(pkg, "__init__.py"), submodule_search_locations=[pkg])
+        ref = importlib.util.module_from_spec(spec)
+        sys.modules["_ref_dgr"] = ref
+        spec.loader.exec_module(ref)
+        from multiview_inpaint_b200 import scenes as S
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        cfg = S.CONFIGS[args.workload]
+        sc = S.make_config_scene(args.workload)
+        g = {k: sc[k].to(dev).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        cams = [c.to(dev) for c in S.orbit_cameras(max(args.views_per_rank, 2), cfg["W"], cfg["H"], max_deg=args.orbit_deg)]
+        wt = S.loss_weights(cfg["W"], cfg["H"], cfg["seed"]).to(dev)
+        bg = torch.zeros(3, device=dev)
+
+        def view(c):
+            rs = ref.GaussianRasterizationSettings(image_height=cfg["H"], image_width=cfg["W"], tanfovx=c.tanfovx, tanfovy=c.tanfovy,
+                                                   bg=bg, scale_modifier=1.0, viewmatrix=c.world_view_transform,
+                                                   projmatrix=c.full_proj_transform, sh_degree=cfg["sh_degree"],
+                                                   campos=c.camera_center, prefiltered=False)
+            m2d = torch.zeros_like(g["means3D"], requires_grad=True)
+            out = ref.GaussianRasterizer(rs)(means3D=g["means3D"], means2D=m2d, opacities=g["opacities"], shs=g["shs"],
+                                             scales=g["scales"], rotations=g["rotations"], colors_precomp=None, cov3D_precomp=None)
+            (out[0] * wt).sum().backward()
+            for t in g.values():
+                t.grad = None
+        for i in range(max(args.warmup, 3)):
+            view(cams[i % len(cams)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            view(cams[i % len(cams)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        value = args.steps / (ms / 1000.0)
+        return {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, **cfg, "note": "the reference's own diff_gaussian_rasterization install under baseline/_ref, one view per step on one GPU"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "GPU run of the reference extension (not a CPU baseline)"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    except Exception as ex:   # a broken install must not lose the reference arm: fall back to the oracle port
+        sys.stderr.write(f"baseline/_ref present but unusable ({ex!r}); timing the CPU oracle port instead\n")
+        return None
 
 
 def run_reference(args):
@@ -164,8 +273,14 @@ def run_reference(args):
         return
     import torch
     from multiview_inpaint_b200 import scenes as S
+    ref_line = run_reference_install(args)     # the reference's own CUDA rasterizer, if an install exists
+    if ref_line is not None:
+        print(json.dumps(ref_line), flush=True)
+        return
     from oracle import oracle as O
     O.build()
+    # all host cores, whatever the launcher exported: torchrun sets OMP_NUM_THREADS=1 for its workers
+    O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     cfg = S.CONFIGS[args.workload]
     sc = S.make_config_scene(args.workload)
     cams = S.orbit_cameras(max(args.views_per_rank, 2), cfg["W"], cfg["H"], max_deg=args.orbit_deg)
@@ -222,8 +337,10 @@ def bench_train_step(args, torch, _C, mv, S, sc, gauss, settings_list, dev, time
     caps, slots = [av.capacity(v) for v in mine], [av.slot(v) for v in mine]
 
     def step_fused():
+        # apply=True with asynchronous views: the capacities carry a 25 % margin over the learnt high-water mark and the
+        # overflow words are checked after the loop (`capacity_overflow` below)
         fused_train_step(pa, settings_list, losses, arena, lrs, flags=args.flags, pipeline=pipe, capacities=caps,
-                         async_results=slots, workspaces=workspaces)
+                         async_results=slots, workspaces=workspaces, apply=True, batched=not args.no_batched)
     l0 = _C.kernel_launches()
     for _ in range(2):
         step_fused()
@@ -267,6 +384,53 @@ def bench_train_step(args, torch, _C, mv, S, sc, gauss, settings_list, dev, time
             "views_per_step": nv, "steps": steps, "speedup": ms_t / ms_f}
 
 
+def parity_against_oracle(torch, _C, gauss, rs, wt, kept, P, W, H, tile_step, flags):
+    """Full-size parity (round-1 verdict item 1): the view the cpu_baseline leg has just pushed through the C oracle
+    against the same view through the C ABI (exact-size path).  Integers bit-exact: radii, num_rendered, the sorted
+    point list and the tile ranges; colour / depth against BASELINE's 1e-5 bar on the tiles the oracle blended;
+    gradients as max |a - b| / max |b|."""
+    import numpy as np
+    f, g_ref = kept["f"], kept["g"]
+    e = torch.empty(0, device=wt.device)
+    n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
+        rs.bg, gauss["means3D"], e, gauss["opacities"], gauss["scales"], gauss["rotations"], rs.scale_modifier, e, rs.viewmatrix,
+        rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, gauss["shs"], rs.sh_degree, rs.campos, rs.prefiltered,
+        flags=flags, capacity=0)
+    st = _C.unpack_state(P, W, H, n, geom, binning, img, flags)
+    out = {"view": "first view of rank 0", "tile_step": tile_step, "num_rendered": [int(n), int(f.num_rendered)]}
+    out["radii_equal"] = bool(np.array_equal(radii.cpu().numpy(), f.radii))
+    out["point_list_equal"] = bool(n == f.num_rendered and np.array_equal(st["point_list"].cpu().numpy().view(np.uint32), f.point_list))
+    out["ranges_equal"] = bool(np.array_equal(st["ranges"].cpu().numpy().view(np.uint32), f.ranges))
+    gx = (W + 15) // 16
+    tiles = np.arange(0, gx * ((H + 15) // 16), tile_step)
+    mask = np.zeros((H, W), bool)
+    for t in tiles:
+        mask[(t // gx) * 16:(t // gx) * 16 + 16, (t % gx) * 16:(t % gx) * 16 + 16] = True
+    c_err = np.abs(color.cpu().numpy() - f.color).max(0)[mask]
+    d_err = np.abs(depth.cpu().numpy()[0] - f.depth[0])[mask]
+    out["pixels_compared"] = int(mask.sum())
+    out["colour_max_abs_err"] = float(c_err.max())
+    out["colour_pixels_over_1e-5"] = int((c_err > 1e-5).sum())
+    out["depth_pixels_over_1e-5"] = int((d_err > 1e-5).sum())
+    if tile_step == 1:
+        grads = _C.rasterize_gaussians_backward(rs.bg, gauss["means3D"], radii, e, gauss["scales"], gauss["rotations"], rs.scale_modifier,
+                                                e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, wt, gauss["shs"], rs.sh_degree,
+                                                rs.campos, geom, n, binning, img, flags=flags)
+        names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
+        rel = {}
+        for name, t in zip(names, grads):
+            if name in ("dL_dcolors", "dL_dcov3D"):
+                continue
+            a, b = t.cpu().numpy().astype(np.float64), g_ref[name].astype(np.float64)
+            rel[name] = float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+        out["grad_rel_err"] = rel
+        out["grad_ok_1e-3"] = bool(max(rel.values()) < 1e-3)
+    out["ok"] = bool(out["radii_equal"] and out["point_list_equal"] and out["ranges_equal"] and out["colour_max_abs_err"] < 5e-3
+                     and out["colour_pixels_over_1e-5"] <= max(2, int(1e-4 * out["pixels_compared"]))
+                     and out.get("grad_ok_1e-3", True))
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -290,10 +454,34 @@ def run_ours(args):
     G = ((W + 15) // 16) * ((H + 15) // 16)
     gauss = {k: sc[k].to(dev) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
     vpr = args.views_per_rank
-    n_views = vpr * world
+    strong = args.total_views > 0
+    n_views = args.total_views if strong else vpr * world
     cams_cpu = S.orbit_cameras(n_views, W, H, max_deg=args.orbit_deg)
     mine = mv.shard_views(n_views, rank, world)
     bg = torch.zeros(3, device=dev)
+    balance = None
+    if strong and world > 1 and not args.no_balance:
+        # Views of an orbit differ in cost (num_rendered): learn every view's N with the round-robin map, then give each
+        # rank a set of views of about equal total N (longest-processing-time first).  SURVEY 8e.
+        e = torch.empty(0, device=dev)
+        n_of = torch.zeros(n_views, dtype=torch.int64, device=dev)
+        for v in mine:
+            c = cams_cpu[v].to(dev)
+            n_of[v] = _C.rasterize_gaussians(bg, gauss["means3D"], e, gauss["opacities"], gauss["scales"], gauss["rotations"], 1.0, e,
+                                             c.world_view_transform, c.full_proj_transform, c.tanfovx, c.tanfovy, H, W, gauss["shs"],
+                                             D, c.camera_center, False, flags=args.flags, capacity=0)[0]
+        dist.all_reduce(n_of)
+        n_list = [int(x) for x in n_of.tolist()]
+        loads, assign = [0] * world, [[] for _ in range(world)]
+        for v in sorted(range(n_views), key=lambda v: -n_list[v]):
+            r = min(range(world), key=lambda r: (loads[r], len(assign[r])))
+            assign[r].append(v)
+            loads[r] += n_list[v]
+        rr_loads = [sum(n_list[v] for v in mv.shard_views(n_views, r, world)) for r in range(world)]
+        mine = sorted(assign[rank])
+        balance = {"views_per_rank": [len(a) for a in assign], "instances_max_over_mean": max(loads) / (sum(loads) / world),
+                   "round_robin_max_over_mean": max(rr_loads) / (sum(rr_loads) / world)}
+        torch.cuda.empty_cache()
 
     def settings(cam):
         return GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
@@ -471,6 +659,33 @@ def run_ours(args):
     #      rasterizer the reference depends on (GSR_FLAG_REFERENCE: host round trip for N, one 64-bit cub sort,
     #      thread-per-pixel blend, 9 atomics per pair), one view at a time on one stream, arena zeroed per step.
     #      A stand-in: the reference's own extension is not in its tree and cannot be built offline. ----
+    # ---- the DROP-IN path itself: GaussianRasterizer(...)(...) + loss.backward() one view at a time on one stream,
+    #      exactly as gs-simp/train.py:86-93 drives it through gaussian_renderer/__init__.py:85-93 (autograd Function,
+    #      allocator-owned buffers, capacity speculation inside the binding) -- what an UNCHANGED train.py sees. ----
+    dropin = None
+    if world == 1 and not args.no_dropin:
+        from multiview_inpaint_b200.rasterizer import GaussianRasterizer
+        leaves = {k: gauss[k].detach().clone().requires_grad_(True) for k in gauss}
+        sets = [settings(cams_dev[v]) for v in mine]
+
+        def step_dropin():
+            for rs, v in zip(sets, mine):
+                means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
+                color, radii, depth = GaussianRasterizer(raster_settings=rs)(
+                    means3D=leaves["means3D"], means2D=means2D, shs=leaves["shs"], colors_precomp=None,
+                    opacities=leaves["opacities"], scales=leaves["scales"], rotations=leaves["rotations"], cov3D_precomp=None)
+                (color * wts_dev[v]).sum().backward()
+            for t in leaves.values():
+                t.grad = None
+        for _ in range(3):
+            step_dropin()
+        dsteps = max(3, min(args.steps, 20))
+        ms_d = timed(step_dropin, dsteps)
+        dropin = {"value": len(mine) * dsteps / (ms_d / 1000.0), "unit": UNIT, "ms_per_view": ms_d / (len(mine) * dsteps), "steps": dsteps,
+                  "note": "GaussianRasterizer + loss.backward(), one view per call, default stream, as gs-simp/train.py:86-93 drives the "
+                          "drop-in; includes torch autograd, the (color * w).sum() loss and the per-call host read of num_rendered"}
+        del leaves
+
     ref_struct = None
     if world == 1 and not args.no_reference_structure:
         def step_refstruct():
@@ -510,53 +725,70 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ----
     peak, peak_kind = peaks()
-    alg = algorithmic_bytes(P, V, N, G, W, H, M)
+    nv_shared = 1 if args.no_batched else min(len(mine), 8)      # views per batched launch (GSR_MAX_BATCH)
+    alg = algorithmic_bytes(P, V, N, G, W, H, M, nv_shared)
+    alg_survey = survey_bytes(P, V, N, G, W, H, M)
+    n_view_steps = max(len(mine) * args.steps, 1)
     per_launch = {k: stage_ms[k] / max(stage_cnt[k], 1) for k in stage_ms}
-    per_view = {k: stage_ms[k] / max(len(mine) * args.steps, 1) for k in stage_ms}   # batched stages launch once per step
+    per_view = {k: stage_ms[k] / n_view_steps for k in stage_ms}   # batched stages launch once per step
+    views_per_launch = {k: (n_view_steps / stage_cnt[k] if stage_cnt[k] else 1.0) for k in stage_ms}
     dom = max((k for k in per_launch if k in alg), key=lambda k: stage_ms[k])
-    ach = alg[dom] / (per_launch[dom] / 1000.0) / 1e9 if per_launch[dom] > 0 else 0.0
+    launch_bytes = alg[dom] * views_per_launch[dom]                # algorithmic bytes of ONE launch of the dominant kernel
+    ach = launch_bytes / (per_launch[dom] / 1000.0) / 1e9 if per_launch[dom] > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+            if traffic is not None:
+                traffic = traffic * views_per_launch[dom]          # the capture is per view
         except Exception:
             traffic = None
+    ctr = issue_counters().get(dom, {})
+    issue_bound = dom.startswith("blend")
     b_view = sum(alg.values())
     ms_view = ms_total / views_total * world   # per-GPU time per view
-    stages = {k: {"ms_per_view": round(per_view[k], 4), "ms_per_launch": round(per_launch[k], 4), "alg_bytes_per_view": alg.get(k),
-                  "gbps": (round(alg[k] / (per_view[k] / 1000.0) / 1e9, 1) if k in alg and per_view[k] > 0 else None)}
+    stages = {k: {"ms_per_view": round(per_view[k], 4), "ms_per_launch": round(per_launch[k], 4),
+                  "alg_bytes_per_view": (int(alg[k]) if k in alg else None),
+                  "survey_bytes_per_view": alg_survey.get(k),
+                  "gbps": (round(alg[k] / (per_view[k] / 1000.0) / 1e9, 1) if k in alg and per_view[k] > 0 else None),
+                  "frac_hbm": (round(alg[k] / (per_view[k] / 1000.0) / 1e9 / peak, 3) if k in alg and per_view[k] > 0 else None)}
               for k in per_launch}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, **cfg, "views_per_rank": vpr, "views_per_step": n_views, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_front_end": not args.no_batched, "batched_geom_backward": not args.per_view_backward, "ar_chunks": args.ar_chunks, "P": P, "V": V, "N": N,
+        "config": {"workload": args.workload, **cfg, "views_per_rank": (None if strong else vpr), "views_per_step": n_views, "view_balance": balance, "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_front_end": not args.no_batched, "batched_geom_backward": not args.per_view_backward, "ar_chunks": args.ar_chunks, "P": P, "V": V, "N": N,
                    "G": G, "M": M, "flags": args.flags, "parallelism": f"views sharded over {world} rank(s), fp32 grad-arena all-reduce", "allreduce": comm,
+                   "allreduce_method": comm.get("method"),
                    "l2": "inputs (>= 700 MB of Gaussians per view) larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "alloc": {"cudaMalloc_in_timed_region": int(device_allocs), "reserved_gb": round(torch.cuda.memory_reserved(dev) / 2**30, 2)},
         "clocks": sampler.summary(),
         "profiled_ms_per_step": ms_prof / args.steps,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": traffic, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": alg[dom],
-                     "ms_per_launch": per_launch[dom],
-                     "note": ("the blend kernels gather through L2 and are bound by instruction issue, not by HBM (ncu: ~80 % "
-                              "issue-active, ~2 % DRAM; profiles/r01_v4_ncu_full.md), so their fraction of the HBM peak is low by "
-                              "construction; the HBM-bound stages are in `stages` (gbps) and the whole view in `view`")
-                             if dom.startswith("blend") else None,
-                     "view": {"alg_bytes": b_view, "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
+        # `achieved / peak / frac` are the contract's HBM figures for the dominant kernel (algorithmic bytes of one launch /
+        # its CUDA-event time / the measured copy peak).  The blend kernels gather 48-byte records that the 126 MB L2 serves
+        # (`traffic` << algorithmic bytes) and are bound by instruction ISSUE: their roof is the issue-slot utilisation
+        # `issue_active_frac` measured by ncu, not the HBM fraction, which is low by construction.
+        "roofline": {"bound": "issue" if issue_bound else "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": int(launch_bytes),
+                     "views_per_launch": views_per_launch[dom], "ms_per_launch": per_launch[dom],
+                     "issue_active_frac": ctr.get("issue_active_frac"), "warp_inst_per_launch": ctr.get("warp_inst"),
+                     "counters_from": ctr.get("source"),
+                     "view": {"alg_bytes": int(b_view), "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
                               "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
         "stages": stages,
         # SURVEY 8d timing protocol: forward, backward and forward+backward reported separately (stage-profiler pass,
-        # one stream, per view; the two-stream timed loop above overlaps them: ms_per_step / views < the sum)
+        # one stream, per view)
         "split": {"fwd_ms_per_view": round(sum(per_view[k] for k in FWD_STAGES if k in per_view), 4),
                   "bwd_ms_per_view": round(sum(per_view[k] for k in BWD_STAGES if k in per_view), 4),
                   "fwd_bwd_ms_per_view_serial": round(sum(per_view[k] for k in FWD_STAGES + BWD_STAGES if k in per_view), 4),
-                  "fwd_bwd_ms_per_view_pipelined": round(ms_view, 4)},
+                  "fwd_bwd_ms_per_view_timed_loop": round(ms_view, 4)},
     }
+    if dropin is not None:
+        line["dropin"] = dropin
     if ref_struct is not None:
         line["reference_structure"] = ref_struct
     if train_step is not None:
@@ -570,11 +802,18 @@ def run_ours(args):
             tile_step = args.cpu_tile_step or 1
             cpu_view_seconds(sc, cams_cpu[0], wts_cpu[mine[0]].numpy(), 8)          # warm-up (page-in, thread pool)
             ests, meas, parts, t_start = [], 0.0, {}, time.perf_counter()
+            kept = {}
             while len(ests) < 8 and (time.perf_counter() - t_start < 15.0 or len(ests) < 2):
                 v = mine[len(ests) % len(mine)]
-                est, m, parts = cpu_view_seconds(sc, cams_cpu[v], wts_cpu[v].numpy(), tile_step)
+                est, m, parts = cpu_view_seconds(sc, cams_cpu[v], wts_cpu[v].numpy(), tile_step, keep=(kept if not ests else None))
                 ests.append(est)
                 meas += m
+            # the oracle has just computed view mine[0] in full: compare it with the CUDA path instead of throwing it away
+            try:
+                line["parity_headline"] = parity_against_oracle(torch, _C, gauss, settings(cams_dev[mine[0]]), wts_dev[mine[0]], kept,
+                                                                P, W, H, tile_step, args.flags)
+            except Exception as ex:
+                line["parity_headline"] = {"failed": repr(ex)[:300]}
             est = sum(ests) / len(ests)
             line["cpu_baseline"] = {"value": 1.0 / est, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
                                     "sample": f"{len(ests)} full fwd+bwd view(s) of '{args.workload}' through the C oracle (OpenMP), blend on "
@@ -636,7 +875,7 @@ def run_infer(args):
     def step_resident(pipe=pipe):
         mv.cuda_views_render(gauss, [settings(cams_dev[v]) for v in mine], flags=args.flags,
                              capacities=[av.capacity(v) for v in mine], async_results=[av.slot(v) for v in mine],
-                             pipeline=pipe, workspaces=workspaces)
+                             pipeline=pipe, workspaces=workspaces, batched=not args.no_batched)
         throttle.tick(dev)
 
     # e2e: camera from pinned host memory in, colour + depth to pinned host memory out (what the PNG / NPY writer reads)
@@ -661,7 +900,8 @@ def run_infer(args):
             host_color[k].copy_(color, non_blocking=True)
             host_depth[k].copy_(depth, non_blocking=True)
         mv.cuda_views_render(gauss, [stage(v) for v in mine], flags=args.flags, capacities=[av.capacity(v) for v in mine],
-                             async_results=[av.slot(v) for v in mine], pipeline=pipe, workspaces=workspaces, sink=sink)
+                             async_results=[av.slot(v) for v in mine], pipeline=pipe, workspaces=workspaces, sink=sink,
+                             batched=not args.no_batched)
         torch.cuda.current_stream(dev).synchronize()     # the step's result is on the host
         assert not av.check(mine), "capacity overflow inside the timed region"
     h2d = len(mine) * 35 * 4
@@ -714,11 +954,12 @@ def run_infer(args):
             dist.destroy_process_group()
         return
     peak, peak_kind = peaks()
-    alg = algorithmic_bytes(P, V, N, G, W, H, M)
-    fwd_stages = ("preprocess", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward")
+    alg = algorithmic_bytes(P, V, N, G, W, H, M, 1 if args.no_batched else min(len(mine), 8))
+    fwd_stages = ("preprocess", "depth_sort", "duplicate", "tile_sort", "tile_ranges", "blend_forward")
     per_launch = {k: stage_ms[k] / max(stage_cnt[k], 1) for k in stage_ms if stage_cnt[k] > 0}
     dom = max((k for k in per_launch if k in fwd_stages), key=lambda k: stage_ms[k])
-    ach = alg[dom] / (per_launch[dom] / 1000.0) / 1e9
+    vpl = (len(mine) * args.steps) / max(stage_cnt[dom], 1)           # views per launch of the dominant stage
+    ach = alg[dom] * vpl / (per_launch[dom] / 1000.0) / 1e9
     b_view = sum(alg[k] for k in fwd_stages)
     ms_view = ms_total / views_total * world
     line = {
@@ -726,18 +967,20 @@ def run_infer(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "mode": "infer", **cfg, "views_per_rank": vpr, "views_per_step": n_views,
-                   "orbit_deg": args.orbit_deg, "streams": args.streams, "P": P, "V": V, "N": N, "G": G, "M": M, "flags": args.flags,
+                   "orbit_deg": args.orbit_deg, "streams": args.streams, "batched_front_end": not args.no_batched, "P": P, "V": V, "N": N, "G": G, "M": M, "flags": args.flags,
                    "parallelism": f"views sharded over {world} rank(s), no collective",
                    "l2": "inputs larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": views_total / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": sampler.summary(), "profiled_ms_per_step": ms_prof / args.steps,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": None, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": alg[dom],
+        "roofline": {"bound": "issue" if dom.startswith("blend") else "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_kind": "of " + peak_kind, "alg_bytes_per_launch": int(alg[dom] * vpl),
+                     "issue_active_frac": issue_counters().get(dom, {}).get("issue_active_frac"),
                      "ms_per_launch": per_launch[dom],
                      "view": {"alg_bytes": b_view, "ms": ms_view, "gbps": b_view / (ms_view / 1000.0) / 1e9,
                               "frac": b_view / (ms_view / 1000.0) / 1e9 / peak}},
-        "stages": {k: {"ms_per_launch": round(per_launch[k], 4), "alg_bytes_per_view": alg.get(k)} for k in per_launch},
+        "stages": {k: {"ms_per_launch": round(per_launch[k], 4), "ms_per_view": round(stage_ms[k] / max(len(mine) * args.steps, 1), 4),
+                       "alg_bytes_per_view": (int(alg[k]) if k in alg else None)} for k in per_launch},
     }
     to_disk = None
     if args.files > 0 and world == 1:

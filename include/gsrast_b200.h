@@ -381,8 +381,8 @@ const char* gsr_last_error(void);
 int gsr_version(void);
 
 /* Experiment switches (tools/ only; the product path never calls this).  knob 0: warp ranking of the radix sort
- * (0 match_any, 1 ballots = default, 2 shared-memory atomicOr); knob 1: 0 drops the per-instance tile_count atomics of
- * the expansion (results are then WRONG: timing experiments only). */
+ * (0 match_any, 1 ballots, 2 shared-memory atomicOr = default); knob 1: 0 drops the per-instance tile_count atomics of
+ * the expansion (results are then WRONG: timing experiments only); knob 2: resident CTAs per SM K1 is compiled for (4 / 5 / 6). */
 int gsr_debug_set(int knob, int value);
 
 #ifdef __cplusplus

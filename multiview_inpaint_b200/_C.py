@@ -28,6 +28,7 @@ FLAG_PRECISE = 2
 FLAG_REFERENCE = 4     # reference-structure ablation baseline (cub sort, thread-per-pixel blend, 9 atomics/pair)
 FLAG_ACCUMULATE = 8
 FLAG_ASYNC = 16
+MAX_BATCH = 8           # views per batched launch of the front end / blend kernels (GSR_MAX_BATCH)
 GM_MAX_VIEWS = 4        # views per launch of the batched per-Gaussian backward (csrc/geom_backward_multi.cu)
 NUM_STAGES = 10
 STAGE_NAMES = ("preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward",
@@ -123,6 +124,8 @@ _lib.gsr_inclusive_scan_u32.restype = _i
 _lib.gsr_inclusive_scan_u32.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp, _sz]
 _lib.gsr_get_layout.restype = _i
 _lib.gsr_get_layout.argtypes = [_i, _i, _i, _i64, _u32, C.POINTER(GsrLayout)]
+_lib.gsr_debug_set.restype = _i
+_lib.gsr_debug_set.argtypes = [_i, _i]
 _lib.gsr_kernel_launches.restype = C.c_uint64
 _lib.gsr_profile_enable.restype = None
 _lib.gsr_profile_enable.argtypes = [_i]
@@ -610,8 +613,6 @@ def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_coun
 
 def debug_set(knob: int, value: int):
     """Experiment switches of the library (gsr_debug_set); never used by the product path."""
-    _lib.gsr_debug_set.restype = _i
-    _lib.gsr_debug_set.argtypes = [_i, _i]
     _check(_lib.gsr_debug_set(int(knob), int(value)), "gsr_debug_set")
 
 

@@ -117,7 +117,10 @@ struct PreArgs {
   int nv;
 };
 
-__global__ void __launch_bounds__(256)
+int g_pre_min_blocks = 6;   // experiment switch (gsr_debug_set knob 2): resident CTAs per SM the kernel is compiled for
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
                   const float* __restrict__ scales, const float* __restrict__ rotations,
                   const float* __restrict__ opacities, const float* __restrict__ shs,
@@ -349,8 +352,13 @@ cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* 
     args.v[k] = views[k];
     args.v[k].cam.scale_modifier = scale_modifier;
   }
-  preprocess_kernel<<<(unsigned)cdiv(P, 256) * (unsigned)nv, 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs,
-                                                                        cov3D_precomp, colors_precomp, prefiltered, args);
+  const unsigned grid = (unsigned)cdiv(P, 256) * (unsigned)nv;
+  if (g_pre_min_blocks >= 6)
+    preprocess_kernel<6><<<grid, 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, prefiltered, args);
+  else if (g_pre_min_blocks == 5)
+    preprocess_kernel<5><<<grid, 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, prefiltered, args);
+  else
+    preprocess_kernel<4><<<grid, 256, 0, s>>>(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp, prefiltered, args);
   count_launch();
   return cudaGetLastError();
 }

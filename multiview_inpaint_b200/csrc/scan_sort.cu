@@ -256,77 +256,50 @@ struct RsPassArgs {
   RsPassSeg<KeyT> seg[GSR_MAX_BATCH];
 };
 
-template <typename StatusT>
-__device__ __forceinline__ StatusT ld_status(const volatile StatusT* p) { return *p; }
+// Look-back words are read and written with relaxed GPU-scope accesses (a `volatile` access compiles to a
+// system-scope strong one); each word carries its own flag, so no ordering with other memory is needed.
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // RANK: how the lanes of a warp find their equal-digit peers.
 //   0  match_any         one instruction, but MATCH.ANY iterates over the DISTINCT values of the warp: ~30 of them with
 //                        uniform 8-bit digits -- it was most of this kernel's time
 //   1  eight ballots     fixed cost: one VOTE + one select per digit bit (what cub's onesweep does)
 //   2  shared atomicOr   each lane ORs its lane bit into a per-(warp, digit) word and reads the word back
-template <typename KeyT, int ITEMS, typename StatusT, bool COMPACT, int RANK>
-__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? 4 : 2)
-rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int nbits) {
-  using ST = RsStatus<StatusT>;
-  constexpr int TILE = RS_THREADS * ITEMS;
-  static_assert(ITEMS % 2 == 0 && TILE < 65535, "packed 16-bit ranks");
-  const RsPassSeg<KeyT>& sg = args.seg[blockIdx.y];
-  // the element count may live on the device (no host round trip): grid is sized by capacity and
-  // surplus CTAs retire before taking a ticket
-  const int64_t n = sg.n_dev ? min((int64_t)*sg.n_dev, sg.n_cap) : sg.n_cap;
-  if ((int64_t)blockIdx.x * TILE >= n) return;
-  const KeyT* __restrict__ keys_in = sg.keys_in;
-  const uint32_t* __restrict__ vals_in = sg.vals_in;
-  volatile StatusT* status = reinterpret_cast<volatile StatusT*>(sg.status);
-  extern __shared__ __align__(16) unsigned char rs_smem[];
-  KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                  // [TILE]
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * TILE);    // [TILE]
-  uint32_t* s_warp_cnt = s_vals + TILE;                                             // [WARPS][256]
-  uint32_t* s_digit_off = s_warp_cnt + RS_WARPS * RS_RADIX;                         // [256]
-  uint32_t* s_global_off = s_digit_off + RS_RADIX;                                  // [256]
-  uint32_t* s_misc = s_global_off + RS_RADIX;                                       // [16]
-  uint32_t* s_match = s_misc + 16;                                                  // [WARPS][256], RANK == 2 only
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t mask = (1u << nbits) - 1;
-  if (tid == 0) s_misc[0] = atomicAdd(sg.ticket, 1u);
-  for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) {
-    s_warp_cnt[i] = 0;
-    if (RANK == 2) s_match[i] = 0;
-  }
-  __syncthreads();
-  const uint32_t tile = s_misc[0];
-  const int64_t base = (int64_t)tile * TILE;
-  const int64_t wbase = base + (int64_t)warp * 32 * ITEMS + lane;  // warp-striped arrangement
-
-  KeyT key[ITEMS];
-  uint32_t val[ITEMS];
-  uint32_t live = 0;  // bit r: item r takes part (inside the array and, in a COMPACT pass, not a culled sentinel)
-#pragma unroll
-  for (int r = 0; r < ITEMS; r++) {
-    const int64_t idx = wbase + r * 32;
-    key[r] = ~(KeyT)0;
-    val[r] = (uint32_t)idx;
-    if (idx < n) {
-      key[r] = keys_in[idx];
-      if (vals_in) val[r] = vals_in[idx];
-      if (!COMPACT || key[r] != ~(KeyT)0) live |= 1u << r;
-    }
-  }
-
-  // ---- stable ranking: per-warp digit counters + match_any multi-split ----
-  uint32_t rank2[ITEMS / 2];  // two 16-bit ranks per register
+// Phases of a tile (4096 pairs of 32-bit keys):
+//   1. keys in (warp-striped), 2. EARLY COUNTS: the tile's digit histogram by plain shared-memory atomics, published
+//   as the tile's look-back aggregate BEFORE the ranking -- successors find it there instead of spinning while this
+//   tile ranks (the spin was 11 % of the kernel's instructions), 3. stable ranking per warp, 4. look-back (eight
+//   predecessors per round trip), 5. reorder through shared memory (values are loaded here, not held in registers
+//   across the ranking), 6. run-contiguous scatter.  FULL tiles (every item takes part) run without per-item predicates.
+template <typename KeyT, int ITEMS, bool COMPACT, int RANK, bool FULL>
+__device__ __forceinline__ void rs_rank_items(const KeyT (&key)[ITEMS], uint32_t live, int shift, uint32_t mask, int lane, int warp,
+                                              uint32_t* s_warp_cnt, uint32_t* s_match, uint32_t (&rank2)[ITEMS / 2]) {
   const uint32_t lt_mask = (1u << lane) - 1;
 #pragma unroll
   for (int r = 0; r < ITEMS; r++) {
-    const bool ok = (live >> r) & 1u;
+    const bool ok = FULL || ((live >> r) & 1u);
     // items that do not take part get a private pseudo-digit: they never pair up and touch no counter
     const uint32_t d = ok ? rs_digit(key[r], shift, mask) : (0x100u | (uint32_t)lane);
     unsigned peers;
     if (RANK == 0) {
       peers = __match_any_sync(0xffffffffu, d);
     } else if (RANK == 1) {
-      peers = __ballot_sync(0xffffffffu, ok);   // items that take part
+      peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, ok);   // items that take part
 #pragma unroll
       for (int bit = 0; bit < 8; bit++) {
         const bool one = (d >> bit) & 1u;
@@ -353,9 +326,79 @@ rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int
     if (r & 1) rank2[r >> 1] |= rk << 16; else rank2[r >> 1] = rk;
     __syncwarp();
   }
+}
+
+template <typename KeyT, int ITEMS, typename StatusT, bool COMPACT, int RANK>
+__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? 4 : 2)
+rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int nbits) {
+  using ST = RsStatus<StatusT>;
+  constexpr int TILE = RS_THREADS * ITEMS;
+  static_assert(ITEMS % 2 == 0 && TILE < 65535, "packed 16-bit ranks");
+  const RsPassSeg<KeyT>& sg = args.seg[blockIdx.y];
+  // the element count may live on the device (no host round trip): grid is sized by capacity and
+  // surplus CTAs retire before taking a ticket
+  const int64_t n = sg.n_dev ? min((int64_t)*sg.n_dev, sg.n_cap) : sg.n_cap;
+  if ((int64_t)blockIdx.x * TILE >= n) return;
+  const KeyT* __restrict__ keys_in = sg.keys_in;
+  const uint32_t* __restrict__ vals_in = sg.vals_in;
+  StatusT* status = reinterpret_cast<StatusT*>(sg.status);
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(rs_smem);                                  // [TILE]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + sizeof(KeyT) * TILE);    // [TILE]
+  uint32_t* s_warp_cnt = s_vals + TILE;                                             // [WARPS][256]
+  uint32_t* s_digit_off = s_warp_cnt + RS_WARPS * RS_RADIX;                         // [256]
+  uint32_t* s_global_off = s_digit_off + RS_RADIX;                                  // [256]
+  uint32_t* s_misc = s_global_off + RS_RADIX;                                       // [16]
+  uint32_t* s_match = s_misc + 16;                                                  // [WARPS][256], RANK == 2 only
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t mask = (1u << nbits) - 1;
+  if (tid == 0) s_misc[0] = atomicAdd(sg.ticket, 1u);
+  for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) {
+    s_warp_cnt[i] = 0;
+    if (RANK == 2) s_match[i] = 0;
+  }
+  s_digit_off[tid] = 0;   // early counts accumulate here (RS_THREADS == RS_RADIX)
+  __syncthreads();
+  const uint32_t tile = s_misc[0];
+  const int64_t base = (int64_t)tile * TILE;
+  const int64_t wbase = base + (int64_t)warp * 32 * ITEMS + lane;  // warp-striped arrangement
+  const bool full = !COMPACT && base + TILE <= n;                   // CTA-uniform
+
+  KeyT key[ITEMS];
+  uint32_t live = 0;  // bit r: item r takes part (inside the array and, in a COMPACT pass, not a culled sentinel)
+  if (full) {
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) key[r] = keys_in[wbase + r * 32];
+    live = (1u << ITEMS) - 1;
+  } else {
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+      const int64_t idx = wbase + r * 32;
+      key[r] = ~(KeyT)0;
+      if (idx < n) {
+        key[r] = keys_in[idx];
+        if (!COMPACT || key[r] != ~(KeyT)0) live |= 1u << r;
+      }
+    }
+  }
+
+  // ---- early counts: the tile's digit histogram, published as the look-back aggregate before the ranking ----
+#pragma unroll
+  for (int r = 0; r < ITEMS; r++)
+    if ((live >> r) & 1u) atomicAdd(&s_digit_off[rs_digit(key[r], shift, mask)], 1u);
+  __syncthreads();
+  const uint32_t count = s_digit_off[tid];   // thread d owns digit d
+  StatusT* my = status + (size_t)tile * RS_RADIX + tid;
+  st_status(my, (tile == 0 ? ST::INC : ST::AGG) | (StatusT)count);
+
+  // ---- stable ranking: per-warp digit counters + warp multi-split ----
+  uint32_t rank2[ITEMS / 2];  // two 16-bit ranks per register
+  if (full) rs_rank_items<KeyT, ITEMS, COMPACT, RANK, true>(key, live, shift, mask, lane, warp, s_warp_cnt, s_match, rank2);
+  else rs_rank_items<KeyT, ITEMS, COMPACT, RANK, false>(key, live, shift, mask, lane, warp, s_warp_cnt, s_match, rank2);
   __syncthreads();
 
-  // ---- thread d owns digit d: warp offsets, tile count, look-back ----
+  // ---- thread d owns digit d: warp offsets, exclusive digit offsets inside the tile, look-back ----
   {
     const int d = tid;
     uint32_t run = 0;
@@ -365,7 +408,6 @@ rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int
       s_warp_cnt[w * RS_RADIX + d] = run;
       run += c;
     }
-    const uint32_t count = run;
     // exclusive scan of `count` over the 256 digits of this tile
     uint32_t x = count;
 #pragma unroll
@@ -382,44 +424,55 @@ rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int
     if (d == RS_RADIX - 1) s_misc[10] = digit_off + count;  // elements of this tile that take part
 
     StatusT excl = 0;
-    volatile StatusT* my = status + (size_t)tile * RS_RADIX + d;
-    if (tile == 0) {
-      *my = ST::INC | (StatusT)count;
-    } else {
-      *my = ST::AGG | (StatusT)count;
+    if (tile != 0) {
       int64_t t = (int64_t)tile - 1;
       bool found = false;
       while (!found) {
         StatusT st[RS_LOOKBACK];
 #pragma unroll
         for (int j = 0; j < RS_LOOKBACK; j++)
-          st[j] = (t - j >= 0) ? ld_status<StatusT>(status + (size_t)(t - j) * RS_RADIX + d) : ST::INC;  // before tile 0: "inclusive 0"
+          st[j] = (t - j >= 0) ? ld_status(status + (size_t)(t - j) * RS_RADIX + d) : ST::INC;  // before tile 0: "inclusive 0"
 #pragma unroll
         for (int j = 0; j < RS_LOOKBACK; j++) {
           if (!found) {
-            StatusT s = st[j];
-            while ((s >> ST::SHIFT) == 0) s = ld_status<StatusT>(status + (size_t)(t - j) * RS_RADIX + d);
-            excl += s & ST::MASK;
-            found = (s & ST::INC) != 0;
+            StatusT sv = st[j];
+            while ((sv >> ST::SHIFT) == 0) sv = ld_status(status + (size_t)(t - j) * RS_RADIX + d);
+            excl += sv & ST::MASK;
+            found = (sv & ST::INC) != 0;
           }
         }
         t -= RS_LOOKBACK;
       }
-      *my = ST::INC | ((excl + (StatusT)count) & ST::MASK);
+      st_status(my, ST::INC | ((excl + (StatusT)count) & ST::MASK));
     }
     s_global_off[d] = sg.global_base[d] + (uint32_t)excl - digit_off;   // positions are < 2^32: mod-2^32 arithmetic
   }
   __syncthreads();
 
   // ---- reorder through shared memory so that the global scatter is run-wise contiguous ----
+  if (full) {
+    uint32_t val[ITEMS];
 #pragma unroll
-  for (int r = 0; r < ITEMS; r++) {
-    if ((live >> r) & 1u) {
+    for (int r = 0; r < ITEMS; r++) val[r] = vals_in ? vals_in[wbase + r * 32] : (uint32_t)(wbase + r * 32);
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
       const uint32_t d = rs_digit(key[r], shift, mask);
       const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
       const uint32_t pos = s_digit_off[d] + s_warp_cnt[warp * RS_RADIX + d] + rk;
       s_keys[pos] = key[r];
       s_vals[pos] = val[r];
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+      if ((live >> r) & 1u) {
+        const int64_t idx = wbase + r * 32;
+        const uint32_t d = rs_digit(key[r], shift, mask);
+        const uint32_t rk = (r & 1) ? (rank2[r >> 1] >> 16) : (rank2[r >> 1] & 0xffffu);
+        const uint32_t pos = s_digit_off[d] + s_warp_cnt[warp * RS_RADIX + d] + rk;
+        s_keys[pos] = key[r];
+        s_vals[pos] = vals_in ? vals_in[idx] : (uint32_t)idx;
+      }
     }
   }
   __syncthreads();
@@ -436,7 +489,7 @@ rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int
   }
 }
 
-int g_rs_rank_mode = 1;   // see rs_onesweep_kernel; gsr_debug_set(0, mode) switches it for experiments
+int g_rs_rank_mode = 2;   // see rs_onesweep_kernel (measured: 2 < 1 < 0 in time); gsr_debug_set(0, mode) switches it for experiments
 
 template <typename KeyT, typename StatusT, bool COMPACT, int RANK>
 static cudaError_t rs_launch_pass_r(cudaStream_t s, const RsPassArgs<KeyT>& pa, int nseg, int64_t max_tiles, int shift, int bits) {
@@ -458,8 +511,8 @@ template <typename KeyT, typename StatusT, bool COMPACT>
 static cudaError_t rs_launch_pass(cudaStream_t s, const RsPassArgs<KeyT>& pa, int nseg, int64_t max_tiles, int shift, int bits) {
   switch (g_rs_rank_mode) {
     case 0: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 0>(s, pa, nseg, max_tiles, shift, bits);
-    case 2: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 2>(s, pa, nseg, max_tiles, shift, bits);
-    default: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 1>(s, pa, nseg, max_tiles, shift, bits);
+    case 1: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 1>(s, pa, nseg, max_tiles, shift, bits);
+    default: return rs_launch_pass_r<KeyT, StatusT, COMPACT, 2>(s, pa, nseg, max_tiles, shift, bits);
   }
 }
 

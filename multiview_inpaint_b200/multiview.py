@@ -381,6 +381,10 @@ def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena
     statistics are WRITTEN into `arena` (added with `accumulate`), so the arena needs no zeroing."""
     from . import _C
     if not states:
+        # a rank without views (fewer views than ranks): the batched kernel WRITES the arena, so nothing else would
+        # clear last step's gradients and statistics -- this rank must contribute zeros to the all-reduce
+        if not accumulate:
+            arena.zero_()
         return None
     views = [dict(radii=s.radii, geom=s.geom, scratch=s.scratch, viewmatrix=s.settings.viewmatrix,
                   projmatrix=s.settings.projmatrix, campos=s.settings.campos, tanfovx=s.settings.tanfovx,
@@ -413,18 +417,21 @@ def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewSta
     views = [dict(radii=s.radii, geom=s.geom, scratch=s.scratch, viewmatrix=s.settings.viewmatrix,
                   projmatrix=s.settings.projmatrix, campos=s.settings.campos, tanfovx=s.settings.tanfovx,
                   tanfovy=s.settings.tanfovy, width=s.settings.image_width, height=s.settings.image_height) for s in states]
-    rs = states[0].settings
+    rs = states[0].settings if states else None
     dev = gaussians["means3D"].device
     main, comm = torch.cuda.current_stream(dev), arena.comm_stream()
+    if not states:
+        arena.zero_()   # a rank without views contributes zeros, and still takes part in every barrier and reduction below
     for st in states:
         for t in (st.radii, st.geom, st.scratch):
             t.record_stream(main)
     step = ((P + chunks - 1) // chunks + 31) // 32 * 32
     for g0 in range(0, P, step):
         g1 = min(P, g0 + step)
-        _C.backward_geom_multi(gaussians["means3D"], gaussians["shs"], gaussians["scales"], gaussians["rotations"],
-                               rs.scale_modifier, rs.sh_degree, views, arena.views,
-                               stats=(arena.grad_norm_accum, arena.visible_count, arena.max_radii), flags=flags, g_range=(g0, g1))
+        if states:
+            _C.backward_geom_multi(gaussians["means3D"], gaussians["shs"], gaussians["scales"], gaussians["rotations"],
+                                   rs.scale_modifier, rs.sh_degree, views, arena.views,
+                                   stats=(arena.grad_norm_accum, arena.visible_count, arena.max_radii), flags=flags, g_range=(g0, g1))
         ev = torch.cuda.Event()
         ev.record(main)
         comm.wait_event(ev)
@@ -569,7 +576,8 @@ def sharded_step(view_fwd_bwd: Callable[[int], None], n_views: int, arena: GradA
 def cuda_views_render(gaussians: dict, settings_list: Sequence, flags: int = 0, capacities: Sequence[int] | None = None,
                       async_results: Sequence | None = None, pipeline: ViewPipeline | None = None,
                       workspaces: Sequence | None = None,
-                      sink: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None] | None = None) -> list[ViewResult]:
+                      sink: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None] | None = None,
+                      batched: bool = False) -> list[ViewResult]:
     """Batched inference: the forward of every view of `settings_list` -- the loops of
     render.py:32-39, render_depth.py:31-39 and gen_seq.py:36-58, which call render() once per camera under
     no_grad and then block on an image write.  Views alternate over the pipeline's streams (front end of view
@@ -580,6 +588,24 @@ def cuda_views_render(gaussians: dict, settings_list: Sequence, flags: int = 0, 
     import contextlib
     from . import _C
     out = []
+    if batched and capacities and async_results and all(c > 0 for c in capacities) and settings_list \
+            and not (flags & (_C.FLAG_BINNING_KEY64 | _C.FLAG_REFERENCE)):
+        # one launch per stage for up to eight views at a time (gsr_forward_views); groups alternate over the pipeline's streams
+        with torch.no_grad(), (pipeline.step() if pipeline else contextlib.nullcontext()):
+            for k0 in range(0, len(settings_list), _C.MAX_BATCH):
+                sl = slice(k0, min(k0 + _C.MAX_BATCH, len(settings_list)))
+                with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
+                    rss = [s() if callable(s) else s for s in settings_list[sl]]
+                    e = torch.empty(0, device=gaussians["means3D"].device)
+                    outs = _C.forward_views(rss[0].bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"],
+                                            gaussians["rotations"], rss[0].scale_modifier, e, rss, gaussians["shs"], rss[0].sh_degree,
+                                            rss[0].prefiltered, capacities[sl], async_results[sl],
+                                            workspaces=workspaces[sl] if workspaces else None, flags=flags)
+                    for j, o in enumerate(outs):
+                        if sink is not None:
+                            sink(k0 + j, o[1], o[6], o[2])
+                        out.append(ViewResult(o[1], o[6], o[2], -1))
+        return out
     with torch.no_grad(), (pipeline.step() if pipeline else contextlib.nullcontext()):
         for k, settings in enumerate(settings_list):
             with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):

@@ -285,13 +285,34 @@ class ViewLoss:
 
 def fused_train_step(params: GaussianParamArena, settings_list: Sequence, losses: Sequence[ViewLoss], arena: GradArena,
                      lrs: dict, flags: int = 0, pipeline: ViewPipeline | None = None, all_reduce: bool = False,
-                     capacities=None, async_results=None, workspaces=None, chunks: int = 4):
+                     capacities=None, async_results=None, workspaces=None, chunks: int = 4, apply: bool | None = None,
+                     batched: bool = False):
     """One optimisation step on this rank's views (train.py:86-128 for a batch of views; with `all_reduce` the
     gradient arena is summed over ranks first).  Returns the per-view ViewState list; the densification
-    statistics of the step are in `arena` (grad_norm_accum / visible_count / max_radii)."""
+    statistics of the step are in `arena` (grad_norm_accum / visible_count / max_radii).
+
+    `apply`: whether Adam runs inside this call.  Default: yes for the synchronous path, NO for the asynchronous one
+    (`async_results`): there the host has not seen the views' (num_rendered, overflow) words yet, and a view that
+    outgrew its binning capacity has a truncated instance list -- wrong image, wrong gradients -- which must not reach
+    the Adam moments.  The asynchronous caller therefore finishes the step itself:
+
+        states = fused_train_step(..., async_results=slots)          # gradients only, nothing blocks
+        torch.cuda.current_stream().synchronize()                    # (or the step's natural sync point)
+        if async_views.check(views):  <raise capacities, redo the step>   # the parameters are still untouched
+        else:                         params.apply_gradients(arena, lrs)
+
+    `apply=True` with `async_results` is allowed for callers that size the capacities so that an overflow cannot
+    happen (bench.py: 25 % margin over a learnt high-water mark, checked after the timed region).
+
+    Deviation from train.py:112-128, stated: the reference runs densify_and_prune / reset_opacity BEFORE
+    optimizer.step(); on those iterations the re-created parameters have no .grad and Adam skips them.  Callers that
+    need that trajectory pass apply=False on densification iterations, densify, and skip apply_gradients."""
     g = params.activate()
     states = cuda_views_fwd_bwd(g, settings_list, losses, arena, flags=flags, capacities=capacities,
                                 async_results=async_results, pipeline=pipeline, all_reduce=all_reduce, chunks=chunks,
-                                workspaces=workspaces)
-    params.apply_gradients(arena, lrs)
+                                workspaces=workspaces, batched=batched)
+    if apply is None:
+        apply = async_results is None
+    if apply:
+        params.apply_gradients(arena, lrs)
     return states

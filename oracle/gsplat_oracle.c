@@ -56,6 +56,16 @@ int gso_num_threads(void) {
 #endif
 }
 
+/* bench.py --impl reference sets the thread count itself: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+ * made the reference arm of the multi-GPU runs 9x slower than its own single-process run (round-1 verdict). */
+void gso_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* A.4 getHigherMsb */
 uint32_t gso_higher_msb(uint32_t n) {
   uint32_t msb = sizeof(n) * 4;

@@ -121,6 +121,7 @@ void gso_mark_visible(int P, const float* means3D, const float* viewmatrix, uint
 void gso_knn3_mean_dist2(int P, const float* pts, const int32_t* queries, int nq, float* out);
 
 int gso_num_threads(void);
+void gso_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

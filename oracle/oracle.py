@@ -60,6 +60,13 @@ def num_threads() -> int:
     return int(lib().gso_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the oracle from here on (bench.py's reference arm: all host cores, whatever
+    OMP_NUM_THREADS the launcher exported).  Returns the count in effect."""
+    lib().gso_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def higher_msb(n: int) -> int:
     return int(lib().gso_higher_msb(C.c_uint32(n)))
 
