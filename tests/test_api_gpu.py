@@ -76,6 +76,13 @@ def test_render_replay_train_step_and_consumers(oracle):
     assert not cam.camera_center.is_contiguous() or cam.camera_center.storage_offset() >= 0
     bg = torch.rand(3, device="cuda")                                   # train.py:84 random background
     pkg = render(cam, pc, Pipe(), bg)
+    # names extracted from the reference file by tests/golden/make_contract_golden.py (ast walk), not typed in here
+    import inspect, json, os
+    contract = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "render_contract.json")))
+    assert list(pkg) == contract["result_keys"]
+    src = inspect.getsource(render)
+    for kw in contract["settings_keywords"] + contract["call_keywords"] + contract["rasterizer_ctor_keywords"]:
+        assert kw + "=" in src, kw     # the replay passes every keyword the reference passes
     image, depth, radii = pkg["render"], pkg["depth"], pkg["radii"]
     assert image.shape == (3, 96, 128) and depth.shape == (1, 96, 128) and radii.shape == (4000,)
     assert radii.dtype == torch.int32 and pkg["visibility_filter"].dtype == torch.bool
