@@ -58,14 +58,114 @@ __device__ __forceinline__ float warp_transpose_reduce9(float v0, float v1, floa
   return k;
 }
 
+// ---- the nine sums as ONE tensor-core contraction (default, non-PRECISE flavour) -------------------------------------
+// Every one of the nine per-(warp, Gaussian) sums has the form  sum_p W(g, p) * F(p, f):
+//     dL/dcolor_c  = sum_p dch(g,p)          * dL_dpixel_c(p)                       W1 = alpha * T,  F1 = dL_dpixel (3 cols)
+//     S0,Su,..,Svv = sum_p G*dL_dalpha(g,p)  * {1, u, v, u^2, u v, v^2}(p)          W3 = G * dL_dalpha, FP = monomials of the
+//                                                                                   pixel's offset (u, v) from the sub-tile centre
+// and the sums the accumulator holds follow from the six moments with the Gaussian's own offset (X, Y) from that centre
+// (dx = X - u, dy = Y - v):   sum w dx = X S0 - Su,   sum w dx^2 = X^2 S0 - 2 X Su + Suu,   sum w dx dy = X Y S0 - X Sv - Y Su + Suv, ...
+// (u, v are half-integers |u| <= 3.5, |v| <= 1.5: no cancellation beyond what the per-pixel sums have, and the monomials
+// are exact in tf32).  So instead of a 12-shuffle butterfly per (warp, Gaussian) -- ~45 of the ~106 instructions of a live
+// hit -- a lane stores its two weights W1, W3 into a warp-private shared-memory tile [8 Gaussians][32 pixels], and every
+// eighth live hit the warp runs D[feature][Gaussian] = F^T x W^T as mma.sync.m16n8k8 (tf32 inputs, fp32 accumulate):
+// 4 k-steps x {hi, lo} x 2 matrices = 16 MMAs per 8 hits.  W (and dL_dpixel) are split hi + lo (hi = upper 19 bits,
+// lo = x - hi, exact), so the products carry ~21 bits: the sums differ from the shuffle path by fp32 rounding only.
+// Fragment layout (PTX ISA, m16n8k8 .tf32; q = lane >> 2, t = lane & 3):  A a0 = (row q, k t), a2 = (row q, k t + 4), rows
+// q + 8 (a1, a3) are zero;  B b0 = (k t, col q), b1 = (k t + 4, col q);  D c0 = (row q, col 2 t), c1 = (row q, col 2 t + 1).
+// k-step s maps k = t -> pixel 8 t + 2 s and k = t + 4 -> pixel 8 t + 2 s + 1 on BOTH operands, so a thread's fragments of
+// all four k-steps are the 8 consecutive floats [8 t, 8 t + 8) of row q of a W tile: two LDS.128 (row stride 36 floats
+// keeps them conflict free).  The epilogue transposes D through shared memory (slot-major), forms the nine values per
+// Gaussian and issues them as 3 predicated RED instructions per 8 hits (was 8).
+constexpr int MG_SLOTS = 8;                        // Gaussians per contraction (the MMA's N)
+constexpr int MG_STRIDE = 36;                      // floats per row of a W tile [8 slots][32 pixels]
+constexpr int MG_TILE_BYTES = MG_SLOTS * MG_STRIDE * 4;          // 1152
+constexpr int MG_F_ROWS = 6;                       // feature rows kept (rows 6, 7 of the MMA's M are never read back)
+constexpr int MG_F_STRIDE = 72;                    // floats per feature row: 32 pixels x {F1, FP} interleaved (+ 8 pad)
+constexpr int MG_F_BYTES = MG_F_ROWS * MG_F_STRIDE * 4;          // 1728
+constexpr int MG_INFO_OFF = 2 * MG_TILE_BYTES;                   // per warp: W1 tile | W3 tile | info[8] | feature table
+constexpr int MG_F_OFF = MG_INFO_OFF + MG_SLOTS * 16;
+constexpr int MG_WARP_BYTES = MG_F_OFF + MG_F_BYTES;             // 4160
+constexpr int MG_M_STRIDE = 20;                    // floats per slot row of the transposed result (aliases the W1 tile)
+
+// A = {a0, a1, a2, a3} (four consecutive registers, straight from one LDS.128), B = {b0, b1}
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const float4& a, float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Contracts the `ns` filled slots of the warp's tiles and adds the nine sums of each into its Gaussian's accumulator.
+// s_warp: the warp's region {W1 tile, W3 tile, info[8], feature table}; (cx, cy): sub-tile centre.
+// The feature table interleaves F1 and FP per pixel, {F1[f][p], FP[f][p]}: one LDS.128 at pixel pair (8 t + 2 s, + 1) is
+// the A fragment {a0, a1, a2, a3} of k-step s with F1 in rows 0..7 and FP in rows 8..15 of the MMA's M.  Multiplied with
+// W1 the rows 0..7 (c0, c1) are the colour sums and rows 8..15 are discarded; multiplied with W3 it is the other way round.
+__device__ __forceinline__ void flush_slots(uint32_t s_warp, int lane, uint32_t ns, float cx, float cy, float* __restrict__ gacc) {
+  __syncwarp();
+  const uint32_t q = (uint32_t)lane >> 2, t = (uint32_t)lane & 3;
+  const uint32_t w_off = s_warp + (q * MG_STRIDE + 8 * t) * 4;
+  const uint32_t f_off = s_warp + MG_F_OFF + (min(q, (uint32_t)(MG_F_ROWS - 1)) * MG_F_STRIDE + 16 * t) * 4;
+  float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d3[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  const float4 w1a = lds128(w_off), w1b = lds128(w_off + 16);
+  const float4 w3a = lds128(w_off + MG_TILE_BYTES), w3b = lds128(w_off + MG_TILE_BYTES + 16);
+  const float w1[8] = {w1a.x, w1a.y, w1a.z, w1a.w, w1b.x, w1b.y, w1b.z, w1b.w};
+  const float w3[8] = {w3a.x, w3a.y, w3a.z, w3a.w, w3b.x, w3b.y, w3b.z, w3b.w};
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const float4 a = lds128(f_off + 16 * s);
+    const float g0 = tf32_hi(w1[2 * s]), g1 = tf32_hi(w1[2 * s + 1]);
+    mma_m16n8k8_tf32(d1, a, g0, g1);
+    mma_m16n8k8_tf32(d1, a, w1[2 * s] - g0, w1[2 * s + 1] - g1);
+    const float h0 = tf32_hi(w3[2 * s]), h1 = tf32_hi(w3[2 * s + 1]);
+    mma_m16n8k8_tf32(d3, a, h0, h1);
+    mma_m16n8k8_tf32(d3, a, w3[2 * s] - h0, w3[2 * s + 1] - h1);
+  }
+  __syncwarp();   // every lane has its W1 fragments: the W1 tile now becomes M[slot][16] (stride MG_M_STRIDE)
+  {
+    const uint32_t r0 = s_warp + ((2 * t) * MG_M_STRIDE + q) * 4, r1 = r0 + MG_M_STRIDE * 4;
+    sts32(r0, __float_as_uint(d3[2]));        // rows 8..15 of FP|F1 x W3: moment q of slots 2 t, 2 t + 1
+    sts32(r1, __float_as_uint(d3[3]));
+    sts32(r0 + 32, __float_as_uint(d1[0]));   // rows 0..7 of F1 x W1: colour row q (0..2 hi parts, 3..5 lo parts)
+    sts32(r1 + 32, __float_as_uint(d1[1]));
+  }
+  __syncwarp();
+  const uint32_t slot = q, part = t;
+  const uint32_t row = s_warp + slot * (MG_M_STRIDE * 4);
+  const float4 m0 = lds128(row), m1 = lds128(row + 16), m2 = lds128(row + 32), m3 = lds128(row + 48);
+  const float4 inf = lds128(s_warp + MG_INFO_OFF + slot * 16);                       // x, y, opacity, id
+  const float S0 = m0.x, Su = m0.y, Sv = m0.z, Suu = m0.w, Suv = m1.x, Svv = m1.y;
+  const float X = inf.x - cx, Y = inf.y - cy, op = inf.z, nh = -0.5f * inf.z;
+  const float ax = fmaf(X, S0, -Su), ay = fmaf(Y, S0, -Sv);                          // sum W3 dx, sum W3 dy
+  // branch-free: part 0..2 -> (dL/dcolor_part, [3 + part]), part 3 -> ([6], [7]) and [8]
+  const float col = (part == 0 ? m2.x : (part == 1 ? m2.y : m2.z)) + (part == 0 ? m2.w : (part == 1 ? m3.x : m3.y));
+  const float xy = nh * (fmaf(X, ay, Suv) - Y * Su);                                 // -0.5 sum w dx dy
+  const float xx = nh * fmaf(X, ax - Su, Suu), yy = nh * fmaf(Y, ay - Sv, Svv);      // -0.5 sum w dx^2, -0.5 sum w dy^2
+  const float va = part == 3 ? xy : col;
+  const float vb = part == 0 ? op * ax : (part == 1 ? op * ay : (part == 2 ? xx : yy));
+  const uint32_t oa = part == 3 ? 6u : part, ob = part == 3 ? 7u : 3u + part;
+  if (slot < ns) {
+    float* g = gacc + (size_t)__float_as_uint(inf.w) * 12;
+    atomicAdd(g + oa, va);
+    atomicAdd(g + ob, vb);
+    if (part == 3) atomicAdd(g + 8, S0);                                             // dL/dopacity
+  }
+  __syncwarp();   // M consumed before the next hits overwrite the W1 tile
+}
+
+bool g_bwd_mma = true;   // gsr_debug_set knob 3: 0 = the shuffle-butterfly reduction (round-1 kernel), for A/B timing
+
 struct BlendBwdArgs {
   BlendBwdView v[GSR_MAX_BATCH];
 };
 
 // blockIdx.y = view of a batched step
-template <bool PRECISE>
-__global__ void __launch_bounds__(256)
+template <bool PRECISE, bool MMA>
+__global__ void __launch_bounds__(256, MMA ? 4 : 0)
 blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
+  static_assert(!(PRECISE && MMA), "the parity build keeps the oracle's op order: no tensor-core contraction");
   const BlendBwdView& a = args.v[blockIdx.y];
   const int W = a.W, H = a.H, grid_x = a.grid_x;
   if ((int)blockIdx.x >= a.G) return;
@@ -112,6 +212,29 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
   const uint32_t one = (uint32_t)(px >= 0);  // == 1, per-lane and opaque to ptxas (see K6)
   const bool red_lane = (lane & 3) == 0 || lane == 2;
   const uint32_t red_off = lane == 2 ? 8u : (uint32_t)(lane >> 2);
+
+  // tensor-core path: the warp's W tiles and its feature table {F1 = this warp's dL_dpixel (rows 0..2 hi, 3..5 lo),
+  // FP = monomials of the pixel's offset from the sub-tile centre}, interleaved per pixel
+  uint32_t s_warp = 0, w_addr = 0, i_addr = 0, ns = 0;
+  float sub_cx = 0.0f, sub_cy = 0.0f;
+  if constexpr (MMA) {
+    __shared__ __align__(16) unsigned char s_mma[8 * MG_WARP_BYTES];
+    s_warp = pin_reg((uint32_t)__cvta_generic_to_shared(s_mma) + warp * MG_WARP_BYTES);
+    const uint32_t f = s_warp + MG_F_OFF + lane * 8;
+    const float h0 = tf32_hi(dLp0), h1 = tf32_hi(dLp1), h2 = tf32_hi(dLp2);
+    const float u = (float)(lane & 7) - 3.5f, v = (float)(lane >> 3) - 1.5f;
+    const float f1[MG_F_ROWS] = {h0, h1, h2, dLp0 - h0, dLp1 - h1, dLp2 - h2};
+    const float fp[MG_F_ROWS] = {1.0f, u, v, u * u, u * v, v * v};
+#pragma unroll
+    for (int r = 0; r < MG_F_ROWS; r++) {
+      sts32(f + r * MG_F_STRIDE * 4, __float_as_uint(f1[r]));
+      sts32(f + r * MG_F_STRIDE * 4 + 4, __float_as_uint(fp[r]));
+    }
+    w_addr = s_warp + lane * 4;
+    i_addr = s_warp + MG_INFO_OFF;
+    sub_cx = (float)(tile_x0 + (warp & 1) * 8) + 3.5f;
+    sub_cy = (float)(tile_y0 + (warp >> 1) * 4) + 1.5f;
+  }
 
   const uint32_t warp_last = __reduce_max_sync(0xffffffffu, last);
   if (lane == 0) s_wmax[warp] = warp_last;
@@ -195,6 +318,22 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
             acc2 = fmaf(alpha, d2, acc2);
             dch = alpha * T;
           }
+          if constexpr (MMA) {
+            // this hit becomes slot `ns` of the warp's tiles: W1 = alpha * T, W3 = G * dL_dalpha (exact zeros for lanes
+            // that do not contribute), plus the Gaussian's (x, y, opacity, id) for the epilogue
+            sts32(w_addr, __float_as_uint(dch));
+            sts32(w_addr + MG_TILE_BYTES, __float_as_uint(G * dL_dalpha));
+            if (lane == 0) sts128(i_addr, make_float4(e0.x, e0.y, e1.y, e1.w));
+            w_addr += MG_STRIDE * 4;
+            i_addr += 16;
+            if (++ns == MG_SLOTS) {
+              flush_slots(s_warp, lane, MG_SLOTS, sub_cx, sub_cy, gacc);
+              ns = 0;
+              w_addr = s_warp + lane * 4;
+              i_addr = s_warp + MG_INFO_OFF;
+            }
+            continue;
+          }
           const float w = MUL(MUL(e1.y, dL_dalpha), G);  // dL_dG * G
           const float wx = MUL(w, dx), wy = MUL(w, dy);
           const float r9 = warp_transpose_reduce9(MUL(dch, dLp0), MUL(dch, dLp1), MUL(dch, dLp2), wx, wy,
@@ -205,6 +344,9 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
         }
       }
     }
+  }
+  if constexpr (MMA) {
+    if (ns) flush_slots(s_warp, lane, ns, sub_cx, sub_cy, gacc);   // the warp's last, partial group (warp-uniform)
   }
 }
 
@@ -220,10 +362,19 @@ cudaError_t launch_blend_backward(cudaStream_t s, const BlendBwdView* views, int
     max_g = args.v[k].G > max_g ? args.v[k].G : max_g;
   }
   if (max_g == 0) return cudaSuccess;
-  if (precise)
-    blend_backward_kernel<true><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
-  else
-    blend_backward_kernel<false><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
+  if (precise) {
+    blend_backward_kernel<true, false><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
+  } else if (g_bwd_mma) {
+    static bool carveout_set = false;   // 42 KB of static shared memory per CTA, four CTAs per SM: ask for the large carve-out
+    if (!carveout_set) {
+      cudaFuncSetAttribute(blend_backward_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (int)cudaSharedmemCarveoutMaxShared);
+      carveout_set = true;
+    }
+    blend_backward_kernel<false, true><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
+  } else {
+    blend_backward_kernel<false, false><<<dim3((unsigned)max_g, (unsigned)nv), 256, 0, s>>>(args);
+  }
   count_launch();
   return cudaGetLastError();
 }

@@ -126,6 +126,7 @@ BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags);
 // experiment switches behind gsr_debug_set (never changed by the product path)
 extern int g_rs_rank_mode;         // scan_sort.cu: 0 match_any, 1 ballots, 2 shared atomicOr (default)
 extern int g_pre_min_blocks;       // preprocess.cu: resident CTAs per SM K1 is compiled for (4, 5 or 6 = default)
+extern bool g_bwd_mma;             // blend_backward.cu: true (default) = tensor-core contraction of the nine sums, false = shuffle butterfly
 extern bool g_bin_count_atomics;   // binning.cu: false drops the per-instance tile_count atomics (WRONG results: timing only)
 
 // ---- host launchers (one per translation unit) --------------------------------------------------

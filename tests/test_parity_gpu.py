@@ -648,3 +648,32 @@ def test_gaussian_order_does_not_matter_on_the_device(flags):
     assert torch.equal(a[1], b[1]) and torch.equal(a[6], b[6])
     np.testing.assert_array_equal(st_a["ranges"], st_b["ranges"])
     np.testing.assert_array_equal(perm.numpy()[st_b["point_list"].view(np.uint32)], st_a["point_list"].view(np.uint32))
+
+
+@pytest.mark.parametrize("case", [(20000, 320, 240, 3, 61, 5.0), (4000, 200, 136, 1, 62, 18.0), (300, 64, 48, 0, 63, 40.0)])
+def test_blend_backward_tensor_core_contraction_equals_shuffle_reduction(case):
+    """K7's nine per-(warp, Gaussian) sums through the tensor cores (W x F as mma.sync m16n8k8 tf32 with a hi + lo split of
+    both operands, moments about the sub-tile centre) against the round-1 shuffle butterfly (gsr_debug_set knob 3 = 0):
+    the same sums in a different association, so every per-Gaussian gradient must agree to fp32-rounding level -- far
+    inside the 1e-3 the oracle comparison allows -- including large splats whose centre lies hundreds of pixels from the
+    sub-tile (the moment expansion's worst case) and partial 8-slot groups."""
+    from multiview_inpaint_b200 import _C
+    P, W, H, deg, seed, rad = case
+    sc = small_scene(P, W, H, deg, seed, rad)
+    wt = S.loss_weights(W, H, seed)
+    res = {}
+    try:
+        for mode in (1, 0):
+            _C.debug_set(3, mode)
+            out, d, cam, bg = cuda_forward(sc)
+            res[mode] = {k: v.double().cpu().numpy() for k, v in cuda_backward(out, d, cam, bg, sc, wt).items() if v.numel()}
+    finally:
+        _C.debug_set(3, 1)
+    for k in res[0]:
+        a, b = res[1][k], res[0][k]
+        scale = np.abs(b).max() + 1e-30
+        assert np.abs(a - b).max() / scale < 2e-5, (k, np.abs(a - b).max() / scale)
+        # and element-wise where the value is not a cancellation residue
+        big = np.abs(b) > 1e-3 * scale
+        if big.any():
+            assert (np.abs(a - b)[big] / np.abs(b)[big]).max() < 2e-3, k
