@@ -11,9 +11,12 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a tool (nsys / ncu --nvtx) has injected itself
 
 #include "common.cuh"
 
@@ -44,7 +47,36 @@ struct Profiler {
   }
 };
 static Profiler g_prof;
-#define PROF(st) g_prof.mark(s, (st))
+
+// NVTX ranges around the same stage brackets (GSR_NVTX=1): one range per pipeline stage on the calling host thread, so that
+// `nsys` / `ncu --nvtx --nvtx-include "gsr/blend backward/"` can address a stage by name.  Host-side markers only: they cost
+// two library calls per stage and nothing at all when no tool is attached.
+static const char* const kStageNames[GSR_NUM_STAGES] = {"preprocess", "depth sort", "scan", "duplicate", "tile sort", "tile ranges",
+                                                        "blend forward", "accumulator clear", "blend backward",
+                                                        "per-Gaussian backward"};
+struct NvtxStages {
+  bool on = false, open = false;
+  nvtxDomainHandle_t dom = nullptr;
+  NvtxStages() {
+    const char* e = getenv("GSR_NVTX");
+    on = e && e[0] && e[0] != '0';
+    if (on) dom = nvtxDomainCreateA("gsr");
+  }
+  void mark(int st) {
+    if (!on) return;
+    if (open) { nvtxDomainRangePop(dom); open = false; }
+    if (st < 0 || st >= GSR_NUM_STAGES) return;
+    nvtxEventAttributes_t a{};
+    a.version = NVTX_VERSION;
+    a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+    a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+    a.message.ascii = kStageNames[st];
+    nvtxDomainRangePushEx(dom, &a);
+    open = true;
+  }
+};
+static thread_local NvtxStages g_nvtx;
+#define PROF(st) do { g_prof.mark(s, (st)); g_nvtx.mark(st); } while (0)
 
 static int fail_cuda(cudaError_t e, const char* where) {
   g_last_error = std::string(where) + ": " + cudaGetErrorString(e);

@@ -81,7 +81,8 @@ constexpr int MG_SLOTS = 8;                        // Gaussians per contraction 
 constexpr int MG_STRIDE = 36;                      // floats per row of a W tile [8 slots][32 pixels]
 constexpr int MG_TILE_BYTES = MG_SLOTS * MG_STRIDE * 4;          // 1152
 constexpr int MG_F_ROWS = 6;                       // feature rows kept (rows 6, 7 of the MMA's M are never read back)
-constexpr int MG_F_STRIDE = 72;                    // floats per feature row: 32 pixels x {F1, FP} interleaved (+ 8 pad)
+constexpr int MG_F_STRIDE = 72;                    // floats per feature row: 32 pixels x {F1, FP} interleaved = 16 chunks of
+                                                   // 16 bytes, the upper eight shifted by one chunk (bank swizzle), + pad
 constexpr int MG_F_BYTES = MG_F_ROWS * MG_F_STRIDE * 4;          // 1728
 constexpr int MG_INFO_OFF = 2 * MG_TILE_BYTES;                   // per warp: W1 tile | W3 tile | info[8] | feature table
 constexpr int MG_F_OFF = MG_INFO_OFF + MG_SLOTS * 16;
@@ -107,7 +108,9 @@ __device__ __forceinline__ void flush_slots(uint32_t s_warp, int lane, uint32_t 
   __syncwarp();
   const uint32_t q = (uint32_t)lane >> 2, t = (uint32_t)lane & 3;
   const uint32_t w_off = s_warp + (q * MG_STRIDE + 8 * t) * 4;
-  const uint32_t f_off = s_warp + MG_F_OFF + (min(q, (uint32_t)(MG_F_ROWS - 1)) * MG_F_STRIDE + 16 * t) * 4;
+  // pixel pair p = 4 t + s sits at 16-byte chunk p + (p >> 3) of its row (= 4 t + (t >> 1) + s): with the row stride of 18
+  // chunks the eight lanes of a quarter warp (two rows x four t) then hit eight different bank groups
+  const uint32_t f_off = s_warp + MG_F_OFF + (min(q, (uint32_t)(MG_F_ROWS - 1)) * MG_F_STRIDE + 16 * t + 4 * (t >> 1)) * 4;
   float d1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, d3[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   const float4 w1a = lds128(w_off), w1b = lds128(w_off + 16);
   const float4 w3a = lds128(w_off + MG_TILE_BYTES), w3b = lds128(w_off + MG_TILE_BYTES + 16);
@@ -220,7 +223,7 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
   if constexpr (MMA) {
     __shared__ __align__(16) unsigned char s_mma[8 * MG_WARP_BYTES];
     s_warp = pin_reg((uint32_t)__cvta_generic_to_shared(s_mma) + warp * MG_WARP_BYTES);
-    const uint32_t f = s_warp + MG_F_OFF + lane * 8;
+    const uint32_t f = s_warp + MG_F_OFF + lane * 8 + (lane >> 4) * 16;   // pair p = lane >> 1 at chunk p + (p >> 3)
     const float h0 = tf32_hi(dLp0), h1 = tf32_hi(dLp1), h2 = tf32_hi(dLp2);
     const float u = (float)(lane & 7) - 3.5f, v = (float)(lane >> 3) - 1.5f;
     const float f1[MG_F_ROWS] = {h0, h1, h2, dLp0 - h0, dLp1 - h1, dLp2 - h2};

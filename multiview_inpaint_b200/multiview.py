@@ -84,6 +84,10 @@ class GradArena:
         return self._mc != 0 and self.method == "nvls"
 
     method = "nvls"   # preferred collective when a multicast mapping exists; see calibrate()
+    # CTAs of the in-switch kernel (512 threads each; 0 = the library's default of two per SM).  The reduction is bound by
+    # the links, not by the SMs, and when it overlaps the chunked per-Gaussian backward every CTA it holds is taken from
+    # that kernel: tools/exp_scale8.py sweeps this at 8 GPUs.
+    nvls_blocks = int(__import__("os").environ.get("GSR_NVLS_BLOCKS", "0"))
 
     def calibrate(self, iters: int = 3) -> dict:
         """Times the in-switch kernel against the NCCL all-reduce on this arena (contents are summed
@@ -137,7 +141,7 @@ class GradArena:
             h.barrier()      # every replica is complete (stream-ordered after this rank's kernels)
             rows = self.P if (self.sparse and (3 * self.M) % 4 == 0) else 0
             _C.nvls_all_reduce(self._mc, self.storage.device, 0, self._n_f32, self._off_cnt, self.P, self._off_max, self.P,
-                               h.rank, h.world_size, 0, self._sh_first, rows, 3 * self.M)
+                               h.rank, h.world_size, self.nvls_blocks, self._sh_first, rows, 3 * self.M)
             h.barrier()      # every slice has been written back everywhere
             return
         dist.all_reduce(self.storage[:self._n_f32], op=dist.ReduceOp.SUM, group=group)
@@ -164,7 +168,8 @@ class GradArena:
         dense.append((4 * (self._n_flat + g0), r4(g1 - g0)))                      # grad_norm_accum
         h.barrier()
         _C.nvls_all_reduce_plan(self._mc, self.storage.device, h.rank, h.world_size, dense=dense, rows=rows,
-                                add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0))
+                                add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0),
+                                blocks=self.nvls_blocks)
         if post_barrier:
             h.barrier()
 
@@ -174,6 +179,7 @@ class GradArena:
         gaussian_model.py:423-425).  With symmetric memory this is a collective call (rendezvous)."""
         new = GradArena(P, self.M, self.storage.device, symmetric=self._handle is not None, group=self.group)
         new.sparse = self.sparse
+        new.nvls_blocks = self.nvls_blocks
         new.method = self.method if new._mc else "nccl"
         return new
 

@@ -49,18 +49,43 @@ if os.path.exists(rep):
         n = short(r[ki]).split("<")[0]
         b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
         acc[n].append(b)
-    traffic = {}
-    for n, xs in acc.items():
-        st = STAGE_OF.get(n)
+    # the capture is ONE batched step of `views` views (tools/ncu_step.py): a stage's traffic PER VIEW is the sum over its
+    # launches divided by the views.  The onesweep launches split into the depth sort (the first 4: 32 key bits) and the
+    # tile sort (the rest) by order.
+    views = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    STAGE_OF.update({"geom_backward_multi_kernel": "geom_backward", "zero_regions_kernel": "accum_clear"})
+    traffic, seen_sweeps = {}, 0
+    for r in rows[2:]:
+        n = short(r[ki]).split("<")[0]
+        b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
         if n == "rs_onesweep_kernel":
-            continue
+            st = "depth_sort" if seen_sweeps < 4 else "tile_sort"
+            seen_sweeps += 1
+        else:
+            st = STAGE_OF.get(n)
         if st:
-            traffic[st] = traffic.get(st, 0) + sum(xs) / len(xs)
+            traffic[st] = traffic.get(st, 0) + b / views
     tp = os.path.join(PR, "traffic.json")
     old = json.load(open(tp)) if os.path.exists(tp) else {}
     old["headline"] = {k: int(v) for k, v in traffic.items()}
-    old["_source"] = f"profiles/{tag}_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full)"
+    old["_source"] = (f"profiles/{tag}_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full of one batched "
+                      f"{views}-view step, per view)")
     json.dump(old, open(tp, "w"), indent=1)
+    # issue-slot utilisation and warp instructions of the issue-bound blend kernels (bench.py: roofline.issue_active_frac)
+    def col(name):
+        return hdr.index(name) if name in hdr else None
+    ii, wi_, ti = col("smsp__issue_active.avg.pct_of_peak_sustained_active"), col("smsp__inst_executed.sum"), col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+    ctr = {}
+    for r in rows[2:]:
+        n = short(r[ki]).split("<")[0]
+        st = STAGE_OF.get(n)
+        if st in ("blend_forward", "blend_backward") and ii is not None:
+            ctr[st] = {"issue_active_frac": round(float(r[ii].replace(",", "")) / 100.0, 4),
+                       "warp_inst": int(float(r[wi_].replace(",", ""))) if wi_ is not None else None,
+                       "tensor_pipe_active_frac": (round(float(r[ti].replace(",", "")) / 100.0, 4) if ti is not None else None),
+                       "views_per_launch": views, "source": f"profiles/{tag}_ncu_full.md"}
+    if ctr:
+        json.dump(ctr, open(os.path.join(PR, "roofline_counters.json"), "w"), indent=1)
 
 # ---- bench lines ----
 out = {}
