@@ -90,10 +90,17 @@ nvls_allreduce_kernel(char* __restrict__ mc, const NvlsPlan pl, int rank, int wo
     const size_t per = (groups + world - 1) / world;
     const size_t g_lo = min(groups, per * rank), g_hi = min(groups, g_lo + per);
     const size_t warp_id = tid >> 5, n_warps = nthreads >> 5;
+    // The group's counts are fetched ONE ITERATION AHEAD: the count reduction is a full NVLink round trip, and issued in
+    // front of the loads that depend on it, it would double the latency of every iteration of this latency-bound loop.
+    auto fetch_counts = [&](size_t g) -> int {
+      const size_t r = g * G + lane;
+      return (g < g_hi && lane < G && r < rows) ? mm_ld_reduce_add_s32(cnt + r) : 0;
+    };
+    int c_next = fetch_counts(g_lo + warp_id);
     for (size_t g = g_lo + warp_id; g < g_hi; g += n_warps) {     // warp-uniform
       const size_t row0 = g * G;
-      int c = 0;
-      if (lane < G && row0 + lane < rows) c = mm_ld_reduce_add_s32(cnt + row0 + lane);
+      const int c = c_next;
+      c_next = fetch_counts(g + n_warps);
       float4* p = base + pl.row_lo4 + row0 * row_f4;
       float4 v[3];
       bool live[3];

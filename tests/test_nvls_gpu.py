@@ -1,4 +1,4 @@
-"""World-2 check of the in-switch arena all-reduce (gsr_nvls_all_reduce over symmetric memory with an
+"""World-2 (GSR_TEST_WORLD=N: world-N) check of the in-switch arena all-reduce (gsr_nvls_all_reduce over symmetric memory with an
 NVSwitch multicast mapping) against NCCL.  Needs two GPUs: skipped on the single-GPU test box."""
 import os
 import sys
@@ -33,6 +33,7 @@ def _worker(rank, world, port, out_dir):
             x.max_radii.copy_(torch.randint(0, 900, (P,), device=dev, generator=g, dtype=torch.int32))
             x.views["dL_dsh"][x.visible_count == 0] = 0     # unseen Gaussians have zero rows (what the kernels write)
         a.method = "nvls"
+        a.nvls_blocks = 148 if M == 4 else 0      # the leaner grid the pipelined step uses, and the library default
         a.all_reduce()
         b.all_reduce()
         torch.cuda.synchronize()
@@ -61,11 +62,12 @@ def _worker(rank, world, port, out_dir):
 
 
 def test_nvls_arena_all_reduce_matches_nccl(tmp_path):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    world = int(os.environ.get("GSR_TEST_WORLD", "2"))     # 2 by default; the 8-GPU calls of tools/ run it with 8
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, 29541, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
+    mp.spawn(_worker, args=(world, 29541, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
         res = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         for M, d in res.items():
             if not d["nvls"]:
