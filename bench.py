@@ -665,7 +665,7 @@ def run_ours(args):
         # CTAs of the reduction kernel), max over ranks, keep the fastest -- part of the warm-up, outside every timed region.
         cands = [("nccl", 1, 0)]
         if arena._mc:
-            cands += [("nvls", c, b) for c in (4, 8) for b in (148, 0)]
+            cands += [("nvls", 4, 148), ("nvls", 4, 74), ("nvls", 8, 74), ("nvls", 4, 0)]   # tools/exp_scale8.py: the sweep these come from
         trials = []
         for m_, c_, b_ in cands:
             arena.method, arena.nvls_blocks, args.ar_chunks = m_, b_, c_
