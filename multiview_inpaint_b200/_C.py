@@ -22,6 +22,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgsrast_b200.so")
+if os.environ.get("GSR_LIB_VARIANT"):   # experiments only (tools/build_variant.py): the same sources compiled with extra -D switches
+    LIB_PATH = os.path.join(_HERE, "variants", f"libgsrast_b200_{os.environ['GSR_LIB_VARIANT']}.so")
 
 FLAG_BINNING_KEY64 = 1
 FLAG_PRECISE = 2

@@ -251,7 +251,7 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
   for (int b = nb - 1; b >= 0; b--) {
     __syncthreads();  // WAR on the staging buffer
     const uint32_t pos = (uint32_t)b * BLEND_BATCH + tid;
-    const uint32_t bits = stage_entry<PRECISE>(pos < cta_last, range.x + pos, point_list, rec,
+    const uint32_t bits = stage_entry<PRECISE, GSR_REFINE_BWD != 0>(pos < cta_last, range.x + pos, point_list, rec,
                                                s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
     publish_masks<false>(bits, s_mask, warp, lane);
     __syncthreads();
@@ -264,16 +264,18 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
         if (gbase >= warp_last) continue;
         if (warp_last - gbase < 32) m &= (1u << (warp_last - gbase)) - 1;  // entries >= warp_last
         const uint32_t ebase = s_ent + ws * 32 * ENTRY_BYTES;
+        // entry j of the group is list position gbase + j (0-based == contributor index): it lies in front of this
+        // pixel's last contributor iff j < last - gbase (negative when the pixel stopped before this group)
+        const int last_rel = (int)last - (int)gbase;
         while (m) {
           const int j = bfind(m);
           m &= ~(one << j);
           const uint32_t ea = ebase + j * ENTRY_BYTES;
-          const uint32_t epos = gbase + j;  // 0-based list position == contributor index
           const float4 e0 = lds128(ea);
           const float4 e1 = lds128(ea + 16);
           float dx, dy;
           const float power = pair_power<PRECISE>(e0, e1, pxf, pyf, dx, dy);
-          bool contrib = (epos < last) && !(power > 0.0f || power < e1.z);
+          bool contrib = (j < last_rel) && !(power > 0.0f || power < e1.z);
           float G = 0.0f, alpha = 0.0f;
           if (contrib) {
             G = pair_gauss<PRECISE>(power);

@@ -50,10 +50,75 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// Exact ellipse-vs-sub-tile test (the bounding-box test above it passes 30 % of its hits to pairs no pixel of which can
+// contribute -- elongated, diagonal splats; a CPU replay of the headline view, tests/analysis_blend_hits.py, finds that
+// 93 % of those "dead" hits are such geometric misses).  A pair contributes only if power >= power_cut, i.e.
+//     q(dx, dy) = a dx^2 + 2 b dx dy + c dy^2 <= -2 power_cut          (a, b, c the conic; d = mean - pixel)
+// so sub-tile v can be dropped when the MINIMUM of q over the rectangle spanned by its pixel centres exceeds that bound.
+// q is convex: the minimum is 0 when the mean lies inside the rectangle, otherwise it is attained on one of the four
+// edges, where q is a 1-D quadratic minimised in closed form (clamped).  Conservative by construction (the rectangle is
+// a superset of the pixel centres; power_cut carries GSR_POWER_SLACK = 0.05, i.e. 0.1 in q); when the terms of q get
+// large enough for their fp32 rounding to approach that slack the test is skipped and the bounding-box bits stand.
+// The terms of the four x-edges and eight y-edges are shared between the sub-tiles: ~220 instructions per staged entry,
+// once per (tile, entry) -- against ~26 warp instructions saved per dead (warp, entry) hit in K6 and K7.
+// Build switches (tools/build_variant.py): which kernels refine, and how the code is emitted.
+#ifndef GSR_REFINE_FWD
+#define GSR_REFINE_FWD 0
+#endif
+#ifndef GSR_REFINE_BWD
+#define GSR_REFINE_BWD 1
+#endif
+#ifdef GSR_REFINE_NOINLINE
+#define GSR_REFINE_ATTR static __noinline__
+#else
+#define GSR_REFINE_ATTR __forceinline__
+#endif
+__device__ GSR_REFINE_ATTR uint32_t ellipse_subtile_mask(float4 q0, float conic_z, float power_cut, float tile_x0,
+                                                         float tile_y0) {
+  const float a = q0.z, b = q0.w, c = conic_z;
+  const float thr = -2.0f * power_cut;
+  // d = mean - pixel over the whole tile: dx in [x - tx0 - 15, x - tx0], dy likewise
+  const float X1 = q0.x - tile_x0, Y1 = q0.y - tile_y0;
+  const float mx = fmaxf(fabsf(X1), fabsf(X1 - 15.0f)), my = fmaxf(fabsf(Y1), fabsf(Y1 - 15.0f));
+  if (!(a * mx * mx + c * my * my + 2.0f * fabsf(b) * mx * my < 3.0e4f)) return 0xffu;   // rounding guard (also NaN)
+  const float r1 = -b / c, r2 = -b / a;   // minimisers: dy*(dx) = r1 dx on a vertical edge, dx*(dy) = r2 dy on a horizontal one
+  const float b2 = 2.0f * b;
+  // vertical edges: dx = X1 - {0, 7, 8, 15}  (sub-tile column k spans pixel columns 8 k .. 8 k + 7)
+  float xe[4], xu[4], xw[4], xz[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    xe[k] = X1 - (float)((k >> 1) * 8 + (k & 1) * 7);
+    xu[k] = r1 * xe[k];
+    xw[k] = b2 * xe[k];
+    xz[k] = a * xe[k] * xe[k];
+  }
+  uint32_t keep = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const float yhi = Y1 - (float)(4 * r), ylo = yhi - 3.0f;            // dy range of sub-tile row r: [ylo, yhi]
+    // horizontal edges of this row: dy = yhi, ylo
+    const float u0 = r2 * yhi, w0 = b2 * yhi, z0 = c * yhi * yhi;
+    const float u1 = r2 * ylo, w1 = b2 * ylo, z1 = c * ylo * ylo;
+    const bool y_in = ylo <= 0.0f && yhi >= 0.0f;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float xhi_ = xe[2 * k], xlo_ = xe[2 * k + 1];               // dx range of sub-tile column k: [xlo_, xhi_]
+      float t, qmin;
+      t = fminf(fmaxf(xu[2 * k], ylo), yhi);      qmin = fmaf(fmaf(c, t, xw[2 * k]), t, xz[2 * k]);
+      t = fminf(fmaxf(xu[2 * k + 1], ylo), yhi);  qmin = fminf(qmin, fmaf(fmaf(c, t, xw[2 * k + 1]), t, xz[2 * k + 1]));
+      t = fminf(fmaxf(u0, xlo_), xhi_);           qmin = fminf(qmin, fmaf(fmaf(a, t, w0), t, z0));
+      t = fminf(fmaxf(u1, xlo_), xhi_);           qmin = fminf(qmin, fmaf(fmaf(a, t, w1), t, z1));
+      const bool inside = y_in && xlo_ <= 0.0f && xhi_ >= 0.0f;
+      if (inside || qmin <= thr) keep |= 1u << (2 * r + k);
+    }
+  }
+  return keep;
+}
+
 // Stages list element `pos` (if valid) into entry slot `tid` and returns the 8-bit mask of warps
 // (8x4 pixel sub-tiles, warp v = row*2 + col) whose box the Gaussian's {alpha >= 1/255} bounding
 // box [x - hx, x + hx] x [y - hy, y + hy] overlaps.
-template <bool PRECISE>
+template <bool PRECISE, bool REFINE_CULL>
 __device__ __forceinline__ uint32_t stage_entry(bool valid, uint32_t list_index,
                                                 const uint32_t* __restrict__ point_list,
                                                 const float4* __restrict__ rec, uint32_t s_entry,
@@ -81,6 +146,7 @@ __device__ __forceinline__ uint32_t stage_entry(bool valid, uint32_t list_index,
 #pragma unroll
     for (int r = 0; r < 4; r++)
       if (yhi >= tile_y0 + 4.0f * r && ylo <= tile_y0 + 4.0f * r + 3.0f) bits |= cx << (2 * r);
+    if (REFINE_CULL) bits &= ellipse_subtile_mask(q0, q1.x, q2.w, tile_x0, tile_y0);
   }
   return bits;
 }

@@ -29,7 +29,10 @@ struct BlendFwdArgs {
 
 // blockIdx.y = view of a batched step (one launch blends every view's tiles: no launch gaps, one tail)
 template <bool PRECISE>
-__global__ void __launch_bounds__(256)
+#ifndef GSR_FWD_MINB
+#define GSR_FWD_MINB 0
+#endif
+__global__ void __launch_bounds__(256, PRECISE ? 0 : GSR_FWD_MINB)
 blend_forward_kernel(const __grid_constant__ BlendFwdArgs args) {
   const BlendFwdView& a = args.v[blockIdx.y];
   const int W = a.W, H = a.H, grid_x = a.grid_x;
@@ -74,7 +77,7 @@ blend_forward_kernel(const __grid_constant__ BlendFwdArgs args) {
     // all pixels of the tile saturated -> stop (also the WAR barrier for the staging buffer)
     if (__syncthreads_and(done)) break;
     const int pos = b * BLEND_BATCH + tid;
-    const uint32_t bits = stage_entry<PRECISE>(pos < todo, range.x + pos, point_list, rec,
+    const uint32_t bits = stage_entry<PRECISE, GSR_REFINE_FWD != 0>(pos < todo, range.x + pos, point_list, rec,
                                                s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
     publish_masks<true>(bits, s_mask, warp, lane);
     __syncthreads();

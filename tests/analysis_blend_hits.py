@@ -81,6 +81,7 @@ rng = np.random.default_rng(0)
 sel = rng.choice(N, size=min(n_sample, N), replace=False)
 n_contrib = f.n_contrib.astype(np.int64)
 live, lanes = 0, 0
+exact_culled, exact_culled_live = 0, 0
 hits_sel = int(hits[sel].sum())
 lane_hist = np.zeros(33, dtype=np.int64)
 ly, lx = np.mgrid[0:4, 0:8]
@@ -100,6 +101,23 @@ for v in range(8):
     alive = pos_in_tile[s][:, None, None] < n_contrib[py, px]
     contrib = inside & alive & (power <= 0.0) & (alpha >= 1.0 / 255.0)
     k = contrib.reshape(len(s), -1).sum(1)
+    # would an EXACT ellipse-vs-rect test at staging time have culled this hit?  (min over the sub-tile's pixel centres'
+    # bounding rect of the quadratic form > 2 tau: no pixel can reach alpha >= 1/255)  -- geometric misses of the bbox cull
+    gx0, gx1 = mx[g] - (tx0[s] + (v & 1) * 8.0 + 7.0), mx[g] - (tx0[s] + (v & 1) * 8.0)       # dx range [gx0, gx1]
+    gy0, gy1 = my[g] - (ty0[s] + (v >> 1) * 4.0 + 3.0), my[g] - (ty0[s] + (v >> 1) * 4.0)
+    A_, B_, C_ = a[g], b[g], c[g]
+    def q(dx_, dy_):
+        return A_ * dx_ * dx_ + 2.0 * B_ * dx_ * dy_ + C_ * dy_ * dy_
+    inside_c = (gx0 <= 0) & (gx1 >= 0) & (gy0 <= 0) & (gy1 >= 0)
+    cand = []
+    for xe in (gx0, gx1):
+        cand.append(q(xe, np.clip(-B_ * xe / C_, gy0, gy1)))
+    for ye in (gy0, gy1):
+        cand.append(q(np.clip(-B_ * ye / A_, gx0, gx1), ye))
+    qmin = np.where(inside_c, 0.0, np.minimum.reduce(cand))
+    exact_keep = qmin <= 2.0 * tau[g]
+    exact_culled += int((~exact_keep).sum())
+    exact_culled_live += int(((~exact_keep) & (k > 0)).sum())      # must be 0: the test is conservative
     live += int((k > 0).sum())
     lanes += int(k.sum())
     lane_hist += np.bincount(k, minlength=33)
@@ -112,6 +130,8 @@ out = {
     "instances_with_no_hit": float((hits == 0).mean()),
     "sample_instances": int(len(sel)),
     "live_fraction_of_hits": live / max(hits_sel, 1),
+    "hits_an_exact_ellipse_rect_test_would_cull": exact_culled / max(hits_sel, 1),
+    "live_hits_wrongly_culled_by_it": exact_culled_live,
     "live_hits_per_instance": live / len(sel),
     "contributing_lanes_per_live_hit": lanes / max(live, 1),
     "contributing_pairs_per_instance": lanes / len(sel),
