@@ -81,9 +81,15 @@ duplicate_tiles_kernel(int P, const uint32_t* __restrict__ order, const float4* 
 // Emission order is unchanged: depth rank, then y-major over the rect (Appendix A.3).
 // =================================================================================================
 constexpr int BE_THREADS = 256;
-constexpr int BE_ROUNDS = 4;
+#ifndef GSR_BE_ROUNDS
+#define GSR_BE_ROUNDS 4
+#endif
+#ifndef GSR_BE_BIG
+#define GSR_BE_BIG 64
+#endif
+constexpr int BE_ROUNDS = GSR_BE_ROUNDS;
 constexpr int BE_TILE = BE_THREADS * BE_ROUNDS;  // == SCAN_TILE: the look-back status array is the scan's
-constexpr uint32_t BE_BIG = 64;                  // rects with more tiles than this go to the work list
+constexpr uint32_t BE_BIG = GSR_BE_BIG;                  // rects with more tiles than this go to the work list
 constexpr unsigned long long BE_FLAG_AGG = 1ull << 62;
 constexpr unsigned long long BE_FLAG_INC = 2ull << 62;
 constexpr unsigned long long BE_VAL_MASK = (1ull << 62) - 1;

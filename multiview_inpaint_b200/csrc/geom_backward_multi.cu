@@ -97,8 +97,11 @@ __device__ __forceinline__ void sh_group_backward(float4* row4, int nco, const f
   row4[3 * G + 2] = make_float4(o[8], o[9], o[10], o[11]);
 }
 
+#ifndef GSR_GM_MINB
+#define GSR_GM_MINB 0
+#endif
 template <int NV, int MT, bool ACC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GSR_GM_MINB)
 geom_backward_multi_kernel(int P, int D, const float* __restrict__ means3D, const float* __restrict__ shs,
                            const float* __restrict__ scales, const float* __restrict__ rotations,
                            float scale_modifier, const MultiArgs<NV> args, float* __restrict__ dL_dopacity,

@@ -149,7 +149,10 @@ template <> struct RsStatus<unsigned long long> {
 static size_t rs_status_bytes(int64_t n) { return n >= RS_WIDE_FROM ? 8 : 4; }
 
 template <typename KeyT> struct RsCfg;
-template <> struct RsCfg<uint32_t> { static constexpr int ITEMS = 16; };
+#ifndef GSR_RS_ITEMS32
+#define GSR_RS_ITEMS32 16
+#endif
+template <> struct RsCfg<uint32_t> { static constexpr int ITEMS = GSR_RS_ITEMS32; };
 template <> struct RsCfg<uint64_t> { static constexpr int ITEMS = 12; };
 
 static int rs_tile(int key_bytes) {
@@ -329,7 +332,10 @@ __device__ __forceinline__ void rs_rank_items(const KeyT (&key)[ITEMS], uint32_t
 }
 
 template <typename KeyT, int ITEMS, typename StatusT, bool COMPACT, int RANK>
-__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? 4 : 2)
+#ifndef GSR_RS_MINB
+#define GSR_RS_MINB 4
+#endif
+__global__ void __launch_bounds__(RS_THREADS, sizeof(KeyT) == 4 ? GSR_RS_MINB : 2)
 rs_onesweep_kernel(const __grid_constant__ RsPassArgs<KeyT> args, int shift, int nbits) {
   using ST = RsStatus<StatusT>;
   constexpr int TILE = RS_THREADS * ITEMS;
