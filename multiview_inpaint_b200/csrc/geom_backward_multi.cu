@@ -98,10 +98,15 @@ __device__ __forceinline__ void sh_group_backward(float4* row4, int nco, const f
 }
 
 #ifndef GSR_GM_MINB
-#define GSR_GM_MINB 0
+#define GSR_GM_MINB 5
 #endif
+#ifndef GSR_GM_THREADS
+#define GSR_GM_THREADS 128
+#endif
+constexpr int GM_THREADS = GSR_GM_THREADS;   // Gaussians per CTA (128 threads, <= 102 registers, five CTAs per SM: measured
+                                             // 0.167 vs 0.174 ms per view for 256 threads at 126 registers; 64 / 128 / 256 alone change nothing)
 template <int NV, int MT, bool ACC>
-__global__ void __launch_bounds__(256, GSR_GM_MINB)
+__global__ void __launch_bounds__(GM_THREADS, GSR_GM_MINB)
 geom_backward_multi_kernel(int P, int D, const float* __restrict__ means3D, const float* __restrict__ shs,
                            const float* __restrict__ scales, const float* __restrict__ rotations,
                            float scale_modifier, const MultiArgs<NV> args, float* __restrict__ dL_dopacity,
@@ -112,14 +117,14 @@ geom_backward_multi_kernel(int P, int D, const float* __restrict__ means3D, cons
   constexpr int R = 3 * MT;
   constexpr bool STAGED = (MT == 4 || MT == 16);
   __shared__ float s_cam[NV][36];
-  __shared__ uint8_t s_vis[256];
-  extern __shared__ __align__(16) float s_tile[];  // [256][row_stride(R)] when STAGED
+  __shared__ uint8_t s_vis[GM_THREADS];
+  extern __shared__ __align__(16) float s_tile[];  // [GM_THREADS][row_stride(R)] when STAGED
   const int tid = threadIdx.x;
-  const int block_start = blockIdx.x * 256;
+  const int block_start = blockIdx.x * GM_THREADS;
   const int i = block_start + tid;
-  const int rows = min(256, P - block_start);
+  const int rows = min(GM_THREADS, P - block_start);
   const bool valid = i < P;
-  for (int t = tid; t < NV * 35; t += 256) {
+  for (int t = tid; t < NV * 35; t += GM_THREADS) {
     const int vw = t / 35, k = t - vw * 35;
     const ViewGrad& V = args.v[vw];
     s_cam[vw][k] = k < 16 ? __ldg(V.view + k) : (k < 32 ? __ldg(V.proj + (k - 16)) : __ldg(V.campos + (k - 32)));
@@ -135,7 +140,7 @@ geom_backward_multi_kernel(int P, int D, const float* __restrict__ means3D, cons
   __syncthreads();
   const int nco = (D + 1) * (D + 1);
   if (STAGED) {
-    if (D > 0) rows_load<STAGED ? R : 12>(shs + (size_t)block_start * R, s_tile, s_vis, rows);
+    if (D > 0) rows_load<STAGED ? R : 12, GM_THREADS>(shs + (size_t)block_start * R, s_tile, s_vis, rows);
     __syncthreads();
   }
   const size_t i3 = 3 * (size_t)i;
@@ -374,7 +379,7 @@ geom_backward_multi_kernel(int P, int D, const float* __restrict__ means3D, cons
   }
   if (STAGED) {
     __syncthreads();
-    rows_store<STAGED ? R : 12, ACC>(dL_dsh + (size_t)block_start * R, s_tile, s_vis, rows, 3 * nco);
+    rows_store<STAGED ? R : 12, ACC, GM_THREADS>(dL_dsh + (size_t)block_start * R, s_tile, s_vis, rows, 3 * nco);
   }
 }
 
@@ -386,13 +391,13 @@ static cudaError_t launch_nv_mt(cudaStream_t s, int P, int D, const float* means
                                 int32_t* max_radii, bool acc) {
   MultiArgs<NV> args;
   for (int v = 0; v < NV; v++) args.v[v] = views[v];
-  const size_t smem = (MT == 4 || MT == 16) ? (size_t)256 * row_stride(3 * MT) * sizeof(float) : 0;
+  const size_t smem = (MT == 4 || MT == 16) ? (size_t)GM_THREADS * row_stride(3 * MT) * sizeof(float) : 0;
   auto kern = acc ? geom_backward_multi_kernel<NV, MT, true> : geom_backward_multi_kernel<NV, MT, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  kern<<<cdiv(P, 256), 256, smem, s>>>(P, D, means3D, shs, scales, rotations, scale_modifier, args, dL_dopacity,
+  kern<<<cdiv(P, GM_THREADS), GM_THREADS, smem, s>>>(P, D, means3D, shs, scales, rotations, scale_modifier, args, dL_dopacity,
                                        dL_dmean3D, dL_dsh, dL_dscale, dL_drot, grad_norm_accum, visible_count,
                                        max_radii);
   count_launch();

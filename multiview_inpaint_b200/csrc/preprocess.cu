@@ -162,6 +162,15 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
   xform4x3(p, view, pv);
   bool alive = in_range && pv[2] > 0.2f;  // A.2 step 2 (the x/y frustum test is disabled upstream)
   if (in_range && !alive && prefiltered) atomicExch(status, 1);
+#ifdef GSR_K1_PREFETCH
+  // the SH row is needed ~300 instructions from here, and only by Gaussians that also pass the rect test: start it
+  // towards L1 / L2 now for every Gaussian in front of the camera (192 bytes at M = 16: two or three 128-byte lines)
+  if (alive && shs != nullptr && colors_precomp == nullptr) {
+    const char* row = reinterpret_cast<const char*>(shs + (size_t)i * M * 3);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+    if (M >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
+  }
+#endif
 
   if (alive) {
     float ph[4];

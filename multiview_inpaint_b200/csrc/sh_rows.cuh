@@ -12,17 +12,17 @@ namespace gsr {
 // (LDS.128 / STS.128 on both sides) and conflict free for the per-thread row walk (the 8 threads of
 // a quarter warp hit the 8 distinct 4-bank groups).
 __host__ __device__ constexpr int row_stride(int R) { return ((R / 4) % 2 ? R / 4 : R / 4 + 1) * 4; }
-template <int R>
+template <int R, int NT = 256>
 __device__ __forceinline__ void rows_load(const float* __restrict__ g, float* s_tile, const uint8_t* s_vis, int rows) {
   constexpr int Q = R / 4, STRIDE = row_stride(R), U = 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
   const int n4 = rows * Q;
-  for (int base = threadIdx.x; base < n4; base += U * 256) {
+  for (int base = threadIdx.x; base < n4; base += U * NT) {
     float4 q[U];
     int so[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int e4 = base + u * 256;
+      const int e4 = base + u * NT;
       const int row = e4 / Q;
       so[u] = -1;
       if (e4 < n4 && s_vis[row]) {
@@ -38,14 +38,14 @@ __device__ __forceinline__ void rows_load(const float* __restrict__ g, float* s_
 // ACC: one vector reduction (RED.ADD.F32x4: fire and forget, the L2 does the read-modify-write) per
 // 16 bytes of a visible row, columns >= cols_used (coefficients above the active degree) skipped.
 // !ACC: every element of the span is written, zeros for culled rows.
-template <int R, bool ACC>
+template <int R, bool ACC, int NT = 256>
 __device__ __forceinline__ void rows_store(float* __restrict__ g, const float* s_tile, const uint8_t* s_vis, int rows,
                                            int cols_used) {
   constexpr int Q = R / 4, STRIDE = row_stride(R);
   float4* g4 = reinterpret_cast<float4*>(g);
   const int n4 = rows * Q;
 #pragma unroll 4
-  for (int e4 = threadIdx.x; e4 < n4; e4 += 256) {
+  for (int e4 = threadIdx.x; e4 < n4; e4 += NT) {
     const int row = e4 / Q, c = (e4 - row * Q) * 4;
     const bool v = s_vis[row] != 0;
     if (ACC) {
