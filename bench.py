@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-balance", action="store_true", help="strong scaling: keep the round-robin view -> rank map instead of "
                     "balancing the ranks' instance counts (longest-processing-time assignment on the learnt num_rendered)")
     ap.add_argument("--orbit-deg", type=float, default=5.0, help="views lie on a +-deg orbit about the scene centre")
-    ap.add_argument("--flags", type=int, default=0, help="GSR_FLAG_* bits (1 = reference-structure 64-bit binning)")
+    ap.add_argument("--flags", type=int, default=32, help="GSR_FLAG_* bits (32 = tight binning, the Python layers' default; 0 = the reference's literal lists; 1 = 64-bit key binning)")
     ap.add_argument("--streams", type=int, default=1, help="view groups in flight per GPU (ViewPipeline depth; 1 = one stream): with the batched "
                     "front end the rank's views are split into this many groups, one stream each")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "nccl", "nvls"],
@@ -394,11 +394,16 @@ def parity_against_oracle(torch, _C, gauss, rs, wt, kept, P, W, H, tile_step, fl
     import numpy as np
     f, g_ref = kept["f"], kept["g"]
     e = torch.empty(0, device=wt.device)
-    n, color, radii, geom, binning, img, depth = _C.rasterize_gaussians(
-        rs.bg, gauss["means3D"], e, gauss["opacities"], gauss["scales"], gauss["rotations"], rs.scale_modifier, e, rs.viewmatrix,
-        rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, gauss["shs"], rs.sh_degree, rs.campos, rs.prefiltered,
-        flags=flags, capacity=0)
-    st = _C.unpack_state(P, W, H, n, geom, binning, img, flags)
+    tight = bool(flags & _C.FLAG_TIGHT_BINNING) and not (flags & (_C.FLAG_BINNING_KEY64 | _C.FLAG_REFERENCE))
+    lit_flags = flags & ~_C.FLAG_TIGHT_BINNING     # the oracle holds the reference's literal lists
+
+    def fwd(fl):
+        return _C.rasterize_gaussians(
+            rs.bg, gauss["means3D"], e, gauss["opacities"], gauss["scales"], gauss["rotations"], rs.scale_modifier, e, rs.viewmatrix,
+            rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, gauss["shs"], rs.sh_degree, rs.campos, rs.prefiltered,
+            flags=fl, capacity=0)
+    n, color, radii, geom, binning, img, depth = fwd(lit_flags)
+    st = _C.unpack_state(P, W, H, n, geom, binning, img, lit_flags)
     out = {"view": "first view of rank 0", "tile_step": tile_step, "num_rendered": [int(n), int(f.num_rendered)]}
     out["radii_equal"] = bool(np.array_equal(radii.cpu().numpy(), f.radii))
     out["point_list_equal"] = bool(n == f.num_rendered and np.array_equal(st["point_list"].cpu().numpy().view(np.uint32), f.point_list))
@@ -414,6 +419,16 @@ def parity_against_oracle(torch, _C, gauss, rs, wt, kept, P, W, H, tile_step, fl
     out["colour_max_abs_err"] = float(c_err.max())
     out["colour_pixels_over_1e-5"] = int((c_err > 1e-5).sum())
     out["depth_pixels_over_1e-5"] = int((d_err > 1e-5).sum())
+    if tight:
+        # the timed path bins only the tiles the {alpha >= 1/255} box reaches: a sub-list of the list just compared, and
+        # the same image bit for bit; the gradients below are those of THIS path
+        del st
+        lit_color, lit_depth, lit_radii = color, depth, radii
+        n, color, radii, geom, binning, img, depth = fwd(flags)
+        out["tight_binning"] = {"num_rendered": int(n), "fraction_of_literal_list": float(n) / max(int(f.num_rendered), 1),
+                                "colour_bit_identical_to_literal": bool(torch.equal(color, lit_color)),
+                                "depth_bit_identical_to_literal": bool(torch.equal(depth, lit_depth)),
+                                "radii_equal": bool(torch.equal(radii, lit_radii))}
     if tile_step == 1:
         grads = _C.rasterize_gaussians_backward(rs.bg, gauss["means3D"], radii, e, gauss["scales"], gauss["rotations"], rs.scale_modifier,
                                                 e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, wt, gauss["shs"], rs.sh_degree,
@@ -429,7 +444,8 @@ def parity_against_oracle(torch, _C, gauss, rs, wt, kept, P, W, H, tile_step, fl
         out["grad_ok_1e-3"] = bool(max(rel.values()) < 1e-3)
     out["ok"] = bool(out["radii_equal"] and out["point_list_equal"] and out["ranges_equal"] and out["colour_max_abs_err"] < 5e-3
                      and out["colour_pixels_over_1e-5"] <= max(2, int(1e-4 * out["pixels_compared"]))
-                     and out.get("grad_ok_1e-3", True))
+                     and out.get("grad_ok_1e-3", True)
+                     and all(v for k, v in out.get("tight_binning", {}).items() if k not in ("num_rendered", "fraction_of_literal_list")))
     return out
 
 

@@ -57,6 +57,16 @@ extern "C" {
  * dL_dmean2D / dL_dconic stay per-view (densification reads the per-view norm, gaussian_model.py:483). */
 #define GSR_FLAG_ACCUMULATE    8u
 #define GSR_FLAG_ASYNC        16u /* gsr_forward: never block the host (see gsr_forward)           */
+#define GSR_FLAG_TIGHT_BINNING 32u /* two-level binning only (ignored with BINNING_KEY64 / REFERENCE): K1 stores, instead of
+                                     the tile rect of the 3-sigma square (Appendix A.2 step 9), its intersection with the tiles
+                                     the bounding box of the Gaussian's {alpha >= 1/255} ellipse reaches -- the very box the
+                                     blend kernels test per 8x4 sub-tile.  An instance outside it has all eight sub-tile bits
+                                     clear: it is sorted and staged, never evaluated.  The point list becomes the SUB-LIST of
+                                     the reference's list (same order) without those instances, num_rendered counts what is
+                                     left (69 % at the headline scene, less tile-sort and expansion work in proportion);
+                                     colour, depth, radii and every gradient are unchanged -- bit for bit in the forward.
+                                     The Python layers of this repository pass it by default (_C.DEFAULT_FLAGS); flags = 0 at
+                                     the C ABI keeps the reference's literal lists.                                          */
 
 /* Buffer grower, replaces `std::function<char*(size_t)>` of the reference core: must return a
  * device allocation of at least `bytes` bytes, 256-byte aligned, that stays alive until the

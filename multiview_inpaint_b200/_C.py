@@ -30,13 +30,19 @@ FLAG_PRECISE = 2
 FLAG_REFERENCE = 4     # reference-structure ablation baseline (cub sort, thread-per-pixel blend, 9 atomics/pair)
 FLAG_ACCUMULATE = 8
 FLAG_ASYNC = 16
+FLAG_TIGHT_BINNING = 32  # bin only the tiles the {alpha >= 1/255} bounding box reaches (same images / gradients, shorter lists)
 MAX_BATCH = 8           # views per batched launch of the front end / blend kernels (GSR_MAX_BATCH)
 GM_MAX_VIEWS = 4        # views per launch of the batched per-Gaussian backward (csrc/geom_backward_multi.cu)
 NUM_STAGES = 10
 STAGE_NAMES = ("preprocess", "depth_sort", "scan", "duplicate", "tile_sort", "tile_ranges", "blend_forward",
                "accum_clear", "blend_backward", "geom_backward")
-#: default kernel flags (see include/gsrast_b200.h); override with GSR_FLAGS=<int>
-DEFAULT_FLAGS = int(os.environ.get("GSR_FLAGS", "0"))
+#: default kernel flags of the Python layers (see include/gsrast_b200.h); override with GSR_FLAGS=<int>.  flags=0 gives
+#: the reference's literal (tile, Gaussian) lists -- what the list-parity tests pin.
+DEFAULT_FLAGS = int(os.environ.get("GSR_FLAGS", str(FLAG_TIGHT_BINNING)))
+
+
+def resolve_flags(flags) -> int:
+    return DEFAULT_FLAGS if flags is None else int(flags)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -456,7 +456,7 @@ static int front_end(cudaStream_t s, FwdView* v, int nv, int P, int D, int M, co
   GSR_CUDA(launch_zero_regions(s, z.data(), (int)z.size()), "clear counters");
   PROF(0);
   GSR_CUDA(launch_preprocess(s, P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
-                             scale_modifier, prefiltered, pv.data(), nv), "preprocess");
+                             scale_modifier, prefiltered, pv.data(), nv, !k64 && (flags & GSR_FLAG_TIGHT_BINNING) != 0), "preprocess");
   if (k64) {
     PROF(2);
     for (int k = 0; k < nv; k++)

@@ -152,7 +152,7 @@ cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* 
                               const float* scales, const float* rotations, const float* opacities,
                               const float* shs, const float* cov3D_precomp,
                               const float* colors_precomp, float scale_modifier, int prefiltered,
-                              const PreView* views, int nv);
+                              const PreView* views, int nv, bool tight = false);
 cudaError_t launch_mark_visible(cudaStream_t s, int P, const float* means3D, const float* view,
                                 uint8_t* present);
 

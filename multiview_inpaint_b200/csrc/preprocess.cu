@@ -115,7 +115,17 @@ __device__ __forceinline__ void eval_sh_vec(const float4* __restrict__ row4, con
 struct PreArgs {
   PreView v[GSR_MAX_BATCH];
   int nv;
+  int tight;   // GSR_FLAG_TIGHT_BINNING: shrink the stored tile rect to the {alpha >= 1/255} bounding box
 };
+
+// Tile-index range [t0, t1) of the tiles (16 pixel centres 16 t .. 16 t + 15 each) that the interval [lo, hi] reaches:
+// exactly the tiles for which blend_common.cuh::stage_entry's tests `hi >= tile0 && lo <= tile0 + 15` hold (the union of
+// its sub-tile tests).  lo / 16 and hi / 16 are exact in fp32 (power-of-two scaling), floorf and the fraction are exact.
+__device__ __forceinline__ void tile_span(float lo, float hi, int& t0, int& t1) {
+  const float u = lo * 0.0625f, fu = floorf(u);
+  t0 = __float2int_rz(fu) + ((u - fu) > 0.9375f ? 1 : 0);   // smallest t with 16 t + 15 >= lo
+  t1 = min(__float2int_rz(floorf(hi * 0.0625f)), 1 << 24) + 1;   // one past the largest t with 16 t <= hi
+}
 
 int g_pre_min_blocks = 6;   // experiment switch (gsr_debug_set knob 2): resident CTAs per SM the kernel is compiled for
 
@@ -162,15 +172,6 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
   xform4x3(p, view, pv);
   bool alive = in_range && pv[2] > 0.2f;  // A.2 step 2 (the x/y frustum test is disabled upstream)
   if (in_range && !alive && prefiltered) atomicExch(status, 1);
-#ifdef GSR_K1_PREFETCH
-  // the SH row is needed ~300 instructions from here, and only by Gaussians that also pass the rect test: start it
-  // towards L1 / L2 now for every Gaussian in front of the camera (192 bytes at M = 16: two or three 128-byte lines)
-  if (alive && shs != nullptr && colors_precomp == nullptr) {
-    const char* row = reinterpret_cast<const char*>(shs + (size_t)i * M * 3);
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
-    if (M >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 128));
-  }
-#endif
 
   if (alive) {
     float ph[4];
@@ -302,9 +303,26 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
         depths[i] = pv[2];
         clamped[i] = clamp_bits;
         out_radius = my_radius;
-        out_tiles = tiles;
-        out_key = __float_as_uint(pv[2]);
-        out_rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+        uint32_t tiles_binned = tiles;
+        if (args.tight) {
+          // Only the tiles the {alpha >= 1/255} bounding box reaches (hx < 0: nothing can contribute).  The Gaussian stays
+          // visible (radii, record, depth: the per-Gaussian backward and the statistics see what they saw before); with an
+          // empty rect it takes no part in the depth sort either.
+          tiles_binned = 0;
+          if (hx >= 0.0f) {
+            int bx0, bx1, by0, by1;
+            tile_span(SUB(pix_x, hx), ADD(pix_x, hx), bx0, bx1);
+            tile_span(SUB(pix_y, hy), ADD(pix_y, hy), by0, by1);
+            x0 = max(x0, bx0); x1 = min(x1, bx1);
+            y0 = max(y0, by0); y1 = min(y1, by1);
+            if (x1 > x0 && y1 > y0) tiles_binned = (uint32_t)((x1 - x0) * (y1 - y0));
+          }
+        }
+        if (tiles_binned != 0) {
+          out_tiles = tiles_binned;
+          out_key = __float_as_uint(pv[2]);
+          out_rect = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+        }
       }
     }
   }
@@ -352,11 +370,12 @@ cudaError_t launch_preprocess(cudaStream_t s, int P, int D, int M, const float* 
                               const float* scales, const float* rotations, const float* opacities,
                               const float* shs, const float* cov3D_precomp,
                               const float* colors_precomp, float scale_modifier, int prefiltered,
-                              const PreView* views, int nv) {
+                              const PreView* views, int nv, bool tight) {
   if (P == 0 || nv <= 0) return cudaSuccess;
   if (nv > GSR_MAX_BATCH) return cudaErrorInvalidValue;
   PreArgs args{};
   args.nv = nv;
+  args.tight = tight ? 1 : 0;
   for (int k = 0; k < nv; k++) {
     args.v[k] = views[k];
     args.v[k].cam.scale_modifier = scale_modifier;

@@ -292,7 +292,7 @@ class _PipelineStep:
 
 
 def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor],
-                      arena: GradArena, flags: int = 0, capacity: int | None = None,
+                      arena: GradArena, flags: int | None = None, capacity: int | None = None,
                       async_result: torch.Tensor | None = None, pipeline: ViewPipeline | None = None) -> ViewResult:
     """One view through the CUDA path: forward, loss gradient, backward ADDING into `arena`.
     `gaussians`: means3D, shs, opacities, scales, rotations (post-activation, as render() passes them);
@@ -302,6 +302,7 @@ def cuda_view_fwd_bwd(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.T
     the step.  With `pipeline` the view runs on the pipeline's next stream (see ViewPipeline)."""
     import contextlib
     from . import _C
+    flags = _C.resolve_flags(flags)
     with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
         rs = settings() if callable(settings) else settings
         e = torch.empty(0, device=gaussians["means3D"].device)
@@ -336,7 +337,7 @@ class ViewState:
     settings: object
 
 
-def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor], flags: int = 0,
+def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch.Tensor], torch.Tensor], flags: int | None = None,
                         capacity: int | None = None, async_result: torch.Tensor | None = None,
                         pipeline: ViewPipeline | None = None, workspace=None) -> ViewState:
     """Forward (K1..K6), loss gradient, blend backward (K7) of one view; the per-Gaussian chain rule is
@@ -344,6 +345,7 @@ def cuda_view_fwd_blend(gaussians: dict, settings, dL_dcolor_fn: Callable[[torch
     the view runs on the pipeline's next stream; views need no mutual ordering here."""
     import contextlib
     from . import _C
+    flags = _C.resolve_flags(flags)
     with (pipeline.next_stream() if pipeline is not None else contextlib.nullcontext()):
         rs = settings() if callable(settings) else settings
         e = torch.empty(0, device=gaussians["means3D"].device)
@@ -382,10 +384,11 @@ def cuda_views_fwd_blend_batched(gaussians: dict, settings_list: Sequence, dL_dc
 
 
 def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena: GradArena, accumulate: bool = False,
-                             flags: int = 0, want_means2D: bool = False):
+                             flags: int | None = None, want_means2D: bool = False):
     """Batched K8+K9 over `states` (one launch per four views): parameter gradients and densification
     statistics are WRITTEN into `arena` (added with `accumulate`), so the arena needs no zeroing."""
     from . import _C
+    flags = _C.resolve_flags(flags)
     if not states:
         # a rank without views (fewer views than ranks): the batched kernel WRITES the arena, so nothing else would
         # clear last step's gradients and statistics -- this rank must contribute zeros to the all-reduce
@@ -406,7 +409,7 @@ def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena
                                   flags=flags | (_C.FLAG_ACCUMULATE if accumulate else 0), want_means2D=want_means2D)
 
 
-def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewState], arena: GradArena, flags: int = 0,
+def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewState], arena: GradArena, flags: int | None = None,
                                        chunks: int = 4):
     """Batched K8+K9 + gradient all-reduce of a multi-rank step, pipelined over Gaussian-range chunks: while the
     switch reduces the arena rows of chunk c (comm stream: barrier, gsr_nvls_all_reduce_plan, barrier), the
@@ -414,6 +417,7 @@ def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewSta
     NVLink-bound, so the backward disappears behind the collective.  Without a multicast mapping (or with NCCL
     selected) it is the plain sequence: backward, then arena.all_reduce()."""
     from . import _C
+    flags = _C.resolve_flags(flags)
     P = arena.P
     if not (arena.uses_nvls and dist.is_initialized() and dist.get_world_size(arena.group) > 1) or chunks <= 1 \
             or P < 4096:
@@ -449,7 +453,7 @@ def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewSta
 
 
 def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: Sequence[Callable], arena: GradArena,
-                       flags: int = 0, capacities: Sequence[int] | None = None, async_results: Sequence | None = None,
+                       flags: int | None = None, capacities: Sequence[int] | None = None, async_results: Sequence | None = None,
                        pipeline: ViewPipeline | None = None, accumulate: bool = False, all_reduce: bool = False,
                        chunks: int = 4, workspaces: Sequence | None = None, batched: bool = False) -> list[ViewState]:
     """A rank's share of a multi-view step: every view's forward + blend backward (two views in flight
@@ -460,6 +464,7 @@ def cuda_views_fwd_bwd(gaussians: dict, settings_list: Sequence, dL_dcolor_fns: 
     steps) -- the steady-state loop then never touches the caching allocator."""
     import contextlib
     from . import _C
+    flags = _C.resolve_flags(flags)
     M = gaussians["shs"].shape[1]
     if not _C.backward_geom_multi_supported(M):
         if not accumulate:
@@ -579,7 +584,7 @@ def sharded_step(view_fwd_bwd: Callable[[int], None], n_views: int, arena: GradA
     return mine
 
 
-def cuda_views_render(gaussians: dict, settings_list: Sequence, flags: int = 0, capacities: Sequence[int] | None = None,
+def cuda_views_render(gaussians: dict, settings_list: Sequence, flags: int | None = None, capacities: Sequence[int] | None = None,
                       async_results: Sequence | None = None, pipeline: ViewPipeline | None = None,
                       workspaces: Sequence | None = None,
                       sink: Callable[[int, torch.Tensor, torch.Tensor, torch.Tensor], None] | None = None,
@@ -593,6 +598,7 @@ def cuda_views_render(gaussians: dict, settings_list: Sequence, flags: int = 0, 
     writer drains; with workspaces the three tensors are views that the next call on that workspace overwrites."""
     import contextlib
     from . import _C
+    flags = _C.resolve_flags(flags)
     out = []
     if batched and capacities and async_results and all(c > 0 for c in capacities) and settings_list \
             and not (flags & (_C.FLAG_BINNING_KEY64 | _C.FLAG_REFERENCE)):

@@ -284,7 +284,7 @@ class ViewLoss:
 
 
 def fused_train_step(params: GaussianParamArena, settings_list: Sequence, losses: Sequence[ViewLoss], arena: GradArena,
-                     lrs: dict, flags: int = 0, pipeline: ViewPipeline | None = None, all_reduce: bool = False,
+                     lrs: dict, flags: int | None = None, pipeline: ViewPipeline | None = None, all_reduce: bool = False,
                      capacities=None, async_results=None, workspaces=None, chunks: int = 4, apply: bool | None = None,
                      batched: bool = False):
     """One optimisation step on this rank's views (train.py:86-128 for a batch of views; with `all_reduce` the
