@@ -212,7 +212,6 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
   float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f;   // accum_rec
   float lc0 = 0.0f, lc1 = 0.0f, lc2 = 0.0f;      // last_color
   float last_alpha = 0.0f;
-  const uint32_t one = (uint32_t)(px >= 0);  // == 1, per-lane and opaque to ptxas (see K6)
   const bool red_lane = (lane & 3) == 0 || lane == 2;
   const uint32_t red_off = lane == 2 ? 8u : (uint32_t)(lane >> 2);
 
@@ -269,20 +268,33 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
         const int last_rel = (int)last - (int)gbase;
         while (m) {
           const int j = bfind(m);
-          m &= ~(one << j);
+          m &= bits_below(j);   // j is the top set bit: clears it (BMSK + LOP3)
           const uint32_t ea = ebase + j * ENTRY_BYTES;
           const float4 e0 = lds128(ea);
           const float4 e1 = lds128(ea + 16);
           float dx, dy;
           const float power = pair_power<PRECISE>(e0, e1, pxf, pyf, dx, dy);
-          bool contrib = (j < last_rel) && !(power > 0.0f || power < e1.z);
-          float G = 0.0f, alpha = 0.0f;
-          if (contrib) {
+          bool contrib = (j < last_rel) && !(power > 0.0f || power < e1.y);
+          float G, alpha;
+          if constexpr (MMA) {
+            // Unconditional: a lane that fails the range test computes garbage (inf, NaN -> fminf gives 0.99) that the
+            // selects below turn into exact zeros -- no predicated chain, no zero initialisation, and NO warp vote: after
+            // the exact ellipse cull at staging ~97 % of the hits that reach this point have a contributing lane, so
+            // skipping the rest costs more (vote + branch + the re-convergence the compiler wraps around it, every hit)
+            // than letting them through as one more all-zero slot of the contraction.
             G = pair_gauss<PRECISE>(power);
-            alpha = fminf(0.99f, MUL(e1.y, G));
-            contrib = !(alpha < 1.0f / 255.0f);
+            alpha = fminf(0.99f, MUL(e1.z, G));
+            contrib = contrib && !(alpha < 1.0f / 255.0f);
+          } else {
+            G = 0.0f;
+            alpha = 0.0f;
+            if (contrib) {
+              G = pair_gauss<PRECISE>(power);
+              alpha = fminf(0.99f, MUL(e1.z, G));
+              contrib = !(alpha < 1.0f / 255.0f);
+            }
+            if (!__any_sync(0xffffffffu, contrib)) continue;
           }
-          if (!__any_sync(0xffffffffu, contrib)) continue;
 
           const float4 e2 = lds128(ea + 32);
           float dch, dL_dalpha;
@@ -328,7 +340,10 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
             // that do not contribute), plus the Gaussian's (x, y, opacity, id) for the epilogue
             sts32(w_addr, __float_as_uint(dch));
             sts32(w_addr + MG_TILE_BYTES, __float_as_uint(G * dL_dalpha));
-            if (lane == 0) sts128(i_addr, make_float4(e0.x, e0.y, e1.y, e1.w));
+            if (lane == 0) {   // {x, y} and {opacity, id} are register pairs of the two entry loads: two STS.64, no moves
+              sts64(i_addr, e0.x, e0.y);
+              sts64(i_addr + 8, e1.z, e1.w);
+            }
             w_addr += MG_STRIDE * 4;
             i_addr += 16;
             if (++ns == MG_SLOTS) {
@@ -339,7 +354,7 @@ blend_backward_kernel(const __grid_constant__ BlendBwdArgs args) {
             }
             continue;
           }
-          const float w = MUL(MUL(e1.y, dL_dalpha), G);  // dL_dG * G
+          const float w = MUL(MUL(e1.z, dL_dalpha), G);  // dL_dG * G
           const float wx = MUL(w, dx), wy = MUL(w, dy);
           const float r9 = warp_transpose_reduce9(MUL(dch, dLp0), MUL(dch, dLp1), MUL(dch, dLp2), wx, wy,
                                                   MUL(-0.5f * dx, wx), MUL(-0.5f * dy, wx), MUL(-0.5f * dy, wy),

@@ -9,7 +9,7 @@
 //                     BASELINE.json (measured ~2e-7).
 //
 // Shared-memory entry (48 bytes, one per staged list element, read by all lanes as broadcast):
-//   +0  {x, y, A|cx, B|cy}     +16 {C|cz, opacity, power_cut, id}     +32 {r, g, b, -}
+//   +0  {x, y, A|cx, B|cy}     +16 {C|cz, power_cut, opacity, id}     +32 {r, g, b, -}
 // Addresses are kept as 32-bit shared-window offsets and read with ld.shared.v4: nvcc otherwise
 // re-derives the (cluster-aware) shared window base inside the hot loop (S2UR SR_CgaCtaId + ULEA
 // per access in the first ncu capture, profiles/).
@@ -30,6 +30,9 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
@@ -132,10 +135,10 @@ __device__ __forceinline__ uint32_t stage_entry(bool valid, uint32_t list_index,
     float4 e0, e1;
     if (PRECISE) {
       e0 = q0;
-      e1 = make_float4(q1.x, q1.y, q2.w, __uint_as_float(id));
+      e1 = make_float4(q1.x, q2.w, q1.y, __uint_as_float(id));
     } else {
       e0 = make_float4(q0.x, q0.y, (-0.5f * GSR_LOG2E) * q0.z, -GSR_LOG2E * q0.w);
-      e1 = make_float4((-0.5f * GSR_LOG2E) * q1.x, q1.y, GSR_LOG2E * q2.w, __uint_as_float(id));
+      e1 = make_float4((-0.5f * GSR_LOG2E) * q1.x, GSR_LOG2E * q2.w, q1.y, __uint_as_float(id));
     }
     sts128(s_entry, e0);
     sts128(s_entry + 16, e1);
@@ -169,6 +172,17 @@ __device__ __forceinline__ int bfind(uint32_t x) {
   int r;
   asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
   return r;
+}
+// (1 << n) - 1 for n in [0, 31]: one BMSK
+__device__ __forceinline__ uint32_t bits_below(int n) {
+  uint32_t r;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(n));
+  return r;
+}
+// x, or a quiet NaN when `cond`: one predicated move (a finished pixel's coordinate, see blend_forward.cu)
+__device__ __forceinline__ float retire_if(bool cond, float x) {
+  asm("{ .reg .pred p; setp.ne.s32 p, %1, 0; @p mov.b32 %0, 0x7fc00000; }" : "+f"(x) : "r"((int)cond));
+  return x;
 }
 // keeps a shared-window address in a register (nvcc otherwise re-derives it -- S2UR + ULEA + MOV --
 // inside the hot loop)

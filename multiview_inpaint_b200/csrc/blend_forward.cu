@@ -66,16 +66,14 @@ blend_forward_kernel(const __grid_constant__ BlendFwdArgs args) {
   const int todo = (int)(range.y - range.x);
   const int rounds = (todo + BLEND_BATCH - 1) / BLEND_BATCH;
 
-  // == 1, but opaque to ptxas and per-lane (so it lives in a vector register): the shift below then
-  // needs no constant re-materialised per pair
-  const uint32_t one = (uint32_t)(px >= 0);
-  float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f, Dm = 15.0f;
-  uint32_t last = 0;
-  bool done = !inside;
+  float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
+  uint32_t last = 0, median_id = 0xFFFFFFFFu;   // the Gaussian at which T crossed 0.5 (its depth is fetched once, at the end)
+  // `done` (outside the image, or saturated) IS the NaN coordinate: no separate flag to keep in step with it
+#define GSR_DONE (pxf != pxf)
 
   for (int b = 0; b < rounds; b++) {
     // all pixels of the tile saturated -> stop (also the WAR barrier for the staging buffer)
-    if (__syncthreads_and(done)) break;
+    if (__syncthreads_and(GSR_DONE)) break;
     const int pos = b * BLEND_BATCH + tid;
     const uint32_t bits = stage_entry<PRECISE, GSR_REFINE_FWD != 0>(pos < todo, range.x + pos, point_list, rec,
                                                s_ent + tid * ENTRY_BYTES, (float)tile_x0, (float)tile_y0);
@@ -83,45 +81,44 @@ blend_forward_kernel(const __grid_constant__ BlendFwdArgs args) {
     __syncthreads();
 
     // ---- walk the entries that can touch this warp's sub-tile ----
-    if (!__all_sync(0xffffffffu, done)) {
+    if (!__all_sync(0xffffffffu, GSR_DONE)) {
 #pragma unroll 1
       for (int ws = 0; ws < 8; ws++) {
         // every pixel of the sub-tile saturated inside this batch: the rest of it can only be skipped
         // pair by pair (NaN coordinate), so stop walking at the next group of 32 entries
-        if (ws && __all_sync(0xffffffffu, done)) break;
+        if (ws && __all_sync(0xffffffffu, GSR_DONE)) break;
         unsigned m = lds32(s_mask + (warp * 8 + ws) * 4);  // bit 31 - j <=> entry j of this group
         const uint32_t etop = s_ent + (ws * 32 + 31) * ENTRY_BYTES;          // entry 31 of the group
         const uint32_t last_top = (uint32_t)(b * BLEND_BATCH + ws * 32 + 32);  // its 1-based list position
         while (m) {
           const int jr = bfind(m);  // entry 31 - jr
-          m &= ~(one << jr);
+          m &= bits_below(jr);      // jr is the top set bit: clears it (BMSK + LOP3, no constant to materialise)
           const uint32_t ea = etop - jr * ENTRY_BYTES;
           const float4 e0 = lds128(ea);
           const float4 e1 = lds128(ea + 16);
           float dx, dy;
           const float power = pair_power<PRECISE>(e0, e1, pxf, pyf, dx, dy);
-          if (!(power <= 0.0f && power >= e1.z)) continue;  // power > 0, below the cut-off, or NaN (done)
+          if (!(power <= 0.0f && power >= e1.y)) continue;  // power > 0, below the cut-off, or NaN (done)
           const float G = pair_gauss<PRECISE>(power);
-          const float alpha = fminf(0.99f, MUL(e1.y, G));
+          const float alpha = fminf(0.99f, MUL(e1.z, G));
           if (alpha < 1.0f / 255.0f) continue;
           const float test_T = MUL(T, SUB(1.0f, alpha));
-          if (test_T < 0.0001f) {
-            done = true;
-            pxf = __int_as_float(0x7fc00000);
-            continue;
-          }
+          const bool saturated = test_T < 0.0001f;
+          pxf = retire_if(saturated, pxf);   // one predicated move; the compiler's own version saves and restores pxf around the branch
+          if (saturated) continue;
           const float4 e2 = lds128(ea + 32);
           const float wgt = MUL(alpha, T);
           C0 = FMA(e2.x, wgt, C0);
           C1 = FMA(e2.y, wgt, C1);
           C2 = FMA(e2.z, wgt, C2);
-          if (T > 0.5f && test_T < 0.5f) Dm = __ldg(depths + __float_as_uint(e1.w));  // median depth
+          if (T > 0.5f && test_T < 0.5f) median_id = __float_as_uint(e1.w);  // median depth (A.5)
           T = test_T;
           last = last_top - (uint32_t)jr;
         }
       }
     }
   }
+#undef GSR_DONE
 
   if (inside) {
     const size_t HW = (size_t)H * W;
@@ -131,7 +128,7 @@ blend_forward_kernel(const __grid_constant__ BlendFwdArgs args) {
     out_color[pix] = FMA(T, __ldg(bg + 0), C0);
     out_color[HW + pix] = FMA(T, __ldg(bg + 1), C1);
     out_color[2 * HW + pix] = FMA(T, __ldg(bg + 2), C2);
-    out_depth[pix] = Dm;
+    out_depth[pix] = median_id != 0xFFFFFFFFu ? __ldg(depths + median_id) : 15.0f;
   }
 }
 
