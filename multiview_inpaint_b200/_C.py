@@ -624,6 +624,11 @@ def debug_set(knob: int, value: int):
     _check(_lib.gsr_debug_set(int(knob), int(value)), "gsr_debug_set")
 
 
+if os.environ.get("GSR_DEBUG_KNOBS"):   # experiments only (tools/gpu_knobs.sh): "knob=value,knob=value"
+    for _kv in os.environ["GSR_DEBUG_KNOBS"].split(","):
+        debug_set(*[int(x) for x in _kv.split("=")])
+
+
 def kernel_launches() -> int:
     return int(_lib.gsr_kernel_launches())
 
