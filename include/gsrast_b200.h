@@ -57,6 +57,8 @@ extern "C" {
  * dL_dmean2D / dL_dconic stay per-view (densification reads the per-view norm, gaussian_model.py:483). */
 #define GSR_FLAG_ACCUMULATE    8u
 #define GSR_FLAG_ASYNC        16u /* gsr_forward: never block the host (see gsr_forward)           */
+#define GSR_FLAG_SCRATCH_CLEARED 64u /* gsr_backward_blend / _views: the forward has cleared `scratch` (gsr_view_forward.backward_scratch)
+                                       and nothing has written it since: skip the clear                                  */
 #define GSR_FLAG_TIGHT_BINNING 32u /* two-level binning only (ignored with BINNING_KEY64 / REFERENCE): K1 stores, instead of
                                      the tile rect of the 3-sigma square (Appendix A.2 step 9), its intersection with the tiles
                                      the bounding box of the Gaussian's {alpha >= 1/255} ellipse reaches -- the very box the
@@ -126,6 +128,10 @@ typedef struct {
   char* image_buffer;       /* gsr_layout.image_bytes                                                     */
   int64_t capacity;         /* instances the binning buffer holds, 0 < capacity < GSR_MAX_INSTANCES       */
   int64_t* result_host;     /* pinned: [0] = N, [1] = status bits (low word trap, high word overflow)     */
+  char* backward_scratch;   /* optional (NULL: none): the `scratch` this view's gsr_backward_blend_views call will get,
+                               gsr_backward_scratch_bytes(P) bytes, 16-byte aligned.  K1 then clears it on the way (each CTA
+                               the rows of its own 256 Gaussians: 144 MB of stores under a latency-bound kernel instead of
+                               a memset of their own), and the backward is called with GSR_FLAG_SCRATCH_CLEARED.           */
 } gsr_view_forward;
 int gsr_forward_views(void* stream, int P, int D, int M, const float* means3D, const float* shs,
                       const float* colors_precomp, const float* opacities, const float* scales, float scale_modifier,

@@ -30,6 +30,7 @@ FLAG_PRECISE = 2
 FLAG_REFERENCE = 4     # reference-structure ablation baseline (cub sort, thread-per-pixel blend, 9 atomics/pair)
 FLAG_ACCUMULATE = 8
 FLAG_ASYNC = 16
+FLAG_SCRATCH_CLEARED = 64  # backward_blend(_views): the forward cleared the accumulators (forward_views(scratches_out=...))
 FLAG_TIGHT_BINNING = 32  # bin only the tiles the {alpha >= 1/255} bounding box reaches (same images / gradients, shorter lists)
 MAX_BATCH = 8           # views per batched launch of the front end / blend kernels (GSR_MAX_BATCH)
 GM_MAX_VIEWS = 4        # views per launch of the batched per-Gaussian backward (csrc/geom_backward_multi.cu)
@@ -83,7 +84,7 @@ class GsrViewGrad(C.Structure):
 class GsrViewForward(C.Structure):
     _fields_ = [("background", _vp), ("viewmatrix", _vp), ("projmatrix", _vp), ("cam_pos", _vp), ("tan_fovx", _f), ("tan_fovy", _f),
                 ("width", _i), ("height", _i), ("out_color", _vp), ("out_depth", _vp), ("radii", _vp), ("geom_buffer", _vp),
-                ("binning_buffer", _vp), ("image_buffer", _vp), ("capacity", _i64), ("result_host", _vp)]
+                ("binning_buffer", _vp), ("image_buffer", _vp), ("capacity", _i64), ("result_host", _vp), ("backward_scratch", _vp)]
 
 
 class GsrViewBackward(C.Structure):
@@ -445,11 +446,13 @@ def backward_blend(background, dL_dout_color, geomBuffer, binningBuffer, imageBu
 
 
 def forward_views(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, views, sh, degree,
-                  prefiltered, capacities, async_results, workspaces=None, flags=None):
+                  prefiltered, capacities, async_results, workspaces=None, flags=None, scratches_out=None):
     """Batched forward (gsr_forward_views): every pipeline stage is ONE launch for all `views` of the same Gaussians.
     views: list of dicts / settings objects with viewmatrix, projmatrix, campos, tanfovx, tanfovy, image_height,
     image_width (and optionally bg).  capacities[k] > 0 and async_results[k] (pinned int64[2]) per view; nothing
-    blocks the host.  -> list of (-1, color, radii, geom, binning, img, depth) like rasterize_gaussians."""
+    blocks the host.  -> list of (-1, color, radii, geom, binning, img, depth) like rasterize_gaussians.
+    scratches_out: pass an empty list when a backward follows -- it receives one accumulator buffer per view that K1 has
+    already cleared; hand it to backward_blend_views(scratches=...), which then skips its own clear."""
     flags = DEFAULT_FLAGS if flags is None else int(flags)
     P = means3D.shape[0]
     dev = means3D.device
@@ -491,6 +494,12 @@ def forward_views(background, means3D, colors, opacity, scales, rotations, scale
             g.out_color, g.out_depth, g.radii = color.data_ptr(), depth.data_ptr(), (radii.data_ptr() if P else None)
             g.geom_buffer, g.binning_buffer, g.image_buffer = geom.data_ptr(), binning.data_ptr(), img.data_ptr()
             g.capacity, g.result_host = cap, res.data_ptr()
+            g.backward_scratch = None
+            if scratches_out is not None and P:
+                nscratch = int(_lib.gsr_backward_scratch_bytes(P))
+                sc = ws.bytes("scratch", nscratch) if ws is not None else torch.empty(nscratch, dtype=torch.uint8, device=dev)
+                scratches_out.append(sc)
+                g.backward_scratch = sc.data_ptr()
             out.append((-1, color, radii, geom, binning, img, depth))
         if nv:
             _check(_lib.gsr_forward_views(_stream(dev), P, int(degree), M, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
@@ -499,9 +508,13 @@ def forward_views(background, means3D, colors, opacity, scales, rotations, scale
     return out
 
 
-def backward_blend_views(background, dL_dout_colors, geoms, binnings, imgs, P, flags=None, workspaces=None):
-    """K7 of several views in one launch (gsr_backward_blend_views) -> list of packed accumulators (uint8 scratch)."""
+def backward_blend_views(background, dL_dout_colors, geoms, binnings, imgs, P, flags=None, workspaces=None, scratches=None):
+    """K7 of several views in one launch (gsr_backward_blend_views) -> list of packed accumulators (uint8 scratch).
+    scratches: the buffers forward_views(scratches_out=...) handed out (already cleared by K1)."""
     flags = DEFAULT_FLAGS if flags is None else int(flags)
+    if scratches:
+        assert len(scratches) == len(dL_dout_colors)
+        flags |= FLAG_SCRATCH_CLEARED
     nv = len(dL_dout_colors)
     if nv == 0:
         return []
@@ -510,11 +523,15 @@ def backward_blend_views(background, dL_dout_colors, geoms, binnings, imgs, P, f
         nscratch = int(_lib.gsr_backward_scratch_bytes(P))
         background = _f32c(background, "background")
         arr = (GsrViewBackward * nv)()
+        given = scratches if scratches else None
         keep, scratches = [], []
         for k in range(nv):
             dL = _f32c(dL_dout_colors[k], "dL_dout_color")
             keep.append(dL)
-            sc = workspaces[k].bytes("scratch", nscratch) if workspaces is not None else torch.empty(nscratch, dtype=torch.uint8, device=dev)
+            if given:
+                sc = given[k]
+            else:
+                sc = workspaces[k].bytes("scratch", nscratch) if workspaces is not None else torch.empty(nscratch, dtype=torch.uint8, device=dev)
             scratches.append(sc)
             g = arr[k]
             g.background, g.width, g.height = _ptr(background), int(dL.shape[2]), int(dL.shape[1])

@@ -400,6 +400,7 @@ struct FwdView {   // host-side working set of one view
   char* geom;
   char* img;
   char* bin;       // set once the capacity is known
+  char* scratch;   // optional: the backward's accumulator, cleared by K1
   int64_t cap;
   int G, end_bit;
 };
@@ -452,6 +453,7 @@ static int front_end(cudaStream_t s, FwdView* v, int nv, int P, int D, int M, co
     q.depth_keys = k64 ? nullptr : reinterpret_cast<uint32_t*>(w.geom + gl.depth_keys);
     q.rects = k64 ? nullptr : reinterpret_cast<ushort4*>(w.geom + gl.rects);
     q.status = status_of(w, gl);
+    q.gacc = reinterpret_cast<float4*>(w.scratch);
   }
   GSR_CUDA(launch_zero_regions(s, z.data(), (int)z.size()), "clear counters");
   PROF(0);
@@ -665,6 +667,7 @@ static FwdView make_fwd_view(int W, int H, const float* view_d, const float* pro
   w.geom = geom;
   w.img = img;
   w.bin = nullptr;
+  w.scratch = nullptr;
   w.cap = 0;
   w.G = w.cam.grid_x * w.cam.grid_y;
   w.end_bit = tile_bits(W, H);
@@ -823,7 +826,10 @@ int gsr_forward_views(void* stream, int P, int D, int M, const float* means3D, c
     vs[(size_t)k] = make_fwd_view(in.width, in.height, in.viewmatrix, in.projmatrix, in.cam_pos, in.tan_fovx, in.tan_fovy,
                                   scale_modifier, in.background, in.out_color, in.out_depth, in.radii, in.geom_buffer,
                                   in.image_buffer);
+    if (reinterpret_cast<uintptr_t>(in.backward_scratch) & 15)
+      return fail(GSR_E_INVALID, "gsr_forward_views: backward_scratch must be 16-byte aligned");
     vs[(size_t)k].bin = in.binning_buffer;
+    vs[(size_t)k].scratch = in.backward_scratch;
     vs[(size_t)k].cap = in.capacity;
     in.result_host[0] = 0;
     in.result_host[1] = 0;
@@ -943,7 +949,9 @@ int gsr_backward_blend_views(void* stream, int P, const gsr_view_backward* views
     z[(size_t)k] = {in.scratch, (size_t)P * 48};
   }
   PROF(7);
-  if (n_views == 1)
+  if (flags & GSR_FLAG_SCRATCH_CLEARED) {
+    // K1 cleared the accumulators (gsr_view_forward.backward_scratch)
+  } else if (n_views == 1)
     GSR_CUDA(cudaMemsetAsync(z[0].ptr, 0, z[0].bytes, s), "memset accumulator");
   else
     GSR_CUDA(launch_zero_regions(s, z.data(), n_views), "clear accumulators");

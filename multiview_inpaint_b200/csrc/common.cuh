@@ -144,6 +144,7 @@ struct PreView {
   uint32_t* depth_keys;  // two-level binning only (else NULL)
   ushort4* rects;        // two-level binning only (else NULL)
   int32_t* status;
+  float4* gacc;          // optional: the blend backward's 48-byte accumulators, cleared here (else NULL)
 };
 // One launch for all views: CTA b works on view b % nv, Gaussians [256 (b / nv), +256) -- the CTAs of the views
 // of one Gaussian chunk are co-resident, so the (P,M,3) SH rows and the other parameters come from HBM once and

@@ -152,6 +152,14 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D,
   uint32_t* __restrict__ depth_keys = pv_.depth_keys;
   ushort4* __restrict__ rects = pv_.rects;
   int32_t* __restrict__ status = pv_.status;
+  if (pv_.gacc != nullptr) {
+    // the backward's accumulator rows of this CTA's Gaussians (48 bytes each, contiguous): three coalesced 16-byte stores
+    // per thread, issued before anything else so that they drain under the loads below
+    const size_t first = (size_t)(blockIdx.x / (unsigned)args.nv) * 256;
+    const int n4 = 3 * (int)min((size_t)256, (size_t)P - first);
+    float4* g4 = pv_.gacc + 3 * first;
+    for (int t = threadIdx.x; t < n4; t += 256) g4[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
   load_camera(cam, s_cam);
   const float* view = s_cam;
   const float* proj = s_cam + 16;

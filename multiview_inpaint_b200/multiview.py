@@ -374,12 +374,13 @@ def cuda_views_fwd_blend_batched(gaussians: dict, settings_list: Sequence, dL_dc
         return []
     rs0 = rss[0]
     e = torch.empty(0, device=gaussians["means3D"].device)
+    cleared = []   # the blend backward's accumulators, cleared by K1 on the way (no memset of their own)
     outs = _C.forward_views(rs0.bg, gaussians["means3D"], e, gaussians["opacities"], gaussians["scales"], gaussians["rotations"],
                             rs0.scale_modifier, e, rss, gaussians["shs"], rs0.sh_degree, rs0.prefiltered, capacities,
-                            async_results, workspaces=workspaces, flags=flags)
+                            async_results, workspaces=workspaces, flags=flags, scratches_out=cleared)
     dLs = [fn(o[1]) for fn, o in zip(dL_dcolor_fns, outs)]
     scratches = _C.backward_blend_views(rs0.bg, dLs, [o[3] for o in outs], [o[4] for o in outs], [o[5] for o in outs],
-                                        gaussians["means3D"].shape[0], flags=flags, workspaces=workspaces)
+                                        gaussians["means3D"].shape[0], flags=flags, workspaces=workspaces, scratches=cleared)
     return [ViewState(o[1], o[6], o[2], -1, o[3], sc, rs) for o, sc, rs in zip(outs, scratches, rss)]
 
 

@@ -146,3 +146,42 @@ def test_batched_step_gradients_match_the_per_view_step(nv):
         assert rel_err(a_new.views[name].cpu().numpy(), a_ref.views[name].cpu().numpy()) < 1e-4, name
     assert torch.equal(a_new.visible_count, a_ref.visible_count) and torch.equal(a_new.max_radii, a_ref.max_radii)
     assert rel_err(a_new.grad_norm_accum.cpu().numpy(), a_ref.grad_norm_accum.cpu().numpy()) < 1e-4
+
+
+def test_forward_clears_the_backward_accumulators():
+    """gsr_view_forward.backward_scratch + GSR_FLAG_SCRATCH_CLEARED: K1 clears each view's 48-byte accumulator rows on the
+    way, so the blend backward starts without a memset of its own.  The buffers are poisoned first (NaN bit pattern) and
+    P is not a multiple of K1's 256-Gaussian CTAs; the accumulators must equal those of the path that clears them itself."""
+    from multiview_inpaint_b200 import _C
+    sc, g = _scene(P=7013, seed=17)
+    P = sc["P"]
+    bg = torch.zeros(3, device=DEV)
+    nv = 3
+    cams = [c.to(DEV) for c in S.orbit_cameras(nv, sc["W"], sc["H"], max_deg=10.0)]
+    rss = [_settings(c, bg, sc["sh_degree"]) for c in cams]
+    wts = [S.loss_weights(sc["W"], sc["H"], 60 + k).to(DEV) for k in range(nv)]
+    caps = [int(_single(g, rs, _C.DEFAULT_FLAGS)[0] * 1.3) + 100 for rs in rss]
+    e = torch.empty(0, device=DEV)
+
+    def run(clear_in_forward):
+        res = torch.zeros(nv, 2, dtype=torch.int64).pin_memory()
+        wss = [_C.Workspace(DEV) for _ in range(nv)]
+        nb = int(_C._lib.gsr_backward_scratch_bytes(P))
+        for w in wss:
+            w.bytes("scratch", nb).fill_(0xFF)
+        cleared = [] if clear_in_forward else None
+        outs = _C.forward_views(bg, g["means3D"], e, g["opacities"], g["scales"], g["rotations"], 1.0, e, rss, g["shs"],
+                                sc["sh_degree"], False, caps, [res[k] for k in range(nv)], workspaces=wss, scratches_out=cleared)
+        scr = _C.backward_blend_views(bg, wts, [o[3] for o in outs], [o[4] for o in outs], [o[5] for o in outs], P,
+                                      workspaces=wss, scratches=cleared)
+        torch.cuda.synchronize()
+        assert int(res[:, 1].sum()) == 0
+        if clear_in_forward:
+            assert all(a.data_ptr() == b.data_ptr() for a, b in zip(scr, cleared))
+        return [s.view(torch.float32)[:12 * P].clone() for s in scr]
+
+    ref, new = run(False), run(True)
+    for a, b in zip(ref, new):
+        assert torch.isfinite(b).all()
+        assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+        assert torch.equal(a == 0, b == 0)   # rows nobody blended stay exactly zero
