@@ -96,26 +96,27 @@ def survey_bytes(P, V, N, G, W, H, M):
     }
 
 
-def algorithmic_bytes(P, V, N, G, W, H, M, nv=1):
+def algorithmic_bytes(P, V, N, G, W, H, M, nv=1, clear_in_k1=False):
     """Bytes per view THIS design must move, per stage, for `nv` views sharing one batched launch
     (the per-Gaussian inputs are then read once for all of them):
       preprocess     reads 44 B of mean / scale / rotation / opacity per Gaussian and the 12 M-byte SH row of the V visible
                      ones (once per batch); writes the 48-byte blend record + depth + clamp bits per visible Gaussian and
                      radius, tiles_touched, depth key and tile rect (20 B) per Gaussian
       depth_sort     histogram read (4 P) + compacting first pass (4 P in, 8 V out) + three more passes of 16 V
-      duplicate      order + rect in, offsets out (16 V), 8 N of (tile, id) pairs out; the tile_count reductions stay in L2
+      duplicate      order + rect in, offsets out (16 V), 8 N of (tile, id) pairs out; the digit counters stay in shared memory
       tile_sort      16 N per 8-bit pass of the tile id
-      tile_ranges    per-tile counts in, ranges out
+      tile_ranges    ranges out (the 32-ary searches in the sorted keys touch a few lines per tile: not a streaming stage)
       blend_forward  list + records (44 N) and the per-pixel outputs (24 WH): an upper bound, the walk stops at saturation
-      accum_clear    the packed 48-byte accumulator per Gaussian
+      accum_clear    the packed 48-byte accumulator per Gaussian; with the batched front end K1 clears it on the way
+                     (clear_in_k1: the 48 P bytes are charged to preprocess and this stage has no launch)
       blend_backward 80 N + 20 WH (as SURVEY: records in, nine reductions out per instance)
       geom_backward  batched K8+K9: parameters + SH rows once per batch, per view the record + accumulator of the visible
                      Gaussians (96 V) and radius + clamp bits (5 P); the gradient row (4 (11 + 3 M) B per Gaussian) and the
                      three statistics written once per batch"""
     tile_passes = (max(1, math.ceil(math.log2(max(G, 2)))) + 7) // 8
     grad_row = 4 * (3 + 3 * M + 1 + 3 + 4)
-    return {
-        "preprocess": (44 * P + 12 * M * V) / nv + 53 * V + 20 * P,
+    out = {
+        "preprocess": (44 * P + 12 * M * V) / nv + 53 * V + 20 * P + (48 * P if clear_in_k1 else 0),
         "depth_sort": 8 * P + 56 * V,
         "duplicate": 16 * V + 8 * N,
         "tile_sort": 16 * N * tile_passes,
@@ -125,6 +126,10 @@ def algorithmic_bytes(P, V, N, G, W, H, M, nv=1):
         "blend_backward": 80 * N + 20 * W * H,
         "geom_backward": (44 * P + 12 * M * V + (grad_row + 12) * P) / nv + 96 * V + 5 * P,
     }
+    if clear_in_k1:
+        del out["accum_clear"]
+    del out["tile_ranges"]   # latency of G x log32(N) probes, not bytes: no bandwidth figure
+    return out
 
 
 def issue_counters():
@@ -798,7 +803,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel ----
     peak, peak_kind = peaks()
     nv_shared = 1 if args.no_batched else min(len(mine), 8)      # views per batched launch (GSR_MAX_BATCH)
-    alg = algorithmic_bytes(P, V, N, G, W, H, M, nv_shared)
+    alg = algorithmic_bytes(P, V, N, G, W, H, M, nv_shared, clear_in_k1=not args.no_batched)
     alg_survey = survey_bytes(P, V, N, G, W, H, M)
     n_view_steps = max(len(mine) * args.steps, 1)
     per_launch = {k: stage_ms[k] / max(stage_cnt[k], 1) for k in stage_ms}

@@ -397,8 +397,9 @@ const char* gsr_last_error(void);
 int gsr_version(void);
 
 /* Experiment switches (tools/ only; the product path never calls this).  knob 0: warp ranking of the radix sort
- * (0 match_any, 1 ballots, 2 shared-memory atomicOr = default); knob 1: 0 drops the per-instance tile_count atomics of
- * the expansion (results are then WRONG: timing experiments only); knob 2: resident CTAs per SM K1 is compiled for (4 / 5 / 6);
+ * (0 match_any, 1 ballots, 2 shared-memory atomicOr = default); knob 1: how the expansion counts its instances: 2 (default) per-CTA digit histograms for the
+ * tile sort + tile ranges read off the sorted keys, 1 per-instance tile_count atomics (the previous scheme, identical results), 0 nothing
+ * (results are then WRONG: timing experiments only); knob 2: resident CTAs per SM K1 is compiled for (4 / 5 / 6);
  * knob 3: reduction of the blend backward's nine sums: 1 (default) tensor-core contraction (mma.sync m16n8k8 tf32, hi + lo
  * split), 0 the round-1 shuffle butterfly -- same sums up to fp32 rounding, kept for A/B timing and the cross-check test. */
 int gsr_debug_set(int knob, int value);

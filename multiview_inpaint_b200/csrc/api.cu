@@ -239,7 +239,7 @@ int gsr_version(void) { return GSR_VERSION; }
 int gsr_debug_set(int knob, int value) {
   switch (knob) {
     case 0: if (value < 0 || value > 2) return fail(GSR_E_INVALID, "gsr_debug_set: rank mode 0..2"); g_rs_rank_mode = value; return 0;
-    case 1: g_bin_count_atomics = value != 0; return 0;
+    case 1: if (value < 0 || value > 2) return fail(GSR_E_INVALID, "gsr_debug_set: count mode 0..2"); g_bin_count_mode = value; return 0;
     case 2: g_pre_min_blocks = value; return 0;
     case 3: g_bwd_mma = value != 0; return 0;
     default: return fail(GSR_E_INVALID, "gsr_debug_set: unknown knob");
@@ -413,11 +413,15 @@ static int front_end(cudaStream_t s, FwdView* v, int nv, int P, int D, int M, co
                      const float* rotations, const float* cov3D_precomp, int prefiltered, uint32_t flags, bool also_binning);
 static int bin_and_blend(cudaStream_t s, FwdView* v, int nv, int P, uint32_t flags, bool clear);
 
+// what the expansion's counting scheme needs cleared: the per-tile counters (mode 1)
+static ZeroRegion tile_counter_region(const FwdView& w, const ImageLayout& il) {
+  return {w.img + il.tile_count, (size_t)w.G * 4};   // G words: cleared whatever scheme bin_and_blend picks
+}
 static void binning_zero_regions(const FwdView& w, const GeomLayout& gl, const ImageLayout& il, int P, uint32_t flags,
                                  std::vector<ZeroRegion>& z) {
   const BinningLayout bl = binning_layout(w.cap, w.cam.W, w.cam.H, flags);
   z.push_back({w.geom + gl.scan_temp, gl.scan_temp_bytes});
-  z.push_back({w.img + il.tile_count, (size_t)w.G * 4});
+  z.push_back(tile_counter_region(w, il));
   z.push_back({w.bin + bl.temp, bl.temp_bytes});
   (void)P;
 }
@@ -438,7 +442,7 @@ static int front_end(cudaStream_t s, FwdView* v, int nv, int P, int D, int M, co
     if (also_binning && !k64) {   // status block + the adjacent scan temp as one region
       z.push_back({w.geom + gl.status, gl.scan_temp + gl.scan_temp_bytes - gl.status});
       const BinningLayout bl = binning_layout(w.cap, w.cam.W, w.cam.H, flags);
-      z.push_back({w.img + il.tile_count, (size_t)w.G * 4});
+      z.push_back(tile_counter_region(w, il));
       z.push_back({w.bin + bl.temp, bl.temp_bytes});
     } else {
       z.push_back({w.geom + gl.status, 32});
@@ -503,6 +507,15 @@ static int bin_and_blend(cudaStream_t s, FwdView* v, int nv, int P, uint32_t fla
     std::vector<BinView> bins;
     std::vector<PrepView> preps;
     std::vector<SortSeg<uint32_t>> segs;
+    std::vector<RangeView> rviews;
+    // How the expansion counts (binning.cu): per-CTA digit histograms + a range search in the sorted keys (2) win where
+    // rects are small -- headline 0.079 -> 0.061 + 0.009 ms, SVD orbit 0.109 -> 0.051 + 0.005 ms -- and lose 2 % where a few
+    // hundred tiles per Gaussian make the per-instance reductions cheap next to the stores (4K stress shape): there, mode 1.
+    int count_mode = g_bin_count_mode;
+    if (count_mode == 2)
+      for (int k = 0; k < nv; k++)
+        if (v[k].cap > 32 * (int64_t)(P > 0 ? P : 1)) count_mode = 1;
+    const int bases = count_mode == 2 ? 2 : 1;
     int end_bit = 0;
     bool same_bits = true;
     for (int k = 0; k < nv; k++) {
@@ -536,6 +549,8 @@ static int bin_and_blend(cudaStream_t s, FwdView* v, int nv, int P, uint32_t fla
       b.vals = va;
       b.cap = (uint32_t)w.cap;
       b.tile_count = reinterpret_cast<uint32_t*>(w.img + il.tile_count);
+      b.hist = sort_hist_ptr(w.bin + bl.temp);
+      b.end_bit = w.end_bit;
       b.gx = w.cam.grid_x;
       b.ticket = reinterpret_cast<uint32_t*>(w.geom + gl.scan_temp);
       b.lb_status = reinterpret_cast<unsigned long long*>(w.geom + gl.scan_temp + align_up(16));
@@ -563,20 +578,33 @@ static int bin_and_blend(cudaStream_t s, FwdView* v, int nv, int P, uint32_t fla
       q.vals_alt = valt;
       q.temp = w.bin + bl.temp;
       segs.push_back(q);
+      RangeView rv{};
+      rv.keys = kout;
+      rv.n_dev = q.n_dev;
+      rv.cap = w.cap;
+      rv.ranges = pr.ranges;
+      rv.G = w.G;
+      rviews.push_back(rv);
       if (end_bit == 0) end_bit = w.end_bit;
       same_bits = same_bits && end_bit == w.end_bit;
     }
     if (!z.empty()) GSR_CUDA(launch_zero_regions(s, z.data(), (int)z.size()), "clear binning counters");
     PROF(3);
-    GSR_CUDA(launch_bin_expand(s, bins.data(), (int)bins.size()), "scan + duplicate (depth order)");
-    PROF(5);
-    GSR_CUDA(launch_tile_prepare(s, preps.data(), (int)preps.size()), "tile ranges + digit bases");
+    GSR_CUDA(launch_bin_expand(s, bins.data(), (int)bins.size(), count_mode), "scan + duplicate (depth order)");
+    if (count_mode != 2) {
+      PROF(5);
+      GSR_CUDA(launch_tile_prepare(s, preps.data(), (int)preps.size()), "tile ranges + digit bases");
+    }
     PROF(4);
     if (same_bits) {
-      GSR_CUDA(launch_sort_pairs_u32_batched(s, segs.data(), (int)segs.size(), end_bit, true, false, true), "tile sort");
+      GSR_CUDA(launch_sort_pairs_u32_batched(s, segs.data(), (int)segs.size(), end_bit, bases, false, true), "tile sort");
     } else {  // views with different tile-id widths: one sort per view
       for (size_t k = 0; k < segs.size(); k++)
-        GSR_CUDA(launch_sort_pairs_u32_batched(s, &segs[k], 1, preps[k].end_bit, true, false, true), "tile sort");
+        GSR_CUDA(launch_sort_pairs_u32_batched(s, &segs[k], 1, preps[k].end_bit, bases, false, true), "tile sort");
+    }
+    if (count_mode == 2) {
+      PROF(5);
+      GSR_CUDA(launch_tile_ranges_views(s, rviews.data(), (int)rviews.size()), "tile ranges");
     }
   } else if (any) {  // the literal 64-bit key paths: one view at a time
     for (int k = 0; k < nv; k++) {

@@ -127,7 +127,8 @@ BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags);
 extern int g_rs_rank_mode;         // scan_sort.cu: 0 match_any, 1 ballots, 2 shared atomicOr (default)
 extern int g_pre_min_blocks;       // preprocess.cu: resident CTAs per SM K1 is compiled for (4, 5 or 6 = default)
 extern bool g_bwd_mma;             // blend_backward.cu: true (default) = tensor-core contraction of the nine sums, false = shuffle butterfly
-extern bool g_bin_count_atomics;   // binning.cu: false drops the per-instance tile_count atomics (WRONG results: timing only)
+extern int g_bin_count_mode;       // binning.cu: 2 (default) per-CTA digit histograms + ranges off the sorted keys, 1 per-instance tile_count
+                                   // atomics + tile_prepare (the previous scheme), 0 nothing (WRONG results: timing only)
 
 // ---- host launchers (one per translation unit) --------------------------------------------------
 void set_error(const char* msg);
@@ -187,7 +188,8 @@ struct SortSeg {
 // compact: the first pass drops keys equal to 0xFFFFFFFF (culled Gaussians) -- the output holds *n_dev_compact pairs
 // temp_zeroed: the caller has already cleared every segment's temp (launch_zero_regions) -- no memsets here
 cudaError_t launch_sort_pairs_u32_batched(cudaStream_t s, const SortSeg<uint32_t>* segs, int nseg, int end_bit,
-                                          bool have_bases, bool compact, bool temp_zeroed);
+                                          int have_bases, bool compact, bool temp_zeroed);   // have_bases: 0 histogram pass,
+                                          // 1 exclusive bases in temp, 2 digit COUNTS in temp (scanned here)
 cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp);
@@ -209,7 +211,9 @@ struct BinView {
   uint32_t* tile_keys;             // [cap] out
   uint32_t* vals;                  // [cap] out
   uint32_t cap;
-  uint32_t* tile_count;            // [G], zeroed by the caller
+  uint32_t* tile_count;            // [G], zeroed by the caller (count mode 1)
+  uint32_t* hist;                  // the tile sort's [pass][256] digit counters, zeroed by the caller (count mode 2)
+  int end_bit;                     // tile-id width
   int gx;
   unsigned long long* lb_status;   // look-back words, zeroed by the caller (scan_temp + 256)
   uint32_t* ticket;                // zeroed by the caller (scan_temp)
@@ -225,7 +229,15 @@ struct PrepView {
   int passes, end_bit;
   uint32_t* hist;
 };
-cudaError_t launch_bin_expand(cudaStream_t s, const BinView* views, int nv);
+struct RangeView {
+  const uint32_t* keys;    // sorted tile ids
+  const uint32_t* n_dev;   // N on the device
+  int64_t cap;
+  uint2* ranges;           // [G], every entry written
+  int G;
+};
+cudaError_t launch_tile_ranges_views(cudaStream_t s, const RangeView* views, int nv);
+cudaError_t launch_bin_expand(cudaStream_t s, const BinView* views, int nv, int count_mode);
 int64_t bin_big_capacity(int64_t cap);
 cudaError_t launch_tile_prepare(cudaStream_t s, const PrepView* views, int nv);
 // Zeroes up to 4 * GSR_MAX_BATCH regions (4-byte aligned, sizes multiples of 4) with ONE launch.

@@ -526,7 +526,7 @@ static cudaError_t rs_launch_pass(cudaStream_t s, const RsPassArgs<KeyT>& pa, in
 // to ~0 and the later passes read their element count from seg.n_dev_compact (the number of surviving keys).
 template <typename KeyT>
 static cudaError_t sort_pairs_batched(cudaStream_t s, const SortSeg<KeyT>* segs, int nseg, int end_bit,
-                                      bool have_bases, bool compact, bool temp_zeroed = false) {
+                                      int have_bases, bool compact, bool temp_zeroed = false) {
   if (nseg <= 0) return cudaSuccess;
   if (nseg > GSR_MAX_BATCH) return cudaErrorInvalidValue;
   constexpr int ITEMS = RsCfg<KeyT>::ITEMS;
@@ -573,6 +573,9 @@ static cudaError_t sort_pairs_batched(cudaStream_t s, const SortSeg<KeyT>* segs,
       rs_histogram_kernel<KeyT, false><<<dim3(hist_blocks, nseg), 256, 0, s>>>(ha, end_bit);
     rs_scan_hist_kernel<<<dim3(passes, nseg), RS_RADIX, 0, s>>>(sa);
     count_launch(2);
+  } else if (have_bases == 2) {   // the producer of the keys counted the digits (bin_expand_kernel): scan only
+    rs_scan_hist_kernel<<<dim3(passes, nseg), RS_RADIX, 0, s>>>(sa);
+    count_launch(1);
   }
   count_launch(passes);
 
@@ -614,7 +617,7 @@ static cudaError_t sort_pairs_batched(cudaStream_t s, const SortSeg<KeyT>* segs,
 }
 
 cudaError_t launch_sort_pairs_u32_batched(cudaStream_t s, const SortSeg<uint32_t>* segs, int nseg, int end_bit,
-                                          bool have_bases, bool compact, bool temp_zeroed) {
+                                          int have_bases, bool compact, bool temp_zeroed) {
   return sort_pairs_batched<uint32_t>(s, segs, nseg, end_bit, have_bases, compact, temp_zeroed);
 }
 
@@ -623,14 +626,14 @@ cudaError_t launch_sort_pairs_u32(cudaStream_t s, int64_t n, const uint32_t* n_d
                                   uint32_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp, bool have_bases) {
   if (n <= 0) return cudaSuccess;
   SortSeg<uint32_t> g{n, n_dev, nullptr, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, temp};
-  return sort_pairs_batched<uint32_t>(s, &g, 1, end_bit, have_bases, false);
+  return sort_pairs_batched<uint32_t>(s, &g, 1, end_bit, have_bases ? 1 : 0, false);
 }
 cudaError_t launch_sort_pairs_u64(cudaStream_t s, int64_t n, const uint32_t* n_dev, const uint64_t* keys_in,
                                   const uint32_t* vals_in, uint64_t* keys_out, uint32_t* vals_out,
                                   uint64_t* keys_alt, uint32_t* vals_alt, int end_bit, char* temp) {
   if (n <= 0) return cudaSuccess;
   SortSeg<uint64_t> g{n, n_dev, nullptr, keys_in, vals_in, keys_out, vals_out, keys_alt, vals_alt, temp};
-  return sort_pairs_batched<uint64_t>(s, &g, 1, end_bit, false, false);
+  return sort_pairs_batched<uint64_t>(s, &g, 1, end_bit, 0, false);
 }
 
 }  // namespace gsr

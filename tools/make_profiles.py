@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
 STAGE_OF = {"preprocess_kernel": "preprocess", "bin_expand_kernel": "duplicate", "bin_expand_big_kernel": "duplicate",
-            "tile_prepare_kernel": "tile_ranges", "blend_forward_kernel": "blend_forward", "blend_backward_kernel": "blend_backward",
+            "tile_prepare_kernel": "tile_ranges", "tile_ranges_views_kernel": "tile_ranges", "blend_forward_kernel": "blend_forward", "blend_backward_kernel": "blend_backward",
             "geom_backward_kernel": "geom_backward", "view_stats_kernel": "view_stats", "scan_kernel": "scan"}
 
 def short(name):
