@@ -53,7 +53,8 @@ if os.path.exists(rep):
     # launches divided by the views.  The onesweep launches split into the depth sort (the first 4: 32 key bits) and the
     # tile sort (the rest) by order.
     views = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    STAGE_OF.update({"geom_backward_multi_kernel": "geom_backward", "zero_regions_kernel": "accum_clear"})
+    STAGE_OF.update({"geom_backward_multi_kernel": "geom_backward"})   # zero_regions_kernel: counters / look-back words only
+                                                                        # (K1 clears the accumulators since r02_v4)
     traffic, seen_sweeps = {}, 0
     for r in rows[2:]:
         n = short(r[ki]).split("<")[0]
