@@ -63,6 +63,11 @@ class GradArena:
         if storage is None:
             storage = torch.empty(max(total, 4), dtype=torch.float32, device=device)
         storage.zero_()
+        if self._handle is not None:
+            # every rank's replica (and the allocation's signal pads) initialised before anybody's first in-switch
+            # reduction can touch it: one host-level rendezvous per arena, at creation only
+            torch.cuda.synchronize(device)
+            dist.barrier(group)
         self.storage = storage
         self._n_f32 = n_flat + Pp                     # float SUM segment: flat + grad_norm_accum
         self._sh_first = offs[1]                      # first float of the (P, M, 3) SH gradient inside it

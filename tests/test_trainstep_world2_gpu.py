@@ -47,6 +47,8 @@ def _worker(rank, world, port, out_dir, n_views=4):
     arena = mv.GradArena(pa.P, M, dev, symmetric=True)
     if os.environ.get("GSR_TEST_FORCE_NVLS") and arena._mc:
         arena.method = "nvls"
+    if os.environ.get("GSR_TEST_FORCE_NCCL"):
+        arena.method = "nccl"
     arena.flat.fill_(3.0)          # stale gradients: a rank without views must not contribute them
     arena.visible_count.fill_(5)
     losses = [ViewLoss(gts[v], 0.2, weight=1.0 / n_views) for v in mine]
