@@ -698,19 +698,22 @@ def run_ours(args):
         # Pick the exchange on the STEP it is part of, not on the collective alone: the in-switch reduction overlaps the chunked
         # per-Gaussian backward, an NCCL all-reduce follows it.  A few steps of every candidate (collective, Gaussian-range chunks,
         # CTAs of the reduction kernel), max over ranks, keep the fastest -- part of the warm-up, outside every timed region.
-        cands = [("nccl", 1, 0)]
+        cands = [("nccl", 1, 0, False)]
         if arena._mc:
-            cands += [("nvls", 4, 148), ("nvls", 4, 74), ("nvls", 8, 74), ("nvls", 4, 0)]   # tools/exp_scale8.py: the sweep these come from
+            # tools/exp_scale8.py: the sweep these come from; the tapered ones (half-length first and last Gaussian range,
+            # multiview.chunk_ranges) start the links earlier and shorten the reduction tail nobody overlaps
+            cands += [("nvls", 4, 148, False), ("nvls", 4, 74, False), ("nvls", 8, 74, False), ("nvls", 4, 0, False),
+                      ("nvls", 5, 74, True), ("nvls", 6, 74, True)]
         trials = []
-        for m_, c_, b_ in cands:
-            arena.method, arena.nvls_blocks, args.ar_chunks = m_, b_, c_
+        for m_, c_, b_, tp_ in cands:
+            arena.method, arena.nvls_blocks, args.ar_chunks, arena.taper = m_, b_, c_, tp_
             for _ in range(2):
                 step_resident()
             t_ = timed(step_resident, 5) / 5
-            trials.append({"method": m_, "chunks": c_, "nvls_blocks": b_, "ms_per_step": round(t_, 4)})
+            trials.append({"method": m_, "chunks": c_, "nvls_blocks": b_, "taper": tp_, "ms_per_step": round(t_, 4)})
         best = min(trials, key=lambda t: t["ms_per_step"])
-        arena.method, arena.nvls_blocks, args.ar_chunks = best["method"], best["nvls_blocks"], best["chunks"]
-        comm = dict(comm, method=best["method"], chunks=best["chunks"], nvls_blocks=best["nvls_blocks"], step_trials=trials)
+        arena.method, arena.nvls_blocks, args.ar_chunks, arena.taper = best["method"], best["nvls_blocks"], best["chunks"], best["taper"]
+        comm = dict(comm, method=best["method"], chunks=best["chunks"], nvls_blocks=best["nvls_blocks"], taper=best["taper"], step_trials=trials)
         assert not av.check(mine)
     V = int((stats["radii"] > 0).sum().item())
     N = int(stats["N"])

@@ -89,6 +89,7 @@ class GradArena:
         return self._mc != 0 and self.method == "nvls"
 
     method = "nvls"   # preferred collective when a multicast mapping exists; see calibrate()
+    taper = False     # chunk_ranges(): half-length first and last range of the pipelined exchange
     # CTAs of the in-switch kernel (512 threads each; 0 = the library's default of two per SM).  The reduction is bound by
     # the links, not by the SMs, and when it overlaps the chunked per-Gaussian backward every CTA it holds is taken from
     # that kernel: tools/exp_scale8.py sweeps this at 8 GPUs.
@@ -415,6 +416,29 @@ def cuda_views_geom_backward(gaussians: dict, states: Sequence[ViewState], arena
                                   flags=flags | (_C.FLAG_ACCUMULATE if accumulate else 0), want_means2D=want_means2D)
 
 
+def chunk_ranges(P: int, chunks: int, taper: bool = False) -> list[tuple[int, int]]:
+    """Gaussian ranges [g0, g1) of the pipelined backward + exchange, boundaries on multiples of 32.  `taper`: the first
+    and the last range are half as long as the others (weights 1/2, 1, ..., 1, 1/2).  The exchange is the longer stage
+    of the pipeline (the links, not the SMs), so what stays exposed is the wait for the FIRST chunk's backward before
+    any reduction can start plus whatever the reductions lag behind at the end: a short first chunk starts the links
+    earlier, a short last one shortens the tail nobody overlaps."""
+    if chunks <= 1 or P <= 0:
+        return [(0, P)] if P > 0 else []
+    if not taper or chunks < 3:
+        step = ((P + chunks - 1) // chunks + 31) // 32 * 32
+        return [(g0, min(P, g0 + step)) for g0 in range(0, P, step)]
+    unit = P / (chunks - 1)                       # weights sum to chunks - 1
+    edges, acc = [0], 0.0
+    for k in range(chunks):
+        acc += unit * (0.5 if k in (0, chunks - 1) else 1.0)
+        e = P if k == chunks - 1 else min(P, (int(acc) + 31) // 32 * 32)
+        if e > edges[-1]:
+            edges.append(e)
+    if edges[-1] != P:
+        edges.append(P)
+    return list(zip(edges[:-1], edges[1:]))
+
+
 def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewState], arena: GradArena, flags: int | None = None,
                                        chunks: int = 4):
     """Batched K8+K9 + gradient all-reduce of a multi-rank step, pipelined over Gaussian-range chunks: while the
@@ -441,9 +465,7 @@ def cuda_views_geom_backward_allreduce(gaussians: dict, states: Sequence[ViewSta
     for st in states:
         for t in (st.radii, st.geom, st.scratch):
             t.record_stream(main)
-    step = ((P + chunks - 1) // chunks + 31) // 32 * 32
-    for g0 in range(0, P, step):
-        g1 = min(P, g0 + step)
+    for g0, g1 in chunk_ranges(P, chunks, getattr(arena, "taper", False)):
         if states:
             _C.backward_geom_multi(gaussians["means3D"], gaussians["shs"], gaussians["scales"], gaussians["rotations"],
                                    rs.scale_modifier, rs.sh_degree, views, arena.views,

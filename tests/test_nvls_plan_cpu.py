@@ -26,22 +26,33 @@ def _fake_symmetric(arena, world=8, rank=3):
     return calls
 
 
-def _chunks(P, chunks):
+def _chunks(P, chunks, taper=False):
     """the Gaussian ranges cuda_views_geom_backward_allreduce walks (multiview.py)"""
-    step = ((P + chunks - 1) // chunks + 31) // 32 * 32
-    return [(g0, min(P, g0 + step)) for g0 in range(0, P, step)]
+    return mv.chunk_ranges(P, chunks, taper)
 
 
+def test_chunk_ranges_tapered():
+    for P, c in ((3_000_000, 5), (4097, 5), (100003, 6), (64, 5), (33, 4), (1, 5)):
+        r = mv.chunk_ranges(P, c, taper=True)
+        assert r[0][0] == 0 and r[-1][1] == P and all(a[1] == b[0] and a[0] < a[1] for a, b in zip(r, r[1:] + [(P, P + 1)]))
+        assert all(g0 % 32 == 0 for g0, _ in r)
+    r = mv.chunk_ranges(3_000_000, 5, taper=True)
+    lens = [b - a for a, b in r]
+    assert len(r) == 5 and abs(lens[0] - 375_000) <= 32 and abs(lens[1] - 750_000) <= 32 and abs(lens[-1] - 375_000) <= 64
+    assert mv.chunk_ranges(3_000_000, 4) == [(k * 750_016, min(3_000_000, (k + 1) * 750_016)) for k in range(4)]
+
+
+@pytest.mark.parametrize("taper", [False, True])
 @pytest.mark.parametrize("P,M,chunks", [(4096, 16, 8), (4097, 16, 8), (100003, 4, 8), (5000, 1, 4), (33, 16, 2),
                                         (3_000_000, 16, 8), (1_000_001, 4, 5)])
-def test_range_plans_tile_the_arena(monkeypatch, P, M, chunks):
+def test_range_plans_tile_the_arena(monkeypatch, P, M, chunks, taper):
     arena = mv.GradArena(P, M, "cpu")
     calls = _fake_symmetric(arena)
     plans = []
     monkeypatch.setattr(_C, "nvls_all_reduce_plan",
                         lambda mc, dev, rank, world, dense=(), rows=None, add_s32=(0, 0), max_s32=(0, 0), blocks=0:
                         plans.append(dict(mc=mc, rank=rank, world=world, dense=list(dense), rows=rows, add=add_s32, mx=max_s32)))
-    ranges = _chunks(P, chunks)
+    ranges = _chunks(P, chunks, taper)
     assert ranges[0][0] == 0 and ranges[-1][1] == P and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
     for g0, g1 in ranges:
         arena.all_reduce_range(g0, g1, post_barrier=False)
