@@ -401,7 +401,9 @@ int gsr_version(void);
  * tile sort + tile ranges read off the sorted keys, 1 per-instance tile_count atomics (the previous scheme, identical results), 0 nothing
  * (results are then WRONG: timing experiments only); knob 2: resident CTAs per SM K1 is compiled for (4 / 5 / 6);
  * knob 3: reduction of the blend backward's nine sums: 1 (default) tensor-core contraction (mma.sync m16n8k8 tf32, hi + lo
- * split), 0 the round-1 shuffle butterfly -- same sums up to fp32 rounding, kept for A/B timing and the cross-check test. */
+ * split), 0 the round-1 shuffle butterfly -- same sums up to fp32 rounding, kept for A/B timing and the cross-check test;
+ * knob 5: 1 (default) gsr_gather_rows moves its wide rows (SH segments) by cp.async.bulk, 0 by thread loads / stores only
+ * (bit-identical: pure data movement). */
 int gsr_debug_set(int knob, int value);
 
 #ifdef __cplusplus

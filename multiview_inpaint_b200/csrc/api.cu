@@ -242,6 +242,7 @@ int gsr_debug_set(int knob, int value) {
     case 1: if (value < 0 || value > 2) return fail(GSR_E_INVALID, "gsr_debug_set: count mode 0..2"); g_bin_count_mode = value; return 0;
     case 2: g_pre_min_blocks = value; return 0;
     case 3: g_bwd_mma = value != 0; return 0;
+    case 5: g_gather_bulk = value != 0; return 0;
     default: return fail(GSR_E_INVALID, "gsr_debug_set: unknown knob");
   }
 }

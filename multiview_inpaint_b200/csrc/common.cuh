@@ -127,6 +127,7 @@ BinningLayout binning_layout(int64_t N, int W, int H, uint32_t flags);
 extern int g_rs_rank_mode;         // scan_sort.cu: 0 match_any, 1 ballots, 2 shared atomicOr (default)
 extern int g_pre_min_blocks;       // preprocess.cu: resident CTAs per SM K1 is compiled for (4, 5 or 6 = default)
 extern bool g_bwd_mma;             // blend_backward.cu: true (default) = tensor-core contraction of the nine sums, false = shuffle butterfly
+extern int g_gather_bulk;          // densify.cu: 1 (default) wide rows of gsr_gather_rows move by cp.async.bulk, 0 thread path only
 extern int g_bin_count_mode;       // binning.cu: 2 (default) per-CTA digit histograms + ranges off the sorted keys, 1 per-instance tile_count
                                    // atomics + tile_prepare (the previous scheme), 0 nothing (WRONG results: timing only)
 

@@ -18,6 +18,16 @@
 // loads are contiguous per source row (src_row is monotone inside each of the three blocks kept / clones / children,
 // so neighbouring rows mostly share sectors).  Rows whose length is a multiple of 4 floats (SH rows of M = 4 / 16,
 // rotations) move as float4.  Pure data movement: bit-exact.
+//
+// Bulk (TMA) copies for the wide rows.  The SH segments -- 192-byte rows at M = 16, 81 % of the bytes -- need no thread to
+// touch the data: thread r of the CTA issues ONE `cp.async.bulk` global -> shared for source row src_row[row0 + r] (16-byte
+// aligned, a multiple of 16 bytes), all 64 complete on one mbarrier (expect_tx = the bytes of the rows that copy), rows that
+// start from zero state are filled by plain stores + `fence.proxy.async`, and ONE thread sends the CTA's 64 destination rows
+// (contiguous: 12 KB) back with a single `cp.async.bulk` shared -> global.  The gather itself has no tile a tensor map could
+// describe (rows are picked by index), so the 1-D form is the one that applies; it replaces 768 LDG.128 + 768 STG.128 and
+// their address arithmetic per tile and segment by 64 + 1 copy instructions.  Segments whose rows are narrower than 48 bytes
+// or not a multiple of 16 (xyz, opacity, scaling; rotations at 16 bytes would be 64 sixteen-byte TMA operations) keep the
+// thread path.  gsr_debug_set knob 5 = 0 turns the bulk path off (A/B timing, cross-check in tests/test_densify_gpu.py).
 #include "common.cuh"
 
 namespace gsr {
@@ -25,18 +35,52 @@ namespace gsr {
 namespace {
 
 constexpr int GATHER_ROWS = 64;
+constexpr int GATHER_TMA_MAX_ROW_BYTES = 192;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct GatherArgs {
   const float* src[GSR_GATHER_MAX_SEGS];
   float* dst[GSR_GATHER_MAX_SEGS];
   int row_f32[GSR_GATHER_MAX_SEGS];
   int zero_new[GSR_GATHER_MAX_SEGS];
+  int bulk[GSR_GATHER_MAX_SEGS];   // rows of this segment move by cp.async.bulk (launch_gather_rows decides)
   int n_segs;
 };
 
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(GatherArgs a, long long n_dst, long long n_keep_state, const int* __restrict__ src_row) {
   __shared__ int s_src[GATHER_ROWS];
+  __shared__ __align__(128) unsigned char s_rows[GATHER_ROWS * GATHER_TMA_MAX_ROW_BYTES];   // bulk path: the CTA's 64 rows of one segment
+  __shared__ __align__(8) unsigned long long s_bar;
+  const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(s_rows), bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+  uint32_t parity = 0;
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
   const long long n_tiles = (n_dst + GATHER_ROWS - 1) / GATHER_ROWS;
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long row0 = tile * GATHER_ROWS;
@@ -51,6 +95,26 @@ gather_rows_kernel(GatherArgs a, long long n_dst, long long n_keep_state, const 
       const float* __restrict__ src = a.src[s];
       float* __restrict__ dst = a.dst[s];
       const int live = a.zero_new[s] ? keep : rows;   // rows below `live` copy, the rest are zero-filled
+      if (a.bulk[s]) {
+        const uint32_t row_b = (uint32_t)L * 4;
+        if (threadIdx.x == 0) {
+          bulk_wait_read();                         // the previous bulk store has finished reading s_rows
+          mbar_arrive_expect_tx(bar, (uint32_t)live * row_b);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < live)
+          bulk_load(rows_s + threadIdx.x * row_b, reinterpret_cast<const char*>(src) + (size_t)s_src[threadIdx.x] * row_b, row_b, bar);
+        // rows that start from zero state: 16-byte stores through the generic proxy
+        const int nz4 = (rows - live) * (L >> 2);
+        for (int e = threadIdx.x; e < nz4; e += blockDim.x)
+          reinterpret_cast<float4*>(s_rows + (size_t)live * row_b)[e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        fence_proxy_async_smem();                   // the zero rows, before the async proxy reads them
+        __syncthreads();
+        if (threadIdx.x == 0) bulk_store(reinterpret_cast<char*>(dst) + (size_t)row0 * row_b, rows_s, (uint32_t)rows * row_b);
+        continue;
+      }
       if ((L & 3) == 0) {
         const int Lv = L >> 2;
         const float4* __restrict__ src4 = reinterpret_cast<const float4*>(src);
@@ -74,9 +138,12 @@ gather_rows_kernel(GatherArgs a, long long n_dst, long long n_keep_state, const 
       }
     }
   }
+  if (threadIdx.x == 0) bulk_wait_all();
 }
 
 }  // namespace
+
+int g_gather_bulk = 1;   // gsr_debug_set knob 5
 
 cudaError_t launch_gather_rows(cudaStream_t stream, long long n_dst, long long n_keep_state, const int* src_row,
                                const gsr_gather_segment* segs, int n_segs) {
@@ -87,9 +154,12 @@ cudaError_t launch_gather_rows(cudaStream_t stream, long long n_dst, long long n
     a.dst[s] = segs[s].dst;
     a.row_f32[s] = segs[s].row_f32;
     a.zero_new[s] = segs[s].zero_new;
+    const size_t row_b = (size_t)segs[s].row_f32 * 4;
+    a.bulk[s] = g_gather_bulk && row_b >= 48 && row_b <= GATHER_TMA_MAX_ROW_BYTES && (row_b & 15) == 0 &&
+                ((reinterpret_cast<uintptr_t>(segs[s].src) | reinterpret_cast<uintptr_t>(segs[s].dst)) & 15) == 0;
   }
   for (int s = n_segs; s < GSR_GATHER_MAX_SEGS; s++) {
-    a.src[s] = nullptr; a.dst[s] = nullptr; a.row_f32[s] = 0; a.zero_new[s] = 0;
+    a.src[s] = nullptr; a.dst[s] = nullptr; a.row_f32[s] = 0; a.zero_new[s] = 0; a.bulk[s] = 0;
   }
   const long long n_tiles = (n_dst + GATHER_ROWS - 1) / GATHER_ROWS;
   const int grid = (int)min(n_tiles, (long long)148 * 8);   // 8 resident CTAs of 256 threads per SM, grid-stride beyond

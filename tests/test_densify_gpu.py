@@ -155,7 +155,18 @@ def test_reset_opacity_equals_reference(gold, case):
 # ------------------------------------------------------------------------------------------------ the gather kernel
 @pytest.mark.parametrize("n_src,n_dst", [(1, 1), (5, 63), (200, 64), (77, 65), (1000, 4097), (4096, 129), (100003, 250001)])
 @pytest.mark.parametrize("M", [1, 4, 16])
-def test_gather_rows_equals_torch_indexing(C, n_src, n_dst, M):
+@pytest.mark.parametrize("bulk", [1, 0])
+def test_gather_rows_equals_torch_indexing(C, n_src, n_dst, M, bulk):
+    """bulk = 1 (default): the SH segments (48- / 192-byte rows at M = 4 / 16) move by cp.async.bulk -- 64 row loads on one
+    mbarrier, one 12 KB store per tile; bulk = 0: every segment through thread loads / stores.  Same bits either way."""
+    C.debug_set(5, bulk)
+    try:
+        _gather_rows_case(C, n_src, n_dst, M)
+    finally:
+        C.debug_set(5, 1)
+
+
+def _gather_rows_case(C, n_src, n_dst, M):
     g = torch.Generator(device=DEV).manual_seed(n_src * 31 + n_dst + M)
     widths = (3, 3 * M, 1, 3, 4)
     src = [torch.randn(n_src, w, device=DEV, generator=g) for w in widths]
@@ -219,13 +230,15 @@ def test_full_size_repack_checksum(C):
         segs.append(dict(src=getattr(pa, name), dst=getattr(new, name)))
         for a, b in zip(pa.moments(name), new.moments(name)):
             segs.append(dict(src=a, dst=b, zero_new=True))
-    e0.record()
-    C.gather_rows(plan.src_row, P, segs, n_keep_state=plan.n_keep_state)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
     gb = plan.n_dst * (4 + 2 * 3 * 59 * 4) / 1e9
-    print(f"gather_rows: {plan.n_dst} rows x 59 floats x 3 arenas in {ms:.3f} ms = {gb / ms * 1e3:.0f} GB/s")
+    for bulk in (0, 1, 0, 1):      # thread path, bulk (TMA) path -- twice: the first of each pays the cold caches
+        C.debug_set(5, bulk)
+        e0.record()
+        C.gather_rows(plan.src_row, P, segs, n_keep_state=plan.n_keep_state)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(f"gather_rows (bulk={bulk}): {plan.n_dst} rows x 59 floats x 3 arenas in {ms:.3f} ms = {gb / ms * 1e3:.0f} GB/s")
     for k in before:
         assert torch.equal(row_sum(new, getattr(new, k)), before[k][~mask]), k
     assert ms < 5.0
