@@ -704,6 +704,9 @@ def run_ours(args):
             # multiview.chunk_ranges) start the links earlier and shorten the reduction tail nobody overlaps
             cands += [("nvls", 4, 148, False), ("nvls", 4, 74, False), ("nvls", 8, 74, False), ("nvls", 4, 0, False),
                       ("nvls", 5, 74, True), ("nvls", 6, 74, True)]
+            if world == 2 and arena._peer_ptr():
+                # two ranks: peer loads / stores over NVLink move the same bytes at the link rate (csrc/nvls_allreduce.cu)
+                cands += [("p2p", 4, 148, False), ("p2p", 4, 74, False), ("p2p", 6, 148, True), ("p2p", 1, 0, False)]
         trials = []
         for m_, c_, b_, tp_ in cands:
             arena.method, arena.nvls_blocks, args.ar_chunks, arena.taper = m_, b_, c_, tp_

@@ -244,6 +244,11 @@ typedef struct {
   size_t max_s32_off, n_max_s32;
 } gsr_nvls_plan;
 int gsr_nvls_all_reduce_plan(void* stream, void* multicast_ptr, const gsr_nvls_plan* plan, int rank, int world, int blocks);
+/* The same plan between exactly TWO ranks without the switch: rank r (0 or 1) owns half of every segment, loads the peer's
+ * elements over NVLink (`peer_ptr`: the peer's replica of the arena as mapped into this process, e.g. symmetric memory's
+ * buffer_ptrs[1 - r] + offset; `local_ptr`: this rank's replica), adds its own and stores the sum into both.  Same barriers
+ * around the launch as gsr_nvls_all_reduce_plan.  At two GPUs multimem moves the same bytes over the links at a lower rate. */
+int gsr_p2p_all_reduce_plan(void* stream, void* local_ptr, void* peer_ptr, const gsr_nvls_plan* plan, int rank, int blocks);
 
 /* Densification statistics of one view, fused (the reference does this in torch after backward():
  * gs-simp/scene/gaussian_model.py:482-484 `xyz_gradient_accum[vis] += norm(viewspace.grad[vis, :2])`,

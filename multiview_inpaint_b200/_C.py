@@ -113,6 +113,8 @@ class GsrNvlsPlan(C.Structure):
 
 _lib.gsr_nvls_all_reduce_plan.restype = _i
 _lib.gsr_nvls_all_reduce_plan.argtypes = [_vp, _vp, C.POINTER(GsrNvlsPlan), _i, _i, _i]
+_lib.gsr_p2p_all_reduce_plan.restype = _i
+_lib.gsr_p2p_all_reduce_plan.argtypes = [_vp, _vp, _vp, C.POINTER(GsrNvlsPlan), _i, _i]
 _lib.gsr_nvls_all_reduce.restype = _i
 _lib.gsr_nvls_all_reduce.argtypes = [_vp, _vp, _sz, _sz, _sz, _sz, _sz, _sz, _i, _i, _i, _sz, _sz, _i]
 _lib.gsr_accumulate_view_stats.restype = _i
@@ -173,7 +175,7 @@ _lib.gsr_gather_rows.argtypes = [_vp, _i64, _i64, _i64, _vp, C.POINTER(GsrGather
 EXPORTED_SYMBOLS = ("gsr_forward", "gsr_backward", "gsr_backward_scratch_bytes", "gsr_mark_visible",
                     "gsr_accumulate_view_stats", "gsr_loss_temp_bytes", "gsr_loss_l1_ssim_forward",
                     "gsr_loss_l1_ssim_backward", "gsr_activate_forward", "gsr_activate_backward", "gsr_adam_step", "gsr_quantize_rgb8", "gsr_gather_rows",
-                    "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_forward_views", "gsr_backward_blend_views", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan",
+                    "gsr_knn_temp_bytes", "gsr_knn3_mean_dist2", "gsr_forward_views", "gsr_backward_blend_views", "gsr_backward_blend", "gsr_backward_geom_multi", "gsr_backward_geom_multi_range", "gsr_nvls_all_reduce", "gsr_nvls_all_reduce_plan", "gsr_p2p_all_reduce_plan",
                     "gsr_sort_temp_bytes", "gsr_sort_pairs_u64", "gsr_sort_pairs_u32",
                     "gsr_scan_temp_bytes", "gsr_inclusive_scan_u32", "gsr_get_layout",
                     "gsr_profile_enable", "gsr_profile_collect", "gsr_kernel_launches", "gsr_debug_approx_units",
@@ -616,6 +618,22 @@ def nvls_all_reduce_plan(multicast_ptr: int, device, rank: int, world: int, dens
     pl.max_s32_off, pl.n_max_s32 = int(max_s32[0]), int(max_s32[1])
     with torch.cuda.device(device):
         _check(_lib.gsr_nvls_all_reduce_plan(_stream(device), multicast_ptr, C.byref(pl), rank, world, blocks), "nvls_all_reduce_plan")
+
+
+def p2p_all_reduce_plan(local_ptr: int, peer_ptr: int, device, rank: int, dense=(), rows=None, add_s32=(0, 0), max_s32=(0, 0),
+                        blocks: int = 0):
+    """gsr_p2p_all_reduce_plan on the current stream: the plan of nvls_all_reduce_plan between exactly two ranks, by peer
+    loads / stores over NVLink (local_ptr / peer_ptr: this rank's and the peer's replica of the arena)."""
+    pl = GsrNvlsPlan()
+    pl.n_dense = len(dense)
+    for k, (off, n) in enumerate(dense):
+        pl.dense_off[k], pl.dense_n_f32[k] = int(off), int(n)
+    if rows is not None:
+        pl.rows_off, pl.rows, pl.row_f32, pl.rows_count_off = int(rows[0]), int(rows[1]), int(rows[2]), int(rows[3])
+    pl.add_s32_off, pl.n_add_s32 = int(add_s32[0]), int(add_s32[1])
+    pl.max_s32_off, pl.n_max_s32 = int(max_s32[0]), int(max_s32[1])
+    with torch.cuda.device(device):
+        _check(_lib.gsr_p2p_all_reduce_plan(_stream(device), int(local_ptr), int(peer_ptr), C.byref(pl), rank, blocks), "p2p_all_reduce_plan")
 
 
 def accumulate_view_stats(radii, dL_dmeans2D, grad_norm_accum=None, visible_count=None, max_radii=None):

@@ -1091,6 +1091,20 @@ int gsr_nvls_all_reduce_plan(void* stream, void* multicast_ptr, const gsr_nvls_p
   return 0;
 }
 
+int gsr_p2p_all_reduce_plan(void* stream, void* local_ptr, void* peer_ptr, const gsr_nvls_plan* plan, int rank, int blocks) {
+  if (!local_ptr || !peer_ptr || local_ptr == peer_ptr || !plan || rank < 0 || rank > 1 ||
+      ((reinterpret_cast<uintptr_t>(local_ptr) | reinterpret_cast<uintptr_t>(peer_ptr)) & 15) ||
+      plan->n_dense < 0 || plan->n_dense > 6 || (plan->rows_off & 15) || (plan->rows_count_off & 3) ||
+      (plan->add_s32_off & 3) || (plan->max_s32_off & 3) || plan->row_f32 < 0)
+    return fail(GSR_E_INVALID, "gsr_p2p_all_reduce_plan: bad argument (alignment / rank / pointers)");
+  for (int d = 0; d < plan->n_dense; d++)
+    if ((plan->dense_off[d] & 15) || (plan->dense_n_f32[d] & 3))
+      return fail(GSR_E_INVALID, "gsr_p2p_all_reduce_plan: dense segments must be 16-byte aligned multiples of 4 floats");
+  GSR_CUDA(launch_p2p_allreduce_plan(reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<char*>(local_ptr),
+                                     reinterpret_cast<char*>(peer_ptr), *plan, rank, blocks), "p2p all-reduce (plan)");
+  return 0;
+}
+
 int gsr_accumulate_view_stats(void* stream, int P, const int32_t* radii, const float* dL_dmean2D,
                               float* grad_norm_accum, int32_t* visible_count, int32_t* max_radii) {
   if (P < 0 || (P > 0 && (!radii || (grad_norm_accum && !dL_dmean2D))))

@@ -319,6 +319,7 @@ cudaError_t launch_nvls_allreduce(cudaStream_t s, char* mc, size_t off_f32, size
                                   size_t n_add_s32, size_t off_max_s32, size_t n_max_s32, int rank, int world,
                                   int blocks, size_t sparse_first_f32, size_t sparse_rows, int sparse_row_f32);
 cudaError_t launch_nvls_allreduce_plan(cudaStream_t s, char* mc, const gsr_nvls_plan& plan, int rank, int world, int blocks);
+cudaError_t launch_p2p_allreduce_plan(cudaStream_t s, char* local, char* peer, const gsr_nvls_plan& in, int rank, int blocks);
 size_t knn_temp_bytes(int P);
 cudaError_t launch_knn3_mean_dist2(cudaStream_t s, int P, const float* points, float* mean_dist2, char* temp);
 cudaError_t launch_view_stats(cudaStream_t s, int P, const int32_t* radii, const float* dL_dmean2D,

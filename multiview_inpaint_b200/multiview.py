@@ -86,7 +86,19 @@ class GradArena:
 
     @property
     def uses_nvls(self) -> bool:
-        return self._mc != 0 and self.method == "nvls"
+        """the exchange is one of this repository's kernels over symmetric memory (in-switch, or peer-to-peer at two ranks)
+        -- the ones that can be issued per Gaussian range and pipelined with the backward"""
+        return self._mc != 0 and (self.method == "nvls" or (self.method == "p2p" and self._peer_ptr() != 0))
+
+    def _peer_ptr(self) -> int:
+        """the peer's replica of this arena as mapped here (two ranks only), 0 when unavailable"""
+        h = self._handle
+        if h is None or h.world_size != 2:
+            return 0
+        try:
+            return int(h.buffer_ptrs[1 - h.rank]) + int(getattr(h, "offset", 0) or 0)
+        except Exception:
+            return 0
 
     method = "nvls"   # preferred collective when a multicast mapping exists; see calibrate()
     taper = False     # chunk_ranges(): half-length first and last range of the pipelined exchange
@@ -141,6 +153,9 @@ class GradArena:
         group = group if group is not None else self.group
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
+        if self._mc and self.method == "p2p" and self._peer_ptr():
+            self.all_reduce_range(0, self.P)      # the plan form covers the whole arena; barriers inside
+            return
         if self._mc and self.method == "nvls":
             from . import _C
             h = self._handle
@@ -173,9 +188,14 @@ class GradArena:
                 dense.append((4 * (first + g0 * w), r4((g1 - g0) * w)))
         dense.append((4 * (self._n_flat + g0), r4(g1 - g0)))                      # grad_norm_accum
         h.barrier()
-        _C.nvls_all_reduce_plan(self._mc, self.storage.device, h.rank, h.world_size, dense=dense, rows=rows,
-                                add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0),
-                                blocks=self.nvls_blocks)
+        if self.method == "p2p":
+            _C.p2p_all_reduce_plan(self.storage.data_ptr(), self._peer_ptr(), self.storage.device, h.rank, dense=dense, rows=rows,
+                                   add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0),
+                                   blocks=self.nvls_blocks)
+        else:
+            _C.nvls_all_reduce_plan(self._mc, self.storage.device, h.rank, h.world_size, dense=dense, rows=rows,
+                                    add_s32=(self._off_cnt + 4 * g0, g1 - g0), max_s32=(self._off_max + 4 * g0, g1 - g0),
+                                    blocks=self.nvls_blocks)
         if post_barrier:
             h.barrier()
 

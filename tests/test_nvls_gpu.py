@@ -53,7 +53,28 @@ def _worker(rank, world, port, out_dir):
             chunk_ok = bool((c.flat - b.flat).abs().max() <= 1e-5 * b.flat.abs().max()
                             and (c.grad_norm_accum - b.grad_norm_accum).abs().max() <= 1e-5
                             and torch.equal(c.visible_count, b.visible_count) and torch.equal(c.max_radii, b.max_radii))
-        res[M] = dict(nvls=a.uses_nvls, chunks=chunk_ok, err=float((a.flat - b.flat).abs().max()), scale=float(b.flat.abs().max()),
+        # two ranks: the peer-to-peer two-shot kernel, whole arena and in Gaussian ranges
+        p2p_ok = True
+        if world == 2 and a._peer_ptr():
+            for ranges in ([(0, P)], [(g0, min(P, g0 + 23456)) for g0 in range(0, P, 23456)]):
+                d = mv.GradArena(P, M, dev, symmetric=True)
+                d.method = "p2p"
+                g.manual_seed(5 + rank)
+                d.flat.copy_(torch.randn(d.flat.shape, device=dev, generator=g))
+                d.grad_norm_accum.copy_(torch.rand(P, device=dev, generator=g))
+                d.visible_count.copy_(torch.randint(0, 3, (P,), device=dev, generator=g, dtype=torch.int32))
+                d.max_radii.copy_(torch.randint(0, 900, (P,), device=dev, generator=g, dtype=torch.int32))
+                d.views["dL_dsh"][d.visible_count == 0] = 0
+                assert d.uses_nvls
+                if len(ranges) == 1:
+                    d.all_reduce()
+                else:
+                    for g0, g1 in ranges:
+                        d.all_reduce_range(g0, g1)
+                torch.cuda.synchronize()
+                p2p_ok = p2p_ok and bool(torch.equal(d.flat, b.flat) and torch.equal(d.grad_norm_accum, b.grad_norm_accum)
+                                         and torch.equal(d.visible_count, b.visible_count) and torch.equal(d.max_radii, b.max_radii))
+        res[M] = dict(nvls=a.uses_nvls, chunks=chunk_ok, p2p=p2p_ok, err=float((a.flat - b.flat).abs().max()), scale=float(b.flat.abs().max()),
                       norm=float((a.grad_norm_accum - b.grad_norm_accum).abs().max()),
                       ints=bool(torch.equal(a.visible_count, b.visible_count) and torch.equal(a.max_radii, b.max_radii)))
     torch.save(res, os.path.join(out_dir, f"r{rank}.pt"))
@@ -72,4 +93,4 @@ def test_nvls_arena_all_reduce_matches_nccl(tmp_path):
         for M, d in res.items():
             if not d["nvls"]:
                 pytest.skip("no multicast mapping on this system")
-            assert d["err"] <= 1e-5 * d["scale"] and d["norm"] <= 1e-5 and d["ints"] and d["chunks"], (M, d)
+            assert d["err"] <= 1e-5 * d["scale"] and d["norm"] <= 1e-5 and d["ints"] and d["chunks"] and d["p2p"], (M, d)
