@@ -154,3 +154,20 @@ def test_ctypes_argument_counts_match_the_header(built):
             assert is_ptr_c == is_ptr_py, f"{name}: parameter {k} `{p}` vs {t}"
         checked += 1
     assert checked >= 25
+
+
+def test_flag_constants_match_the_header(built):
+    """`#define GSR_FLAG_* <n>u` of include/gsrast_b200.h against the FLAG_* constants of multiview_inpaint_b200/_C.py, and the
+    default of the Python layers: tight binning unless GSR_FLAGS says otherwise (flags = 0 keeps the reference's literal lists)."""
+    import os
+    import re
+    from multiview_inpaint_b200 import _C
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gsrast_b200.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+GSR_FLAG_(\w+)\s+(\d+)u", hdr)}
+    assert set(defs) == {"BINNING_KEY64", "PRECISE", "REFERENCE", "ACCUMULATE", "ASYNC", "TIGHT_BINNING", "SCRATCH_CLEARED"}
+    assert len(set(defs.values())) == len(defs) and all(v & (v - 1) == 0 for v in defs.values())      # distinct single bits
+    for name, v in defs.items():
+        assert getattr(_C, "FLAG_" + name) == v, name
+    if "GSR_FLAGS" not in os.environ:
+        assert _C.DEFAULT_FLAGS == _C.FLAG_TIGHT_BINNING
+    assert _C.resolve_flags(None) == _C.DEFAULT_FLAGS and _C.resolve_flags(0) == 0 and _C.resolve_flags(3) == 3
