@@ -122,3 +122,25 @@ def test_range_requires_alignment_and_nvls():
         arena.all_reduce_range(2, 100)                              # g0 must be a multiple of 4
     with pytest.raises(AssertionError):
         arena.all_reduce_range(0, 1001)
+
+
+def test_two_rank_partition_covers_every_element_once():
+    """the split of csrc/nvls_allreduce.cu::p2p_allreduce2_kernel (rank r owns [min(n, per r), min(n, per r + per)) with
+    per = ceil(n / 2) of every dense range, of the row groups and of the two integer ranges), restated: the two ranks'
+    shares are disjoint and together cover everything, for odd and tiny sizes too"""
+    def share(n, rank):
+        per = (n + 1) // 2
+        lo = min(n, per * rank)
+        return lo, min(n, lo + per)
+    for n in (0, 1, 2, 3, 4, 5, 95, 96, 97, 4001, 70001, 3_000_000):
+        a, b = share(n, 0), share(n, 1)
+        assert a[0] == 0 and a[1] == b[0] and b[1] == n, (n, a, b)
+    for rows, row_f4 in ((4001, 3), (70001, 12), (5, 12), (0, 3), (33, 3)):
+        G = 96 // row_f4
+        groups = (rows + G - 1) // G
+        (g0, g1), (h0, h1) = share(groups, 0), share(groups, 1)
+        covered = np.zeros(rows, np.int16)
+        for lo, hi in ((g0, g1), (h0, h1)):
+            for g in range(lo, hi):
+                covered[g * G:min(rows, (g + 1) * G)] += 1
+        assert (covered == 1).all(), (rows, row_f4)
