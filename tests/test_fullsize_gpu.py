@@ -97,3 +97,39 @@ def test_inference_shape_partial_tiles_1080p():
     assert torch.isfinite(color).all() and (depth > 0.2).all() and (depth <= 15.0).all()
     st = _state(out, sc, 0)
     assert st["ranges"].shape[0] == 120 * 68 and int((st["ranges"][:, 1] - st["ranges"][:, 0]).sum()) == n
+
+
+def test_mip360_against_the_oracle_on_every_16th_tile(mip360, oracle):
+    """The full configs[1] view against the C oracle: K1, the binning and both sorts over all 1 M Gaussians (radii,
+    num_rendered, the sorted point list and the tile ranges bit-exact, with the reference's literal lists: flags = 0), and
+    the blend on every 16th tile (the oracle's blend is what takes minutes at this size; `tile_step` bounds it) inside
+    the bars of tests/test_parity_gpu.py.  The default tight lists must give the same image bit for bit."""
+    from tests.util import oracle_forward  # noqa: F401  (same input plumbing as the small-scene parity tests)
+    sc = mip360
+    cam = sc["camera"]
+    kw = dict(means3D=sc["means3D"].numpy(), opacities=sc["opacities"].numpy(), viewmatrix=cam.world_view_transform.numpy(),
+              projmatrix=cam.full_proj_transform.numpy(), campos=cam.camera_center.contiguous().numpy(), W=cam.image_width,
+              H=cam.image_height, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, sh_degree=sc["sh_degree"], shs=sc["shs"].numpy(),
+              scales=sc["scales"].numpy(), rotations=sc["rotations"].numpy())
+    f = oracle.bin_and_sort(oracle.preprocess(**kw))
+    step = 16
+    oracle.blend(f, sc["bg"].numpy(), tile_start=0, tile_step=step)
+    out, d, camd, bg = cuda_forward(sc, flags=0)
+    n, color, radii, geom, binning, img, depth = out
+    st = _state(out, sc, 0)
+    assert n == f.num_rendered
+    np.testing.assert_array_equal(radii.cpu().numpy(), f.radii)
+    np.testing.assert_array_equal(st["point_list"].cpu().numpy().view(np.uint32), f.point_list)
+    np.testing.assert_array_equal(st["ranges"].cpu().numpy().view(np.uint32), f.ranges)
+    W, H = sc["W"], sc["H"]
+    gx = (W + 15) // 16
+    mask = np.zeros((H, W), bool)
+    for t in range(0, gx * ((H + 15) // 16), step):
+        mask[(t // gx) * 16:(t // gx) * 16 + 16, (t % gx) * 16:(t % gx) * 16 + 16] = True
+    c_err = np.abs(color.cpu().numpy() - f.color).max(0)[mask]
+    d_err = np.abs(depth.cpu().numpy()[0] - f.depth[0])[mask]
+    max_out = max(2, int(1e-4 * mask.sum()))
+    assert (c_err > 1e-5).sum() <= max_out and c_err.max() < 5e-3, (int((c_err > 1e-5).sum()), float(c_err.max()))
+    assert (d_err > 1e-5).sum() <= max_out
+    tight, *_ = cuda_forward(sc, flags=32)
+    assert tight[0] < n and torch.equal(tight[1], color) and torch.equal(tight[6], depth) and torch.equal(tight[2], radii)
