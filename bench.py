@@ -132,7 +132,7 @@ def algorithmic_bytes(P, V, N, G, W, H, M, nv=1, clear_in_k1=False):
     return out
 
 
-def view_roofline(alg, N, W, H, ms_view, peak):
+def view_roofline(alg, N, W, H, ms_view, peak, survey=None):
     """Whole-view bandwidth position.  The blend kernels enter with their per-pixel I/O only: their list gathers (44 N and
     80 N in the stage models: every binned instance) are an upper bound -- the walk stops at saturation -- and are served
     by the L2 (profiles/traffic.json), so charging them to HBM put whole views of early-saturating shapes above the peak."""
@@ -143,7 +143,16 @@ def view_roofline(alg, N, W, H, ms_view, peak):
         b += 20 * W * H
     gather = (44 * N if "blend_forward" in alg else 0) + (80 * N if "blend_backward" in alg else 0)
     g = b / (ms_view / 1000.0) / 1e9
-    return {"alg_bytes": int(b), "blend_list_gather_upper_bound_bytes": int(gather), "ms": ms_view, "gbps": g, "frac": g / peak}
+    out = {"alg_bytes": int(b), "blend_list_gather_upper_bound_bytes": int(gather), "ms": ms_view, "gbps": g, "frac": g / peak}
+    if survey:
+        # SURVEY.md 8(d)'s B_view = B_fwd + B_bwd: what the REFERENCE's structure would move for this view (scan, six 64-bit
+        # sort passes, 44 N + 80 N of blend gathers), with N = the instances THIS run binned (tight binning: fewer than the
+        # reference's).  An equivalence figure -- bytes this design does not move -- kept because the survey's headline
+        # "% of HBM roofline" is defined on it; it can exceed 1.
+        sb = float(sum(v for v in survey.values() if v))
+        out["survey_8d"] = {"bytes": int(sb), "equivalent_gbps": sb / (ms_view / 1000.0) / 1e9,
+                            "equivalent_frac_of_hbm_peak": sb / (ms_view / 1000.0) / 1e9 / peak}
+    return out
 
 
 def issue_counters():
@@ -883,7 +892,7 @@ def run_ours(args):
                      "views_per_launch": views_per_launch[dom], "ms_per_launch": per_launch[dom],
                      "issue_active_frac": ctr.get("issue_active_frac"), "warp_inst_per_launch": ctr.get("warp_inst"),
                      "counters_from": ctr.get("source"),
-                     "view": view_roofline(alg, N, W, H, ms_view, peak)},
+                     "view": view_roofline(alg, N, W, H, ms_view, peak, survey=alg_survey)},
         "stages": stages,
         # SURVEY 8d timing protocol: forward, backward and forward+backward reported separately (stage-profiler pass,
         # one stream, per view)

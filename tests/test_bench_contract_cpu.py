@@ -92,3 +92,19 @@ def test_recorded_bench_line_has_the_contract_keys():
     assert not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     # value = views of the whole job / device time
     assert abs(line["value"] - line["config"]["views_per_step"] / (line["ms_per_step"] / 1000.0)) < 1e-6 * line["value"]
+
+
+def test_view_roofline_helper():
+    """the whole-view roofline object of the bench line: design bytes without the L2-served list gathers, and SURVEY 8(d)'s
+    reference-structure B_view beside it (pure arithmetic: checked here, the bench itself needs a GPU)"""
+    import bench
+    P, V, N, G, W, H, M = 3_000_000, 1_790_869, 5_733_709, 6300, 1600, 1008, 16
+    alg = bench.algorithmic_bytes(P, V, N, G, W, H, M, 4, clear_in_k1=True)
+    sv = bench.survey_bytes(P, V, N, G, W, H, M)
+    r = bench.view_roofline(alg, N, W, H, 1.386, 6537.6, survey=sv)
+    non_blend = sum(v for k, v in alg.items() if not k.startswith("blend"))
+    assert r["alg_bytes"] == int(non_blend + 44 * W * H) and r["blend_list_gather_upper_bound_bytes"] == 124 * N
+    assert 0.1 < r["frac"] < 0.2 and abs(r["gbps"] - r["alg_bytes"] / 1.386e-3 / 1e9) < 1e-6
+    s8 = r["survey_8d"]
+    assert s8["bytes"] == int(sum(sv.values())) and 0.3 < s8["equivalent_frac_of_hbm_peak"] < 0.8
+    assert "survey_8d" not in bench.view_roofline(alg, N, W, H, 1.386, 6537.6)
